@@ -1,0 +1,566 @@
+// C ABI of libafr_sm100.so (declared in include/afr_sm100.h): context, workspaces, and the
+// sequencing of the kernels that make up one training step / one batched render.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/afr_sm100.h"
+#include "afr_gemm.cuh"
+#include "afr_internal.h"
+
+using namespace afr;
+
+struct afr_ctx {
+  afr_config cfg{};
+  int num_sms = 0;
+  int K = 0;  // max_length * hidden : fc_output in_features
+  int P = 0;  // sheet_h * sheet_w   : fc_output out_features
+  SmallLayout lay{};
+  Tensors params{}, grads{}, m{}, v{};
+  bool has_params = false, has_grads = false, has_state = false, shadow_valid = false;
+  // private device buffers
+  __nv_bfloat16* feats = nullptr;    // [max_batch, K]
+  __nv_bfloat16* wshadow = nullptr;  // [P, K]
+  __nv_bfloat16* dz = nullptr;       // [max_batch, P]   unscaled (y - t) * mask
+  float* dfeat = nullptr;            // [max_batch, K]
+  float* logits = nullptr;           // [max_batch, P]   generic path, allocated on first use
+  float* loss_partials = nullptr;
+  int loss_partials_cap = 0;
+  float* bias_scratch = nullptr;     // [32, P]
+  float* partials = nullptr;         // [num_sms, lay.total]
+  // state carried from forward to backward
+  const long long* tokens = nullptr;
+  long long token_stride = 0;
+  int B = 0, S = 0;
+  Dropout drop{};
+  float grad_scale = 0.f;
+  bool fwd_done = false;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+std::string g_create_err;
+
+int fail(afr_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+int fail_cuda(afr_ctx* c, cudaError_t e, const char* where) {
+  return fail(c, AFR_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define AFR_CUDA(ctx, expr, where)                          \
+  do {                                                      \
+    cudaError_t e__ = (expr);                               \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, where); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+Tensors to_tensors(const afr_tensors* t) {
+  Tensors r{};
+  r.pos = t->positional_encoding; r.emb = t->embedding_weight;
+  r.win = t->in_proj_weight; r.bin = t->in_proj_bias;
+  r.wo = t->out_proj_weight; r.bo = t->out_proj_bias;
+  r.lnw = t->layer_norm_weight; r.lnb = t->layer_norm_bias;
+  r.w1 = t->fc1_weight; r.b1 = t->fc1_bias;
+  r.wout = t->fc_output_weight; r.bout = t->fc_output_bias;
+  return r;
+}
+bool all_set(const afr_tensors* t) {
+  const float* const* p = reinterpret_cast<const float* const*>(t);
+  for (int i = 0; i < 12; ++i) if (p[i] == nullptr) return false;
+  return true;
+}
+Dropout to_dropout(const afr_dropout* d) {
+  Dropout r{};
+  if (d == nullptr) return r;
+  r.mode = d->mode; r.seed = d->seed; r.step = d->step; r.sample_offset = d->sample_offset;
+  r.mask_embed = d->mask_embed; r.mask_attn = d->mask_attn; r.mask_fc1 = d->mask_fc1;
+  r.p_embed = d->p_embed; r.p_attn = d->p_attn; r.p_fc1 = d->p_fc1;
+  return r;
+}
+
+// Tile width: minimise waves * (128 + BN) -- per-tile cost is operand-feed bound (the A tile of
+// 128 rows plus the B tile of BN rows per k-block), waves = ceil(tiles / SMs).
+int env_int(const char* name) {
+  const char* s = std::getenv(name);
+  return s ? std::atoi(s) : 0;
+}
+int choose_bn(int M, int N, int num_sms, const char* env_name) {
+  const int forced = env_int(env_name);
+  if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
+  int best = 256;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 128; bn -= 32) {
+    const long long tiles = gemm_num_tiles(M, N, bn);
+    const long long waves = (tiles + num_sms - 1) / num_sms;
+    const long long cost = waves * (128 + bn);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  if (N < best) best = ((N + 31) / 32) * 32;
+  return best;
+}
+
+int ensure_loss_partials(afr_ctx* c, int n) {
+  if (n <= c->loss_partials_cap) return AFR_OK;
+  if (c->loss_partials) cudaFree(c->loss_partials);
+  c->loss_partials = nullptr;
+  AFR_CUDA(c, cudaMalloc(&c->loss_partials, sizeof(float) * n), "cudaMalloc(loss_partials)");
+  c->loss_partials_cap = n;
+  return AFR_OK;
+}
+
+int check_batch(afr_ctx* c, int B, int S, const void* tokens) {
+  if (!c->has_params) return fail(c, AFR_ERR_STATE, "parameters not bound (afr_bind_params)");
+  if (tokens == nullptr) return fail(c, AFR_ERR_INVALID, "tokens is NULL");
+  if (B < 1 || B > c->cfg.max_batch)
+    return fail(c, AFR_ERR_INVALID, "B outside [1, max_batch]");
+  if (S < 1 || S > c->cfg.max_length)
+    return fail(c, AFR_ERR_INVALID, "S outside [1, max_length]");
+  return AFR_OK;
+}
+
+int ensure_shadow(afr_ctx* c, cudaStream_t st) {
+  if (c->shadow_valid) return AFR_OK;
+  AFR_CUDA(c, launch_f32_to_bf16(c->params.wout, c->wshadow,
+                                 static_cast<long long>(c->P) * c->K, st),
+           "f32_to_bf16(fc_output.weight)");
+  c->launches += 1;
+  c->shadow_valid = true;
+  return AFR_OK;
+}
+
+int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
+                 const Dropout& drop, cudaStream_t st) {
+  AFR_CUDA(c, launch_frontend_forward(c->params, tokens, stride, B, S, c->cfg.max_length,
+                                      c->cfg.vocab, drop, c->feats, c->num_sms, st),
+           "frontend_forward");
+  c->launches += 1;
+  return AFR_OK;
+}
+
+AdamHyper make_hyper(double lr, double b1, double b2, double eps, double wd, long long step) {
+  AdamHyper h{};
+  const double bc1 = 1.0 - std::pow(b1, static_cast<double>(step));
+  const double bc2 = 1.0 - std::pow(b2, static_cast<double>(step));
+  h.decay = static_cast<float>(1.0 - lr * wd);
+  h.beta1_w = static_cast<float>(1.0 - b1);
+  h.beta2 = static_cast<float>(b2);
+  h.one_m_beta2 = static_cast<float>(1.0 - b2);
+  h.bc2_sqrt = static_cast<float>(std::sqrt(bc2));
+  h.eps = static_cast<float>(eps);
+  h.neg_step = static_cast<float>(-(lr / bc1));
+  return h;
+}
+
+}  // namespace
+
+extern "C" {
+
+int afr_abi_version(void) { return AFR_ABI_VERSION; }
+
+const char* afr_last_error(const afr_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+int afr_create(const afr_config* cfg, afr_ctx** out) {
+  if (cfg == nullptr || out == nullptr) return fail(nullptr, AFR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->embed_dim != kE || cfg->num_heads != kHeads || cfg->hidden != kF)
+    return fail(nullptr, AFR_ERR_INVALID,
+                "front-end kernels are built for embed_dim=32, num_heads=4, hidden=64");
+  if (cfg->max_length < 1 || cfg->max_length > kMaxL || cfg->vocab < 1 || cfg->max_batch < 1)
+    return fail(nullptr, AFR_ERR_INVALID, "max_length must be in [1,128], vocab >= 1, max_batch >= 1");
+  const long long P = static_cast<long long>(cfg->sheet_h) * cfg->sheet_w;
+  if (cfg->sheet_h < 1 || cfg->sheet_w < 1 || (P % 32) != 0)
+    return fail(nullptr, AFR_ERR_INVALID, "sheet_h*sheet_w must be a positive multiple of 32");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, AFR_ERR_CUDA, "no such CUDA device");
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
+    return fail(nullptr, AFR_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, AFR_ERR_UNSUPPORTED,
+                "libafr_sm100 needs an sm_100 (Blackwell B200) device; there is no fallback path");
+  DeviceGuard guard(cfg->device);
+  afr_ctx* c = new afr_ctx();
+  c->cfg = *cfg;
+  c->num_sms = prop.multiProcessorCount;
+  c->K = cfg->max_length * cfg->hidden;
+  c->P = static_cast<int>(P);
+  c->lay.init(cfg->max_length, cfg->vocab);
+  const size_t Bm = static_cast<size_t>(cfg->max_batch);
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  alloc(reinterpret_cast<void**>(&c->feats), Bm * c->K * 2);
+  alloc(reinterpret_cast<void**>(&c->wshadow), static_cast<size_t>(c->P) * c->K * 2);
+  if (cfg->training) {
+    alloc(reinterpret_cast<void**>(&c->dz), Bm * c->P * 2);
+    alloc(reinterpret_cast<void**>(&c->dfeat), Bm * c->K * 4);
+    alloc(reinterpret_cast<void**>(&c->bias_scratch), static_cast<size_t>(32) * c->P * 4);
+    if (static_cast<long long>(cfg->vocab) * kE * c->num_sms * 4 > (1ll << 31)) {
+      afr_destroy(c);
+      return fail(nullptr, AFR_ERR_INVALID, "training path supports vocab up to ~100k rows");
+    }
+    alloc(reinterpret_cast<void**>(&c->partials),
+          static_cast<size_t>(c->num_sms) * c->lay.total * 4);
+  }
+  if (e != cudaSuccess) {
+    std::string msg = std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e);
+    afr_destroy(c);
+    return fail(nullptr, AFR_ERR_CUDA, msg);
+  }
+  *out = c;
+  return AFR_OK;
+}
+
+int afr_destroy(afr_ctx* c) {
+  if (c == nullptr) return AFR_OK;
+  DeviceGuard guard(c->cfg.device);
+  cudaFree(c->feats); cudaFree(c->wshadow); cudaFree(c->dz); cudaFree(c->dfeat);
+  cudaFree(c->logits); cudaFree(c->loss_partials); cudaFree(c->bias_scratch);
+  cudaFree(c->partials);
+  delete c;
+  return AFR_OK;
+}
+
+int afr_bind_params(afr_ctx* c, const afr_tensors* t) {
+  if (!c || !t || !all_set(t)) return fail(c, AFR_ERR_INVALID, "afr_bind_params: null tensor");
+  c->params = to_tensors(t);
+  c->has_params = true;
+  c->shadow_valid = false;
+  return AFR_OK;
+}
+int afr_bind_grads(afr_ctx* c, const afr_tensors* t) {
+  if (!c || !t || !all_set(t)) return fail(c, AFR_ERR_INVALID, "afr_bind_grads: null tensor");
+  c->grads = to_tensors(t);
+  c->has_grads = true;
+  return AFR_OK;
+}
+int afr_bind_adam_state(afr_ctx* c, const afr_tensors* m, const afr_tensors* v) {
+  if (!c || !m || !v || !all_set(m) || !all_set(v))
+    return fail(c, AFR_ERR_INVALID, "afr_bind_adam_state: null tensor");
+  c->m = to_tensors(m);
+  c->v = to_tensors(v);
+  c->has_state = true;
+  return AFR_OK;
+}
+
+int afr_sync_shadow(afr_ctx* c, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params) return fail(c, AFR_ERR_STATE, "parameters not bound");
+  DeviceGuard guard(c->cfg.device);
+  c->shadow_valid = false;
+  return ensure_shadow(c, static_cast<cudaStream_t>(stream));
+}
+
+int afr_forward_eval(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                     void* out, int out_kind, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  int rc = check_batch(c, B, S, tokens);
+  if (rc) return rc;
+  if (out == nullptr) return fail(c, AFR_ERR_INVALID, "out is NULL");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_shadow(c, st))) return rc;
+  Dropout off{};
+  if ((rc = run_frontend(c, reinterpret_cast<const long long*>(tokens), token_stride, B, S, off, st)))
+    return rc;
+  GemmEpilogue ep{};
+  ep.out = out; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
+  if (out_kind == AFR_OUT_SHEET_F32) { ep.kind = kEpiF32; ep.clamp01 = 1; ep.use_tma_store = 1; }
+  else if (out_kind == AFR_OUT_LOGITS_F32) { ep.kind = kEpiF32; ep.clamp01 = 0; ep.use_tma_store = 1; }
+  else if (out_kind == AFR_OUT_SHEET_U8) { ep.kind = kEpiU8; }
+  else return fail(c, AFR_ERR_INVALID, "unknown out_kind");
+  if (env_int("AFR_NO_TMA_STORE")) ep.use_tma_store = 0;
+  const char* msg = nullptr;
+  const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow, c->K, false, B, c->P, c->K, bn,
+                                   ep, c->num_sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
+  c->launches += 1;
+  return AFR_OK;
+}
+
+int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                           const void* targets, int target_kind, const afr_dropout* dropout,
+                           double loss_count, float* loss_out, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  int rc = check_batch(c, B, S, tokens);
+  if (rc) return rc;
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (targets == nullptr || loss_out == nullptr || !(loss_count > 0))
+    return fail(c, AFR_ERR_INVALID, "targets/loss_out NULL or loss_count <= 0");
+  if (target_kind != AFR_TARGET_U8 && target_kind != AFR_TARGET_F32)
+    return fail(c, AFR_ERR_INVALID, "unknown target_kind");
+  if (reinterpret_cast<uintptr_t>(targets) & 15)
+    return fail(c, AFR_ERR_INVALID, "targets must be 16-byte aligned");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = ensure_shadow(c, st))) return rc;
+  c->drop = to_dropout(dropout);
+  c->tokens = reinterpret_cast<const long long*>(tokens);
+  c->token_stride = token_stride;
+  c->B = B; c->S = S;
+  c->grad_scale = static_cast<float>(2.0 / loss_count);  // d/dy of mean((y-t)^2)
+  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, st))) return rc;
+  const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  const int tiles = gemm_num_tiles(B, c->P, bn);
+  if ((rc = ensure_loss_partials(c, tiles * 4))) return rc;
+  GemmEpilogue ep{};
+  ep.kind = kEpiLoss; ep.out = c->dz; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
+  ep.target = targets; ep.target_is_f32 = target_kind == AFR_TARGET_F32;
+  ep.loss_partials = c->loss_partials;
+  const char* msg = nullptr;
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow, c->K, false, B, c->P, c->K, bn,
+                                   ep, c->num_sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward+loss)");
+  AFR_CUDA(c, launch_loss_finalize(c->loss_partials, tiles * 4, loss_count, loss_out, st),
+           "loss_finalize");
+  c->launches += 2;
+  c->fwd_done = true;
+  return AFR_OK;
+}
+
+int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_wgrad before a training forward");
+  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  if (row_begin < 0 || row_end > c->P || row_begin >= row_end || (row_begin % 32) != 0 ||
+      ((row_end - row_begin) % 32) != 0)
+    return fail(c, AFR_ERR_INVALID, "row range must be 32-aligned inside [0, H*W]");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = row_end - row_begin;
+  // dW[rows, K] = scale * dZ[:, rows]^T feats : A = dZ (MN-major, K = batch), B = feats (MN-major)
+  GemmEpilogue ep{};
+  ep.kind = kEpiF32;
+  ep.out = c->grads.wout + static_cast<long long>(row_begin) * c->K;
+  ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
+  const char* msg = nullptr;
+  const int bn = choose_bn(rows, c->K, c->num_sms, "AFR_BN_WGRAD");
+  cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
+                                   c->B, bn, ep, c->num_sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(wgrad)");
+  // db[rows] = scale * sum_b dZ[b, rows]
+  AFR_CUDA(c, launch_bias_grad(c->dz + row_begin, c->B, rows, c->grad_scale, c->bias_scratch,
+                               c->grads.bout + row_begin, st, c->P),
+           "bias_grad");
+  c->launches += 3;
+  return AFR_OK;
+}
+
+int afr_train_dgrad(afr_ctx* c, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_dgrad before a training forward");
+  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // dfeat[B, K] = scale * dZ[B, P] W[P, K] : A = dZ (K-major over pixels), B = W (MN-major)
+  GemmEpilogue ep{};
+  ep.kind = kEpiF32; ep.out = c->dfeat; ep.ldo = c->K; ep.alpha = c->grad_scale;
+  ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
+  const char* msg = nullptr;
+  const int bn = choose_bn(c->B, c->K, c->num_sms, "AFR_BN_DGRAD");
+  cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow, c->K, true, c->B, c->K, c->P, bn,
+                                   ep, c->num_sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(dgrad)");
+  int grid = 0;
+  AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
+                                       c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
+                                       c->partials, c->num_sms, &grid, c->num_sms, st),
+           "frontend_backward");
+  AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
+           "small_grad_reduce");
+  c->launches += 3;
+  return AFR_OK;
+}
+
+int afr_train_step(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                   const void* targets, int target_kind, const afr_dropout* dropout,
+                   double loss_count, float* loss_out, void* stream) {
+  int rc = afr_train_forward_loss(c, tokens, token_stride, B, S, targets, target_kind, dropout,
+                                  loss_count, loss_out, stream);
+  if (rc) return rc;
+  if ((rc = afr_train_wgrad(c, 0, c->P, stream))) return rc;
+  return afr_train_dgrad(c, stream);
+}
+
+int afr_forward_train(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                      const afr_dropout* dropout, float* sheet_out, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  int rc = check_batch(c, B, S, tokens);
+  if (rc) return rc;
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (sheet_out == nullptr) return fail(c, AFR_ERR_INVALID, "sheet_out is NULL");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->logits == nullptr)
+    AFR_CUDA(c, cudaMalloc(&c->logits, static_cast<size_t>(c->cfg.max_batch) * c->P * 4),
+             "cudaMalloc(logits)");
+  if ((rc = ensure_shadow(c, st))) return rc;
+  c->drop = to_dropout(dropout);
+  c->tokens = reinterpret_cast<const long long*>(tokens);
+  c->token_stride = token_stride;
+  c->B = B; c->S = S;
+  c->grad_scale = 1.f;
+  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, st))) return rc;
+  GemmEpilogue ep{};
+  ep.kind = kEpiF32; ep.out = c->logits; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
+  ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
+  const char* msg = nullptr;
+  const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow, c->K, false, B, c->P, c->K, bn,
+                                   ep, c->num_sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
+  AFR_CUDA(c, launch_clamp01(c->logits, sheet_out, static_cast<long long>(B) * c->P, st), "clamp01");
+  c->launches += 2;
+  c->fwd_done = false;  // becomes true once afr_backward has produced dZ
+  return AFR_OK;
+}
+
+int afr_backward(afr_ctx* c, const float* dsheet, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (c->logits == nullptr || c->tokens == nullptr)
+    return fail(c, AFR_ERR_STATE, "afr_backward before afr_forward_train");
+  if (dsheet == nullptr) return fail(c, AFR_ERR_INVALID, "dsheet is NULL");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AFR_CUDA(c, launch_clamp_backward(dsheet, c->logits, c->dz, static_cast<long long>(c->B) * c->P, st),
+           "clamp_backward");
+  c->launches += 1;
+  c->fwd_done = true;
+  int rc = afr_train_wgrad(c, 0, c->P, stream);
+  if (rc) return rc;
+  return afr_train_dgrad(c, stream);
+}
+
+int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, int row_begin, int row_end, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_grads || !c->has_state)
+    return fail(c, AFR_ERR_STATE, "params / grads / adam state not bound");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
+    return fail(c, AFR_ERR_INVALID, "bad step or row range");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  const long long n = static_cast<long long>(row_end - row_begin) * c->K;
+  AFR_CUDA(c, launch_adamw(c->params.wout + off, c->grads.wout + off, c->m.wout + off,
+                           c->v.wout + off, n, h, c->wshadow + off, c->num_sms, st),
+           "adamw(fc_output.weight)");
+  SmallAdamJob job{c->params.bout + row_begin, c->grads.bout + row_begin, c->m.bout + row_begin,
+                   c->v.bout + row_begin, row_end - row_begin};
+  AFR_CUDA(c, launch_adamw_small(&job, 1, h, st), "adamw(fc_output.bias)");
+  c->launches += 2;
+  return AFR_OK;
+}
+
+int afr_adamw_small(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int64_t step, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_grads || !c->has_state)
+    return fail(c, AFR_ERR_STATE, "params / grads / adam state not bound");
+  if (step < 1) return fail(c, AFR_ERR_INVALID, "step must be >= 1");
+  DeviceGuard guard(c->cfg.device);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  const int L = c->cfg.max_length, V = c->cfg.vocab;
+  const int sizes[10] = {L * kE, V * kE, 3 * kE * kE, 3 * kE, kE * kE, kE, kE, kE, kF * kE, kF};
+  float* const* pp = reinterpret_cast<float* const*>(&c->params);
+  float* const* gg = reinterpret_cast<float* const*>(&c->grads);
+  float* const* mm = reinterpret_cast<float* const*>(&c->m);
+  float* const* vv = reinterpret_cast<float* const*>(&c->v);
+  SmallAdamJob jobs[10];
+  for (int i = 0; i < 10; ++i) jobs[i] = SmallAdamJob{pp[i], gg[i], mm[i], vv[i], sizes[i]};
+  AFR_CUDA(c, launch_adamw_small(jobs, 10, h, static_cast<cudaStream_t>(stream)), "adamw(small)");
+  c->launches += 1;
+  return AFR_OK;
+}
+
+int afr_adamw_step(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  int rc = afr_adamw_rows(c, lr, beta1, beta2, eps, weight_decay, step, 0, c->P, stream);
+  if (rc) return rc;
+  return afr_adamw_small(c, lr, beta1, beta2, eps, weight_decay, step, stream);
+}
+
+int afr_check_tokens(afr_ctx* c, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  DeviceGuard guard(c->cfg.device);
+  int* flag = frontend_error_flag();
+  if (flag == nullptr) return AFR_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int host = 0;
+  AFR_CUDA(c, cudaMemcpyAsync(&host, flag, sizeof(int), cudaMemcpyDeviceToHost, st), "read token flag");
+  AFR_CUDA(c, cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  if (host != 0) {
+    AFR_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(int), st), "reset token flag");
+    return fail(c, AFR_ERR_TOKEN_RANGE, "token id outside [0, vocab) (index out of range in embedding)");
+  }
+  return AFR_OK;
+}
+
+int afr_workspace_ptr(afr_ctx* c, int which, void** ptr, size_t* bytes) {
+  if (!c || !ptr || !bytes) return AFR_ERR_INVALID;
+  const size_t Bm = static_cast<size_t>(c->cfg.max_batch);
+  switch (which) {
+    case 0: *ptr = c->feats; *bytes = Bm * c->K * 2; break;
+    case 1: *ptr = c->dz; *bytes = c->dz ? Bm * c->P * 2 : 0; break;
+    case 2: *ptr = c->dfeat; *bytes = c->dfeat ? Bm * c->K * 4 : 0; break;
+    case 3: *ptr = c->wshadow; *bytes = static_cast<size_t>(c->P) * c->K * 2; break;
+    case 4: *ptr = c->logits; *bytes = c->logits ? Bm * c->P * 4 : 0; break;
+    default: return fail(c, AFR_ERR_INVALID, "unknown workspace id");
+  }
+  return AFR_OK;
+}
+
+int afr_gemm_tiles(afr_ctx* c, int B, int* out) {
+  if (!c || !out || B < 1) return AFR_ERR_INVALID;
+  out[0] = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  out[1] = choose_bn(B, c->K, c->num_sms, "AFR_BN_DGRAD");
+  out[2] = choose_bn(c->P, c->K, c->num_sms, "AFR_BN_WGRAD");
+  return AFR_OK;
+}
+
+int64_t afr_launch_count(const afr_ctx* c) { return c ? c->launches : 0; }
+
+int afr_gemm_bf16(int device, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb,
+                  int b_mn, float* D, int64_t ldd, int M, int N, int K, int tile_n, float alpha,
+                  int use_tma_store, void* stream) {
+  if (!A || !B || !D) return fail(nullptr, AFR_ERR_INVALID, "afr_gemm_bf16: null pointer");
+  int major = 0, sms = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+    return fail(nullptr, AFR_ERR_CUDA, "cudaDeviceGetAttribute failed");
+  if (major != 10) return fail(nullptr, AFR_ERR_UNSUPPORTED, "needs an sm_100 device");
+  DeviceGuard guard(device);
+  GemmEpilogue ep{};
+  ep.kind = kEpiF32; ep.out = D; ep.ldo = ldd; ep.alpha = alpha; ep.use_tma_store = use_tma_store;
+  const char* msg = nullptr;
+  cudaError_t e = launch_gemm_bf16(static_cast<const __nv_bfloat16*>(A), lda, a_mn != 0,
+                                   static_cast<const __nv_bfloat16*>(B), ldb, b_mn != 0, M, N, K,
+                                   tile_n, ep, sms,
+                                   static_cast<cudaStream_t>(stream), nullptr, &msg);
+  if (e != cudaSuccess)
+    return msg ? fail(nullptr, AFR_ERR_INVALID, msg) : fail_cuda(nullptr, e, "afr_gemm_bf16");
+  return AFR_OK;
+}
+
+}  // extern "C"

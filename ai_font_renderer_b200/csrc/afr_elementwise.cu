@@ -1,0 +1,241 @@
+// HBM-bound kernels of the training step: the fused AdamW sweep (reference: optim.AdamW at
+// model.py:273, stepped at model.py:310), the bf16 shadow refresh, the loss finalisation
+// (mean of model.py:270), the fc_output bias gradient and the clamp backward of the generic
+// autograd path. All are 128-bit vectorised, coalesced, grid sized in multiples of the SM count.
+#include "afr_internal.h"
+
+namespace afr {
+namespace {
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// torch.optim.AdamW (single-tensor path) element update, fp32, same operation order:
+//   p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = v*b2 + (1-b2)*g*g;
+//   p += -(lr/bc1) * (m / (sqrt(v)/sqrt(bc2) + eps))
+__device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v,
+                                           const AdamHyper& h) {
+  p = __fmul_rn(p, h.decay);
+  m = fmaf(h.beta1_w, __fsub_rn(g, m), m);
+  v = __fadd_rn(__fmul_rn(v, h.beta2), __fmul_rn(__fmul_rn(h.one_m_beta2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), h.bc2_sqrt), h.eps);
+  p = __fadd_rn(p, __fmul_rn(h.neg_step, __fdiv_rn(m, denom)));
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+             float* __restrict__ v, long long n4, long long n, AdamHyper h,
+             __nv_bfloat16* __restrict__ shadow) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = ld_stream(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_elem(pv.x, gv.x, mv.x, vv.x, h);
+    adamw_elem(pv.y, gv.y, mv.y, vv.y, h);
+    adamw_elem(pv.z, gv.z, mv.z, vv.z, h);
+    adamw_elem(pv.w, gv.w, mv.w, vv.w, h);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow != nullptr) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(pv.z, pv.w);
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(shadow)[i] = packed;
+    }
+  }
+  // scalar tail (n not a multiple of 4)
+  if (blockIdx.x == 0) {
+    for (long long j = n4 * 4 + threadIdx.x; j < n; j += blockDim.x) {
+      float pj = p[j], mj = m[j], vj = v[j];
+      adamw_elem(pj, g[j], mj, vj, h);
+      p[j] = pj; m[j] = mj; v[j] = vj;
+      if (shadow != nullptr) shadow[j] = __float2bfloat16_rn(pj);
+    }
+  }
+}
+
+constexpr int kMaxSmallJobs = 16;
+struct SmallJobs { SmallAdamJob j[kMaxSmallJobs]; int n; };
+
+__global__ void __launch_bounds__(256) adamw_small_kernel(SmallJobs jobs, AdamHyper h) {
+  const SmallAdamJob job = jobs.j[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x) {
+    float pj = job.p[i], mj = job.m[i], vj = job.v[i];
+    adamw_elem(pj, job.g[i], mj, vj, h);
+    job.p[i] = pj; job.m[i] = mj; job.v[i] = vj;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4,
+                   long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += stride) {
+    const float4 x = ld_stream(reinterpret_cast<const float4*>(src) + i);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y);
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(x.z, x.w);
+    uint2 packed;
+    packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+    packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(dst)[i] = packed;
+  }
+  if (blockIdx.x == 0)
+    for (long long j = n4 * 4 + threadIdx.x; j < n; j += blockDim.x)
+      dst[j] = __float2bfloat16_rn(src[j]);
+}
+
+// One block; fixed summation order -> run-to-run deterministic loss.
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const float* __restrict__ partials, int n, double count,
+                     float* __restrict__ loss_out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += static_cast<double>(partials[i]);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_out = static_cast<float>(red[0] / count);
+}
+
+// Stage 1: scratch[slice, p] = sum over the slice's rows of dz[b, p]  (bf16x2 per thread).
+__global__ void __launch_bounds__(128)
+bias_grad_stage1(const __nv_bfloat16* __restrict__ dz, int B, int P, long long ld,
+                 int rows_per_slice, float* __restrict__ scratch) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair * 2 >= P) return;
+  const int b0 = blockIdx.y * rows_per_slice;
+  const int b1 = min(B, b0 + rows_per_slice);
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const __nv_bfloat162 x =
+        reinterpret_cast<const __nv_bfloat162*>(dz + static_cast<long long>(b) * ld)[pair];
+    const float2 f = __bfloat1622float2(x);
+    s0 += f.x; s1 += f.y;
+  }
+  float* out = scratch + static_cast<long long>(blockIdx.y) * P;
+  out[pair * 2] = s0;
+  out[pair * 2 + 1] = s1;
+}
+__global__ void __launch_bounds__(256)
+bias_grad_stage2(const float* __restrict__ scratch, int slices, int P, float alpha,
+                 float* __restrict__ dbias) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float s = 0.f;
+  for (int k = 0; k < slices; ++k) s += scratch[static_cast<long long>(k) * P + p];
+  dbias[p] = s * alpha;
+}
+
+__global__ void __launch_bounds__(256)
+clamp_backward_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                      __nv_bfloat16* __restrict__ dz, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    const float zz = z[i];
+    dz[i] = __float2bfloat16_rn((zz >= 0.f && zz <= 1.f) ? dy[i] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+clamp01_kernel(const float* __restrict__ z, float* __restrict__ y, long long n4, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += stride) {
+    float4 x = reinterpret_cast<const float4*>(z)[i];
+    x.x = fminf(fmaxf(x.x, 0.f), 1.f); x.y = fminf(fmaxf(x.y, 0.f), 1.f);
+    x.z = fminf(fmaxf(x.z, 0.f), 1.f); x.w = fminf(fmaxf(x.w, 0.f), 1.f);
+    reinterpret_cast<float4*>(y)[i] = x;
+  }
+  if (blockIdx.x == 0)
+    for (long long j = n4 * 4 + threadIdx.x; j < n; j += blockDim.x)
+      y[j] = fminf(fmaxf(z[j], 0.f), 1.f);
+}
+
+int stream_grid(long long work_items, int threads, int num_sms) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms) * 8;  // 8 resident CTAs of 256 thr / SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n,
+                         const AdamHyper& h, __nv_bfloat16* shadow, int num_sms, cudaStream_t s) {
+  const long long n4 = n / 4;
+  adamw_kernel<<<stream_grid(n4, 256, num_sms), 256, 0, s>>>(p, g, m, v, n4, n, h, shadow);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_small(const SmallAdamJob* jobs, int njobs, const AdamHyper& h,
+                               cudaStream_t s) {
+  if (njobs <= 0 || njobs > kMaxSmallJobs) return cudaErrorInvalidValue;
+  SmallJobs sj{};
+  int max_n = 0;
+  for (int i = 0; i < njobs; ++i) {
+    sj.j[i] = jobs[i];
+    if (jobs[i].n > max_n) max_n = jobs[i].n;
+  }
+  sj.n = njobs;
+  int gx = (max_n + 255) / 256;
+  if (gx > 32) gx = 32;
+  adamw_small_kernel<<<dim3(gx, njobs), 256, 0, s>>>(sj, h);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s) {
+  const long long n4 = n / 4;
+  f32_to_bf16_kernel<<<stream_grid(n4, 256, 148), 256, 0, s>>>(src, dst, n4, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loss_finalize(const float* partials, int n, double count, float* loss_out,
+                                 cudaStream_t s) {
+  loss_finalize_kernel<<<1, 256, 0, s>>>(partials, n, count, loss_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bias_grad(const __nv_bfloat16* dz, int B, int P, float alpha, float* scratch,
+                             float* dbias, cudaStream_t s, long long ld) {
+  int slices = (B + 31) / 32;
+  if (slices > 32) slices = 32;
+  const int rows = (B + slices - 1) / slices;
+  slices = (B + rows - 1) / rows;
+  const int pairs = (P + 1) / 2;
+  bias_grad_stage1<<<dim3((pairs + 127) / 128, slices), 128, 0, s>>>(dz, B, P, ld, rows, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  bias_grad_stage2<<<(P + 255) / 256, 256, 0, s>>>(scratch, slices, P, alpha, dbias);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clamp01(const float* z, float* y, long long n, cudaStream_t s) {
+  const long long n4 = (reinterpret_cast<uintptr_t>(y) & 15) ? 0 : n / 4;
+  clamp01_kernel<<<stream_grid(n4 > 0 ? n4 : n, 256, 148), 256, 0, s>>>(z, y, n4, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clamp_backward(const float* dy, const float* z, __nv_bfloat16* dz, long long n,
+                                  cudaStream_t s) {
+  clamp_backward_kernel<<<stream_grid(n, 256, 148), 256, 0, s>>>(dy, z, dz, n);
+  return cudaGetLastError();
+}
+
+}  // namespace afr

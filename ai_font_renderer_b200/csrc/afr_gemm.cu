@@ -1,0 +1,123 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding, tile-shape bookkeeping, launch.
+#include <cstdio>
+#include <mutex>
+
+#include "afr_gemm.cuh"
+#include "afr_internal.h"
+
+namespace afr {
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}.
+bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const void* base,
+               long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int EPI, bool A_MN, bool B_MN>
+cudaError_t launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_kernel<EPI, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int gemm_num_tiles(int M, int N, int BN) { return ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN); }
+
+cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
+                             const __nv_bfloat16* B, long long ldb, bool b_mn, int M, int N, int K,
+                             int BN, const GemmEpilogue& epi, int num_sms, cudaStream_t stream,
+                             int* num_tiles_out, const char** err_msg) {
+  static const char* kBadShape = "gemm: need M,N,K > 0, N % 32 == 0, BN % 32 == 0, 32 <= BN <= 256";
+  static const char* kBadAlign = "gemm: operand pointers / leading dimensions must be 16-byte aligned";
+  static const char* kBadMap = "gemm: cuTensorMapEncodeTiled failed";
+  static const char* kBadEpi = "gemm: unsupported epilogue / operand-major combination";
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (BN % 32) != 0 || BN < 32 || BN > kMaxBN) {
+    if (err_msg) *err_msg = kBadShape;
+    return cudaErrorInvalidValue;
+  }
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
+      (lda % 8) != 0 || (ldb % 8) != 0) {
+    if (err_msg) *err_msg = kBadAlign;
+    return cudaErrorInvalidValue;
+  }
+  GemmParams p{};
+  bool ok = true;
+  if (!a_mn) ok &= encode_2d(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kBK, kBM);
+  else       ok &= encode_2d(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, 64, kBK);
+  if (!b_mn) ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, kBK, BN);
+  else       ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, 64, kBK);
+  int use_tma_store = epi.use_tma_store;
+  if (epi.kind == kEpiF32 && use_tma_store) {
+    if ((reinterpret_cast<uintptr_t>(epi.out) & 15) || (epi.ldo % 4) != 0) {
+      use_tma_store = 0;  // unaligned output: fall back to direct stores
+    } else {
+      ok &= encode_2d(&p.tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.out, M, N, epi.ldo, 32, 32);
+    }
+  }
+  if (!ok) {
+    if (err_msg) *err_msg = kBadMap;
+    return cudaErrorInvalidValue;
+  }
+  p.M = M; p.N = N; p.K = K; p.BN = BN;
+  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.idesc = ptx::make_idesc_bf16(kBM, BN, a_mn, b_mn);
+  p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.alpha = epi.alpha;
+  p.clamp01 = epi.clamp01; p.use_tma_store = use_tma_store;
+  p.target = epi.target; p.target_is_f32 = epi.target_is_f32; p.loss_partials = epi.loss_partials;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  if (num_tiles_out) *num_tiles_out = num_tiles;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+
+  if (epi.kind == kEpiF32) {
+    if (!a_mn && !b_mn) return launch_one<kEpiF32, false, false>(p, grid, stream);
+    if (!a_mn && b_mn)  return launch_one<kEpiF32, false, true>(p, grid, stream);
+    if (a_mn && !b_mn)  return launch_one<kEpiF32, true, false>(p, grid, stream);
+    return launch_one<kEpiF32, true, true>(p, grid, stream);
+  }
+  if (epi.kind == kEpiU8 && !a_mn && !b_mn && epi.bias != nullptr)
+    return launch_one<kEpiU8, false, false>(p, grid, stream);
+  if (epi.kind == kEpiLoss && !a_mn && !b_mn && epi.bias != nullptr)
+    return launch_one<kEpiLoss, false, false>(p, grid, stream);
+  if (err_msg) *err_msg = kBadEpi;
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace afr

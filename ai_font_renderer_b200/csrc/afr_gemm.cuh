@@ -1,0 +1,334 @@
+// Persistent, warp-specialised tcgen05 GEMM for the fc_output contraction and its two
+// gradients (reference: model.py:196 forward, autograd of it at model.py:309).
+//
+//   D[M,N] = A[M,K] * B[N,K]^T      bf16 operands, fp32 accumulation in TMEM
+//
+// Each operand can be "K-major" (K contiguous in global memory) or "MN-major" (M resp. N
+// contiguous), so the three GEMMs of a training step all read the natural row-major
+// tensors with no transposed copies:
+//   forward : A = feats [B,6400]  (K-major)   B = W   [19200,6400] (K-major)
+//   dgrad   : A = dZ    [B,19200] (K-major)   B = W   [19200,6400] (MN-major, K = pixel)
+//   wgrad   : A = dZ    [B,19200] (MN-major)  B = feats [B,6400]   (MN-major, K = batch)
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused epilogue -> global / TMA store)
+// Three mbarrier pipelines: smem full/empty, TMEM full/empty (two accumulator buffers so
+// the epilogue of tile i overlaps the MMAs of tile i+1), and a static persistent tile loop.
+#pragma once
+#include "afr_ptx.cuh"
+
+namespace afr {
+
+constexpr int kBM = 128;                       // UMMA M (cta_group::1)
+constexpr int kBK = 64;                        // k-block: 64 bf16 (one 128B swizzle row)
+constexpr int kMaxBN = 256;                    // UMMA N upper bound
+constexpr int kStages = 4;
+constexpr int kAStageBytes = kBM * kBK * 2;    // 16 KB
+constexpr int kBStageBytes = kMaxBN * kBK * 2; // 32 KB
+constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+constexpr int kEpiWarpBufBytes = 32 * 128;     // one 32-row x 128-byte staging slab
+constexpr int kEpiBytes = 4 * 2 * kEpiWarpBufBytes;  // 4 warps x 2 buffers = 32 KB
+constexpr int kBarrierBytes = 256;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;
+constexpr int kGemmThreads = 192;
+constexpr int kTmemCols = 512;                 // 2 accumulator buffers x 256 columns
+
+enum EpiKind : int {
+  kEpiF32 = 0,   // out_f32 = [clamp01](alpha*acc + bias[n])        (logits, dA, dW, eval sheet)
+  kEpiU8 = 1,    // out_u8  = trunc(clamp01(acc + bias[n]) * 255)   (helpers.py:33 quantisation)
+  kEpiLoss = 2,  // clamp + MSE partial sums + masked residual dZ   (model.py:202,270 + backward)
+};
+
+struct GemmParams {
+  CUtensorMap tm_a;
+  CUtensorMap tm_b;
+  CUtensorMap tm_c;      // fp32 store map (kEpiF32 with use_tma_store)
+  int M, N, K;
+  int BN;                // tile N, multiple of 32, <= 256
+  int num_m_tiles, num_n_tiles;
+  uint32_t idesc;
+  // epilogue
+  void* out;             // f32 / u8 / bf16 (dZ) row-major [M, ldo]
+  long long ldo;
+  const float* bias;     // [N] or nullptr
+  float alpha;
+  int clamp01;
+  int use_tma_store;
+  const void* target;    // kEpiLoss: [M, N] u8 (k/255) or f32
+  int target_is_f32;
+  float* loss_partials;  // kEpiLoss: [num_tiles * 4] per-warp sums of (y - t)^2
+};
+
+template <int EPI, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms are 1024-byte aligned.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kAStageBytes;
+  uint8_t* smem_epi = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tmem_full_bar = bars + 2 * kStages; // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int BN = p.BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tm_a);
+    ptx::prefetch_tensormap(&p.tm_b);
+    if (EPI == kEpiF32 && p.use_tma_store) ptx::prefetch_tensormap(&p.tm_c);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_base_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = kAStageBytes;
+      const uint32_t b_boxes = B_MN ? static_cast<uint32_t>((BN + 63) / 64) : 0u;
+      const uint32_t b_bytes = B_MN ? b_boxes * 8192u : static_cast<uint32_t>(BN) * kBK * 2u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_tiles) * kBM;
+        const int n0 = (tile / p.num_m_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          uint8_t* sa = smem_a + stage * kAStageBytes;
+          uint8_t* sb = smem_b + stage * kBStageBytes;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d(&p.tm_a, &full_bar[stage], sa, kb * kBK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < kBM / 64; ++i)
+              ptx::tma_load_2d(&p.tm_a, &full_bar[stage], sa + i * 8192, m0 + i * 64, kb * kBK);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d(&p.tm_b, &full_bar[stage], sb, kb * kBK, n0);
+          } else {
+            for (uint32_t i = 0; i < b_boxes; ++i)
+              ptx::tma_load_2d(&p.tm_b, &full_bar[stage], sb + i * 8192, n0 + i * 64, kb * kBK);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      // K-major  : 8-row groups 1024 B apart (SBO); 16 K-elements = 32 B inside the swizzle row.
+      // MN-major : 64-element MN chunks 8192 B apart (LBO); 8-row K groups 1024 B apart (SBO);
+      //            16 K-rows = 2048 B.
+      const uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
+      const uint32_t a_kstep = (A_MN ? 2048u : 32u) >> 4, b_kstep = (B_MN ? 2048u : 32u) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_smem_desc_sw128(
+              ptx::smem_u32(smem_a + stage * kAStageBytes), a_lbo, 1024u);
+          const uint64_t db = ptx::make_smem_desc_sw128(
+              ptx::smem_u32(smem_b + stage * kBStageBytes), b_lbo, 1024u);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            ptx::umma_bf16(d_tmem, da + static_cast<uint64_t>(k * a_kstep),
+                           db + static_cast<uint64_t>(k * b_kstep), p.idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row_in_tile = q * 32 + lane;
+    uint8_t* my_stage = smem_epi + q * 2 * kEpiWarpBufBytes;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int store_buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.num_m_tiles) * kBM;
+      const int n0 = (tile / p.num_m_tiles) * BN;
+      const int m = m0 + row_in_tile;
+      const bool row_ok = m < p.M;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      float loss_acc = 0.f;
+      const int n_chunks = BN / 32;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * kMaxBN + c * 32),
+                           r);
+        ptx::tmem_ld_wait();
+        if (c == n_chunks - 1 || n + 32 >= p.N) {
+          // last read of this accumulator buffer: hand it back to the MMA warp early
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+
+        if (EPI == kEpiF32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float z = v[j] * p.alpha;
+            if (p.bias != nullptr) z += __ldg(p.bias + n + j);
+            if (p.clamp01) z = fminf(fmaxf(z, 0.f), 1.f);
+            v[j] = z;
+          }
+          if (p.use_tma_store) {
+            uint8_t* buf = my_stage + store_buf * kEpiWarpBufBytes;
+            if (lane == 0) ptx::tma_store_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              float4 val = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((ch ^ (lane & 7)) << 4)) = val;
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&p.tm_c, buf, n, m0 + q * 32);
+              ptx::tma_store_commit();
+            }
+            store_buf ^= 1;
+          } else if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<float4*>(o + 4 * ch) =
+                  make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          }
+        } else if (EPI == kEpiU8) {
+          if (row_ok) {
+            uint32_t packed[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              uint32_t word = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                const int j = 4 * w + b;
+                float z = v[j] + __ldg(p.bias + n + j);
+                z = fminf(fmaxf(z, 0.f), 1.f);
+                const uint32_t u = static_cast<uint32_t>(__fmul_rn(z, 255.0f));  // truncation
+                word |= (u & 0xFFu) << (8 * b);
+              }
+              packed[w] = word;
+            }
+            uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+            *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(o + 16) =
+                make_uint4(packed[4], packed[5], packed[6], packed[7]);
+          }
+        } else {  // kEpiLoss
+          if (row_ok) {
+            float t[32];
+            if (p.target_is_f32) {
+              const float4* tp = reinterpret_cast<const float4*>(
+                  reinterpret_cast<const float*>(p.target) + static_cast<long long>(m) * p.N + n);
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                const float4 tv = __ldg(tp + ch);
+                t[4 * ch] = tv.x; t[4 * ch + 1] = tv.y; t[4 * ch + 2] = tv.z; t[4 * ch + 3] = tv.w;
+              }
+            } else {
+              const uint4* tp = reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const uint8_t*>(p.target) + static_cast<long long>(m) * p.N + n);
+              const uint4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+              const uint32_t words[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+              for (int w = 0; w < 8; ++w)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  // exactly np.float32(u8) / 255.0 (helpers.py:121)
+                  t[4 * w + b] = __fdiv_rn(static_cast<float>((words[w] >> (8 * b)) & 0xFFu), 255.0f);
+            }
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float g2[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float z = v[j + e] + __ldg(p.bias + n + j + e);
+                const float y = fminf(fmaxf(z, 0.f), 1.f);
+                const float d = y - t[j + e];
+                loss_acc = fmaf(d, d, loss_acc);
+                // d clamp / dz is 1 on the closed interval [0,1] (torch.clamp backward)
+                g2[e] = (z >= 0.f && z <= 1.f) ? d : 0.f;
+              }
+              const __nv_bfloat162 h = __floats2bfloat162_rn(g2[0], g2[1]);
+              packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            __nv_bfloat16* o =
+                reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<uint4*>(o + 8 * ch) = make_uint4(
+                  packed[4 * ch], packed[4 * ch + 1], packed[4 * ch + 2], packed[4 * ch + 3]);
+          }
+        }
+      }
+      if (EPI == kEpiLoss) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+          loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+        if (lane == 0) p.loss_partials[tile * 4 + q] = loss_acc;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (EPI == kEpiF32 && p.use_tma_store && lane == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace afr

@@ -1,0 +1,184 @@
+/* libafr_sm100.so -- C ABI of the B200-native hot path of chenglou/ai-font-renderer.
+ *
+ * The reference has no FFI of its own: its hot path is the body of the per-batch loop in
+ * model.py:291-311 (zero_grad -> model(x) -> mse_loss -> backward -> AdamW.step) and the
+ * no-grad forward used by validation (model.py:317-330) and render_strings (helpers.py:62-64),
+ * all expressed as PyTorch eager ops. Each entry point below names the reference statements it
+ * replaces. The binding a maintainer would add on the reference side (a ctypes stub inside
+ * model.py / helpers.py) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: opaque context, raw device pointers, sizes, a cudaStream_t passed as void*.
+ *  - every function returns 0 on success or a negative afr_status; afr_last_error() gives text.
+ *    Nothing throws, aborts or synchronises the host (except afr_check_tokens, by contract).
+ *  - the caller (PyTorch on the host side) owns parameters, gradients, optimizer state, inputs and
+ *    outputs; the library owns only its context: TMA descriptors, the bf16 shadow of
+ *    fc_output.weight, and the activations that live between forward and backward.
+ *  - one context per (device, model shape); not re-entrant per context.
+ *  - sm_100a only. There is no CPU path and no fallback: on any other device afr_create fails.
+ */
+#ifndef AFR_SM100_H_
+#define AFR_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFR_ABI_VERSION 1
+
+typedef struct afr_ctx afr_ctx;
+
+typedef enum afr_status {
+  AFR_OK = 0,
+  AFR_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  AFR_ERR_CUDA = -2,        /* CUDA runtime or driver error (text in afr_last_error) */
+  AFR_ERR_UNSUPPORTED = -3, /* not an sm_100 device */
+  AFR_ERR_STATE = -4,       /* call order violated (e.g. params not bound) */
+  AFR_ERR_TOKEN_RANGE = -5  /* a token id outside [0, vocab): reference raises IndexError, model.py:167 */
+} afr_status;
+
+/* Model shape. Defaults of the reference are in the comments (model.py:64-66,79-81,136,148). */
+typedef struct afr_config {
+  int device;      /* CUDA ordinal */
+  int vocab;       /* nn.Embedding rows: 128 */
+  int max_length;  /* MAX_CHARS_PER_SHEET: 100 (<= 128) */
+  int embed_dim;   /* EMBEDDING_DIM: 32 (only 32 is built) */
+  int num_heads;   /* NUM_ATTENTION_HEADS: 4 (only 4 is built) */
+  int hidden;      /* fc1 width: 64 (only 64 is built) */
+  int sheet_h;     /* SHEET_HEIGHT: 80 */
+  int sheet_w;     /* SHEET_WIDTH: 240; sheet_h*sheet_w must be a multiple of 32 */
+  int max_batch;   /* largest B any call will pass; sizes the private workspaces */
+  int training;    /* nonzero: also allocate the backward workspaces */
+} afr_config;
+
+/* The 12 fp32 tensors of the reference state_dict, in its order (helpers.py:76-79 saves them,
+ * helpers.py:101 loads them). Row-major [out, in] like torch. Device pointers. */
+typedef struct afr_tensors {
+  float* positional_encoding; /* [max_length, 32]        model.py:140 */
+  float* embedding_weight;    /* [vocab, 32]             model.py:136 */
+  float* in_proj_weight;      /* [96, 32]                model.py:144 */
+  float* in_proj_bias;        /* [96] */
+  float* out_proj_weight;     /* [32, 32] */
+  float* out_proj_bias;       /* [32] */
+  float* layer_norm_weight;   /* [32]                    model.py:145 */
+  float* layer_norm_bias;     /* [32] */
+  float* fc1_weight;          /* [64, 32]                model.py:148 */
+  float* fc1_bias;            /* [64] */
+  float* fc_output_weight;    /* [H*W, 64*max_length]    model.py:152 */
+  float* fc_output_bias;      /* [H*W] */
+} afr_tensors;
+
+/* Dropout at the three sites of forward (model.py:137/168, 144 -> torch functional.py attention
+ * dropout, 149/184). mode 0 = off (model.eval()); mode 1 = built-in counter-based generator
+ * (Philox4x32-10 keyed by seed, counter = element block / site / global sample index / step, so
+ * masks do not depend on how the batch is sharded over GPUs and backward regenerates them);
+ * mode 2 = caller-supplied keep-masks (1 = keep), used to reproduce a recorded torch run. */
+typedef struct afr_dropout {
+  int mode;
+  uint64_t seed;
+  uint64_t step;
+  int64_t sample_offset;
+  const uint8_t* mask_embed; /* [B, S, 32] */
+  const uint8_t* mask_attn;  /* [B, 4, S, S] */
+  const uint8_t* mask_fc1;   /* [B, S, 64] */
+  double p_embed;            /* 0.2  (DROPOUT_RATE, model.py:80) */
+  double p_attn;             /* 0.2 */
+  double p_fc1;              /* 0.25 (model.py:149) */
+} afr_dropout;
+
+typedef enum afr_out_kind {
+  AFR_OUT_SHEET_F32 = 0, /* clamp(z,0,1) as fp32 [B,H,W]: what forward() returns, model.py:199-204 */
+  AFR_OUT_SHEET_U8 = 1,  /* (uint8)(clamp(z,0,1)*255), truncation: helpers.py:33 */
+  AFR_OUT_LOGITS_F32 = 2 /* z before the clamp (parity tests) */
+} afr_out_kind;
+
+typedef enum afr_target_kind {
+  AFR_TARGET_U8 = 0, /* 8-bit grey, compared as u8/255.0f exactly like helpers.py:121 */
+  AFR_TARGET_F32 = 1 /* fp32 in [0,1], the TensorDataset layout of helpers.py:177-181 */
+} afr_target_kind;
+
+int afr_abi_version(void);
+
+/* Lifetime. */
+int afr_create(const afr_config* cfg, afr_ctx** out);
+int afr_destroy(afr_ctx* ctx);
+const char* afr_last_error(const afr_ctx* ctx); /* ctx may be NULL: error of the last afr_create */
+
+/* Binding of caller-owned tensors. Replaces nothing in the reference: it is where
+ * model.parameters() / p.grad / optimizer.state (model.py:273) become raw pointers. */
+int afr_bind_params(afr_ctx* ctx, const afr_tensors* params);
+int afr_bind_grads(afr_ctx* ctx, const afr_tensors* grads);
+int afr_bind_adam_state(afr_ctx* ctx, const afr_tensors* exp_avg, const afr_tensors* exp_avg_sq);
+/* Rebuild the private bf16 copy of fc_output.weight from the fp32 master; call after the caller
+ * wrote the master itself (load_state_dict at helpers.py:101, a torch optimizer, init). */
+int afr_sync_shadow(afr_ctx* ctx, void* stream);
+
+/* Eval forward: model.py:158-204 under model.eval(), for validation (model.py:317-330) and
+ * render_strings (helpers.py:62-64), batched. tokens: int64 [B, token_stride], first S columns
+ * used, S <= max_length (positions >= S give zero features, model.py:190-193). */
+int afr_forward_eval(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
+                     void* out, int out_kind, void* stream);
+
+/* Fused training forward: model.py:299 + 304-306. Runs the forward, the clamp, the MSE partial
+ * sums and emits d(loss)/d(logits) internally. *loss_out (device fp32) = sum over the local batch
+ * of (y - t)^2 / loss_count; with loss_count = global_B * H * W the per-rank values add up to the
+ * reference's mean loss. targets: [B, H*W] of target_kind. */
+int afr_train_forward_loss(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
+                           const void* targets, int target_kind, const afr_dropout* dropout,
+                           double loss_count, float* loss_out, void* stream);
+/* Backward of fc_output w.r.t. its weight and bias (part of loss.backward(), model.py:309) for
+ * pixel rows [row_begin, row_end) -- row ranges let a data-parallel caller all-reduce finished
+ * buckets while later ones are still being computed. Overwrites the bound gradient rows. */
+int afr_train_wgrad(afr_ctx* ctx, int row_begin, int row_end, void* stream);
+/* Rest of loss.backward(): d(features) through fc_output, then fc1 / LayerNorm / attention /
+ * embedding backward into the ten small bound gradients (overwritten). */
+int afr_train_dgrad(afr_ctx* ctx, void* stream);
+/* Convenience: afr_train_forward_loss + afr_train_wgrad(0, H*W) + afr_train_dgrad. */
+int afr_train_step(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
+                   const void* targets, int target_kind, const afr_dropout* dropout,
+                   double loss_count, float* loss_out, void* stream);
+
+/* Generic (unfused-loss) training path, so that forward() stays differentiable for any loss the
+ * caller writes in PyTorch: forward keeps the logits, backward takes d(loss)/d(sheet) [B,H*W] fp32. */
+int afr_forward_train(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
+                      const afr_dropout* dropout, float* sheet_out, void* stream);
+int afr_backward(afr_ctx* ctx, const float* dsheet, void* stream);
+
+/* optimizer.step() of optim.AdamW (model.py:273,310), decoupled weight decay, torch's arithmetic.
+ * step is 1-based. The fc_output.weight sweep also refreshes the bf16 shadow.
+ * afr_adamw_rows updates fc_output.weight rows [row_begin,row_end) and the matching bias entries;
+ * afr_adamw_small the other ten tensors; afr_adamw_step both over everything. */
+int afr_adamw_step(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, void* stream);
+int afr_adamw_rows(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int64_t step, int row_begin, int row_end, void* stream);
+int afr_adamw_small(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int64_t step, void* stream);
+
+/* Synchronises the stream and reports AFR_ERR_TOKEN_RANGE if any token id seen since the last
+ * call was outside [0, vocab) (the reference fails with IndexError at model.py:167). */
+int afr_check_tokens(afr_ctx* ctx, void* stream);
+
+/* Introspection for tests and benches. which: 0 = features bf16 [B, 64*max_length],
+ * 1 = d(logits) residual bf16 [B, H*W] (unscaled (y-t)*mask), 2 = d(features) fp32,
+ * 3 = bf16 shadow of fc_output.weight, 4 = logits fp32 of the generic path. */
+int afr_workspace_ptr(afr_ctx* ctx, int which, void** ptr, size_t* bytes);
+/* Tile width (UMMA N) the three GEMMs will use for batch B: out[0..2] = forward, dgrad, wgrad. */
+int afr_gemm_tiles(afr_ctx* ctx, int B, int* out_bn3);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t afr_launch_count(const afr_ctx* ctx);
+
+/* Diagnostic: D[M,N] (fp32, ld = ldd) = alpha * A * B^T with bf16 operands on the tcgen05 path.
+ * a_mn_major / b_mn_major: operand stored [K, M] resp. [K, N] row-major instead of [M, K] / [N, K].
+ * Exists so the tensor-core kernel can be tested against a plain matmul in isolation. */
+int afr_gemm_bf16(int device, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                  int b_mn_major, float* D, int64_t ldd, int M, int N, int K, int tile_n, float alpha,
+                  int use_tma_store, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFR_SM100_H_ */
