@@ -465,10 +465,7 @@ int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps
   AFR_CUDA(c, launch_adamw(c->params.wout + off, c->grads.wout + off, c->m.wout + off,
                            c->v.wout + off, n, h, c->wshadow + off, c->num_sms, st),
            "adamw(fc_output.weight)");
-  SmallAdamJob job{c->params.bout + row_begin, c->grads.bout + row_begin, c->m.bout + row_begin,
-                   c->v.bout + row_begin, row_end - row_begin};
-  AFR_CUDA(c, launch_adamw_small(&job, 1, h, st), "adamw(fc_output.bias)");
-  c->launches += 2;
+  c->launches += 1;
   return AFR_OK;
 }
 
@@ -486,9 +483,10 @@ int afr_adamw_small(afr_ctx* c, double lr, double beta1, double beta2, double ep
   float* const* gg = reinterpret_cast<float* const*>(&c->grads);
   float* const* mm = reinterpret_cast<float* const*>(&c->m);
   float* const* vv = reinterpret_cast<float* const*>(&c->v);
-  SmallAdamJob jobs[10];
+  SmallAdamJob jobs[11];
   for (int i = 0; i < 10; ++i) jobs[i] = SmallAdamJob{pp[i], gg[i], mm[i], vv[i], sizes[i]};
-  AFR_CUDA(c, launch_adamw_small(jobs, 10, h, static_cast<cudaStream_t>(stream)), "adamw(small)");
+  jobs[10] = SmallAdamJob{c->params.bout, c->grads.bout, c->m.bout, c->v.bout, c->P};
+  AFR_CUDA(c, launch_adamw_small(jobs, 11, h, static_cast<cudaStream_t>(stream)), "adamw(small)");
   c->launches += 1;
   return AFR_OK;
 }
@@ -531,6 +529,20 @@ int afr_workspace_ptr(afr_ctx* c, int which, void** ptr, size_t* bytes) {
   return AFR_OK;
 }
 
+int afr_workspace_copy(afr_ctx* c, int which, void* dst, size_t bytes, void* stream) {
+  void* src = nullptr;
+  size_t avail = 0;
+  int rc = afr_workspace_ptr(c, which, &src, &avail);
+  if (rc) return rc;
+  if (dst == nullptr || src == nullptr || bytes > avail)
+    return fail(c, AFR_ERR_INVALID, "afr_workspace_copy: null pointer or size beyond the workspace");
+  DeviceGuard guard(c->cfg.device);
+  AFR_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)),
+           "cudaMemcpyAsync(workspace)");
+  return AFR_OK;
+}
+
 int afr_gemm_tiles(afr_ctx* c, int B, int* out) {
   if (!c || !out || B < 1) return AFR_ERR_INVALID;
   out[0] = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
@@ -540,6 +552,45 @@ int afr_gemm_tiles(afr_ctx* c, int B, int* out) {
 }
 
 int64_t afr_launch_count(const afr_ctx* c) { return c ? c->launches : 0; }
+
+int afr_debug_frontend_forward(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                               const afr_dropout* dropout, float* feats_f32, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  int rc = check_batch(c, B, S, tokens);
+  if (rc) return rc;
+  if (feats_f32 == nullptr) return fail(c, AFR_ERR_INVALID, "feats_f32 is NULL");
+  DeviceGuard guard(c->cfg.device);
+  AFR_CUDA(c, launch_frontend_forward(c->params, reinterpret_cast<const long long*>(tokens),
+                                      token_stride, B, S, c->cfg.max_length, c->cfg.vocab,
+                                      to_dropout(dropout), c->feats, c->num_sms,
+                                      static_cast<cudaStream_t>(stream), feats_f32),
+           "frontend_forward(debug)");
+  c->launches += 1;
+  return AFR_OK;
+}
+
+int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B,
+                                int S, const afr_dropout* dropout, const float* dfeat,
+                                void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  int rc = check_batch(c, B, S, tokens);
+  if (rc) return rc;
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  if (dfeat == nullptr) return fail(c, AFR_ERR_INVALID, "dfeat is NULL");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int grid = 0;
+  AFR_CUDA(c, launch_frontend_backward(c->params, reinterpret_cast<const long long*>(tokens),
+                                       token_stride, B, S, c->cfg.max_length, c->cfg.vocab,
+                                       to_dropout(dropout), dfeat, c->partials, c->num_sms, &grid,
+                                       c->num_sms, st),
+           "frontend_backward(debug)");
+  AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
+           "small_grad_reduce(debug)");
+  c->launches += 2;
+  return AFR_OK;
+}
 
 int afr_gemm_bf16(int device, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb,
                   int b_mn, float* D, int64_t ldd, int M, int N, int K, int tile_n, float alpha,

@@ -28,6 +28,7 @@ struct FrontArgs {
   uint32_t thr_e, thr_a, thr_f;   // keep iff u16 >= thr
   float inv_e, inv_a, inv_f;      // 1 / (1 - p)
   __nv_bfloat16* feats;           // forward
+  float* feats_f32;               // forward, optional fp32 copy (test hook)
   const float* dfeat;             // backward: [B, L*F]
   float* partials;                // backward: [grid, lay.total]
   SmallLayout lay;
@@ -328,9 +329,16 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(FrontArgs
       }
       out[s * kF + lane] = __float2bfloat16_rn(fa);
       out[s * kF + 32 + lane] = __float2bfloat16_rn(fb);
+      if (a.feats_f32 != nullptr) {
+        a.feats_f32[static_cast<long long>(b) * KF + s * kF + lane] = fa;
+        a.feats_f32[static_cast<long long>(b) * KF + s * kF + 32 + lane] = fb;
+      }
     }
     // zero features for positions >= S (model.py:190-193)
-    for (int i = S * kF + tid; i < KF; i += kThreads) out[i] = __float2bfloat16_rn(0.f);
+    for (int i = S * kF + tid; i < KF; i += kThreads) {
+      out[i] = __float2bfloat16_rn(0.f);
+      if (a.feats_f32 != nullptr) a.feats_f32[static_cast<long long>(b) * KF + i] = 0.f;
+    }
     __syncthreads();
   }
 }
@@ -726,13 +734,15 @@ size_t frontend_backward_smem_bytes(int L) { return static_cast<size_t>(make_sme
 
 cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, long long token_stride,
                                     int B, int S, int L, int vocab, const Dropout& drop,
-                                    __nv_bfloat16* feats, int num_sms, cudaStream_t stream) {
+                                    __nv_bfloat16* feats, int num_sms, cudaStream_t stream,
+                                    float* feats_f32) {
   if (S < 1 || S > L || L > kMaxL) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
   FrontArgs a{};
   a.w = w; a.tokens = tokens; a.token_stride = token_stride;
   a.B = B; a.S = S; a.L = L; a.vocab = vocab; a.drop = drop; a.feats = feats;
+  a.feats_f32 = feats_f32;
   a.err_flag = g_err_flag;
   fill_dropout(a);
   const size_t smem = static_cast<size_t>(make_smem(L, false).total) * 4;

@@ -1,0 +1,160 @@
+"""Data conventions of the hot path's callers (helpers.py:107-181, generate_font.ts:164-199) and
+the synthetic workloads bench.py / the tests use when the real FiraCode bitmaps are not on disk
+(bun + node-canvas cannot run offline).
+
+Everything here is host-side setup; the device-resident layout it produces is what the kernels
+consume: tokens int64 [N, Lmax] (0-padded) and targets uint8 [N, H, W] (255 = white).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+LCG_MUL, LCG_ADD, LCG_MOD = 1664525, 1013904223, 4294967296
+
+
+def seeded_text(seed: int, min_len: int = 10, max_len: int = 100) -> str:
+    """The string generate_font.ts produces for one sample (its LCG, word and space rules,
+    generate_font.ts:164-199). JS computes floor(seed / 2**32 * n) in doubles; seed < 2**32 and
+    n <= 91 make that exactly (seed * n) >> 32."""
+    state = seed
+
+    def draw(n: int) -> int:
+        nonlocal state
+        state = (state * LCG_MUL + LCG_ADD) % LCG_MOD
+        return (state * n) >> 32
+
+    remaining = draw(max_len - min_len + 1) + min_len
+    parts: List[str] = []
+    while remaining > 0:
+        wl = min(draw(10) + 1, remaining)
+        parts.append("".join(chr(65 + draw(26)) for _ in range(wl)))
+        remaining -= wl
+        if remaining > 0:
+            parts.append(" ")
+            remaining -= 1
+    return "".join(parts)
+
+
+def dataset_texts(n: int, first_seed: int = 42) -> List[str]:
+    """Line i of train_input/data.txt (generate_font.ts:203-216): seed = i + 42."""
+    return [seeded_text(first_seed + i) for i in range(n)]
+
+
+def encode(strings: Sequence[str], width: int) -> torch.Tensor:
+    """ord() per character, right-padded with 0 to `width` (helpers.py:57-59,163-177)."""
+    arr = np.zeros((len(strings), width), dtype=np.int64)
+    for i, s in enumerate(strings):
+        codes = np.frombuffer(s[:width].encode("latin-1", "replace"), dtype=np.uint8)
+        arr[i, : len(codes)] = codes
+    return torch.from_numpy(arr)
+
+
+def synthetic_sheets(strings: Sequence[str], height: int = 80, width: int = 240,
+                     seed: int = 1234) -> np.ndarray:
+    """uint8 [N,H,W] stand-ins for the FiraCode renders: white (255) with ~5 % ink at four grey
+    levels in the rows the wrapped text would occupy (33 chars/line, 14.4 px line pitch)."""
+    rng = np.random.default_rng(seed)
+    n = len(strings)
+    out = np.full((n, height, width), 255, dtype=np.uint8)
+    levels = np.array([0, 64, 128, 192], dtype=np.uint8)
+    for i, s in enumerate(strings):
+        rows = min(height, max(1, math.ceil(len(s) / 33) * 14))
+        ink = rng.random((rows, width)) < 0.05
+        vals = levels[rng.integers(0, 4, size=(rows, width))]
+        out[i, :rows][ink] = vals[ink]
+    return out
+
+
+def synthetic_batch(n: int, max_length: int = 100, height: int = 80, width: int = 240,
+                    seed: int = 1234, first_seed: int = 42) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(tokens int64 [n, max_length], targets uint8 [n, H, W]) -- the bench workload."""
+    texts = dataset_texts(n, first_seed)
+    return encode(texts, max_length), torch.from_numpy(synthetic_sheets(texts, height, width, seed))
+
+
+def fast_synthetic_batch(n: int, max_length: int = 100, height: int = 80, width: int = 240,
+                         seed: int = 1234) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Vectorised variant for large n (same distributions, different draws): lengths U{10..100},
+    letters A-Z with ~15 % spaces, 5 % ink in the text rows."""
+    g = torch.Generator().manual_seed(seed)
+    lengths = torch.randint(10, 101, (n,), generator=g).clamp(max=max_length)
+    letters = torch.randint(65, 91, (n, max_length), generator=g)
+    spaces = torch.rand((n, max_length), generator=g) < 0.148
+    tokens = torch.where(spaces, torch.full_like(letters, 32), letters)
+    pos = torch.arange(max_length).unsqueeze(0)
+    tokens = torch.where(pos < lengths.unsqueeze(1), tokens, torch.zeros_like(tokens))
+    rows = ((lengths + 32) // 33 * 14).clamp(max=height)
+    ink = torch.rand((n, height, width), generator=g) < 0.05
+    ink &= (torch.arange(height).view(1, height, 1) < rows.view(n, 1, 1))
+    vals = (torch.randint(0, 4, (n, height, width), generator=g) * 64).to(torch.uint8)
+    targets = torch.where(ink, vals, torch.full_like(vals, 255))
+    return tokens.long(), targets
+
+
+def targets_as_u8(targets: torch.Tensor):
+    """The TensorDataset of helpers.py:177-181 stores fp32 k/255 values (they came from 8-bit
+    bitmaps, helpers.py:118-121). Returns the lossless uint8 form, or None if some value is not
+    exactly k/255 (then the fp32 target path of the kernels is used)."""
+    if targets.dtype == torch.uint8:
+        return targets
+    q = torch.round(targets * 255.0)
+    back = q / 255.0
+    if torch.equal(back, targets) and float(q.min()) >= 0 and float(q.max()) <= 255:
+        return q.to(torch.uint8)
+    return None
+
+
+def read_bmp_grey(path: str) -> np.ndarray:
+    """24-bit (generate_font.ts:6-62: BGR, top-down when height < 0, rows padded to 4 bytes) or
+    8-bit palettised BMP -> uint8 grey [H,W] with PIL's convert('L') weights
+    (L = (R*19595 + G*38470 + B*7471 + 0x8000) >> 16)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] != b"BM":
+        raise ValueError(f"{path}: not a BMP file")
+    off = int.from_bytes(raw[10:14], "little")
+    w = int.from_bytes(raw[18:22], "little", signed=True)
+    h = int.from_bytes(raw[22:26], "little", signed=True)
+    bpp = int.from_bytes(raw[28:30], "little")
+    top_down = h < 0
+    h = abs(h)
+    if bpp == 24:
+        stride = (w * 3 + 3) & ~3
+        px = np.frombuffer(raw, dtype=np.uint8, count=stride * h, offset=off).reshape(h, stride)
+        bgr = px[:, : w * 3].reshape(h, w, 3).astype(np.uint32)
+        grey = (bgr[..., 2] * 19595 + bgr[..., 1] * 38470 + bgr[..., 0] * 7471 + 0x8000) >> 16
+        grey = grey.astype(np.uint8)
+    elif bpp == 8:
+        stride = (w + 3) & ~3
+        pal = np.frombuffer(raw, dtype=np.uint8, count=256 * 4, offset=54).reshape(256, 4).astype(np.uint32)
+        lut = ((pal[:, 2] * 19595 + pal[:, 1] * 38470 + pal[:, 0] * 7471 + 0x8000) >> 16).astype(np.uint8)
+        idx = np.frombuffer(raw, dtype=np.uint8, count=stride * h, offset=off).reshape(h, stride)[:, :w]
+        grey = lut[idx]
+    else:
+        raise ValueError(f"{path}: unsupported BMP depth {bpp}")
+    return grey if top_down else grey[::-1].copy()
+
+
+def load_string_dataset_u8(data_dir: str = "train_input", num_samples: int = 50000,
+                           sheet_height: int = 80, sheet_width: int = 240):
+    """Same inputs and errors as helpers.py:125-181, but keeps the lossless uint8 sheets
+    (2.9 GB for 150k samples instead of 11.5 GB fp32). Returns (tokens int64 [N,Lmax], uint8 [N,H,W])."""
+    strings_path = os.path.join(data_dir, "data.txt")
+    with open(strings_path, "r") as f:
+        strings = f.read().splitlines()
+    if len(strings) < num_samples:
+        raise ValueError(f"Not enough strings in {strings_path}. Expected {num_samples}, got {len(strings)}")
+    targets = np.zeros((num_samples, sheet_height, sheet_width), dtype=np.uint8)
+    for i in range(num_samples):
+        image_path = os.path.join(data_dir, f"{i + 1}.bmp")
+        if not os.path.exists(image_path):
+            raise FileNotFoundError(f"Image file not found: {image_path}")
+        targets[i] = read_bmp_grey(image_path)
+    strings = strings[:num_samples]
+    max_len = max(len(s) for s in strings)
+    return encode(strings, max_len), torch.from_numpy(targets)

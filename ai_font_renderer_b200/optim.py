@@ -1,0 +1,96 @@
+"""Fused AdamW for the renderer: one HBM pass per tensor (p, g, m, v read; p, m, v + the bf16
+shadow of fc_output.weight written) in libafr_sm100.so instead of torch's multi-pass foreach
+implementation. Reference: optim.AdamW(model.parameters(), lr, weight_decay, betas=(0.9, 0.99))
+at model.py:273 and optimizer.step() at model.py:310.
+
+It is a torch.optim.Optimizer, so ReduceLROnPlateau (model.py:276-278,337) drives its
+param_groups[0]['lr'] unchanged, and its state uses torch's own keys (step / exp_avg /
+exp_avg_sq).
+"""
+from __future__ import annotations
+
+import torch
+
+from .renderer import AttentionFontRenderer, _stream_ptr
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, model: AttentionFontRenderer, lr: float = 1e-3, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-2):
+        if not isinstance(model, AttentionFontRenderer):
+            raise TypeError("FusedAdamW is bound to an ai_font_renderer_b200.AttentionFontRenderer")
+        if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
+            raise ValueError("invalid AdamW hyper-parameter")
+        self.model = model
+        super().__init__(model._ordered_params(), dict(lr=lr, betas=betas, eps=eps,
+                                                       weight_decay=weight_decay))
+
+    def _ensure_state(self):
+        params = self.model._ordered_params()
+        for p in params:
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+        return params
+
+    def _bind(self):
+        params = self._ensure_state()
+        model = self.model
+        ctx = model._context(1, training=True)
+        ctx.bind_grads(model._param_grads())
+        ctx.bind_adam_state([self.state[p]["exp_avg"] for p in params],
+                            [self.state[p]["exp_avg_sq"] for p in params])
+        return ctx, params
+
+    def _hyper(self):
+        g = self.param_groups[0]
+        return (float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                float(g["weight_decay"]))
+
+    def _next_step(self, params) -> int:
+        return int(self.state[params[0]]["step"].item()) + 1
+
+    def _advance(self, params):
+        for p in params:
+            self.state[p]["step"] += 1
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        ctx, params = self._bind()
+        t = self._next_step(params)
+        ctx.check(ctx.lib.afr_adamw_step(ctx.handle, *self._hyper(), t, _stream_ptr(ctx.device)))
+        self._advance(params)
+        return loss
+
+    # Row-bucketed form used by the data-parallel trainer: bucket b's all-reduce overlaps the
+    # AdamW sweep of bucket b-1. Call begin_step(), any number of step_rows(), step_small(), end_step().
+    @torch.no_grad()
+    def begin_step(self):
+        self._bucket = self._bind()
+        return self._next_step(self._bucket[1])
+
+    @torch.no_grad()
+    def step_rows(self, t: int, row_begin: int, row_end: int):
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_adamw_rows(ctx.handle, *self._hyper(), t, row_begin, row_end,
+                                         _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
+    def step_small(self, t: int):
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_adamw_small(ctx.handle, *self._hyper(), t, _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
+    def end_step(self):
+        self._advance(self._bucket[1])
+        self._bucket = None
+
+    def zero_grad(self, set_to_none: bool = False):
+        """The fused backward overwrites every gradient, so the trainer never needs this; it is
+        kept with in-place semantics (the gradient buffers stay bound to the library)."""
+        for p in self.model._ordered_params():
+            if p.grad is not None:
+                p.grad.zero_()

@@ -1,0 +1,319 @@
+"""Training driver around the fused step (reference: train_attention_model, model.py:209-384).
+
+The reference's per-batch body `zero_grad -> model(x) -> mse_loss -> backward -> step`
+(model.py:291-311) becomes `fused_forward_loss -> fused_backward -> FusedAdamW`, the dataset
+lives on the device (uint8 sheets, 2.9 GB for 150k samples) and batches are gathered there, but
+everything that decides WHAT is computed is kept: the 80/20 random_split with seed 42, the shared
+loader generator (so batch composition and order equal the reference's), unweighted epoch means,
+ReduceLROnPlateau, early stopping with its shallow-copy "best state", the files written.
+
+Data parallel (one process per GPU, torch.distributed/NCCL): every rank walks the same global
+batch order and takes a contiguous slice of each batch; the loss is normalised by the GLOBAL
+batch so per-rank gradients just add; fc_output.weight.grad is all-reduced in row buckets that
+are launched as soon as the bucket's wgrad GEMM is enqueued and overlap the rest of backward;
+AdamW runs bucket by bucket as the reductions land.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.utils.data as tud
+
+from .data import targets_as_u8
+from .optim import FusedAdamW
+from .render import render_strings
+
+
+@dataclass
+class TrainConfig:
+    """Hyper-parameters; defaults are the reference's module constants (model.py:64-93)."""
+    output_dir: str = ""
+    num_epochs: int = 10000
+    learning_rate: float = 0.001
+    early_stopping_patience: int = 70
+    validation_split: float = 0.2
+    weight_decay: float = 0.0005
+    embedding_dim: int = 32
+    dropout_rate: float = 0.2
+    num_attention_heads: int = 4
+    scheduler_patience: int = 20
+    scheduler_factor: float = 0.7
+    min_learning_rate: float = 1e-6
+    seed: int = 42
+    sheet_height: int = 80
+    sheet_width: int = 240
+    max_chars_per_sheet: int = 100
+    num_samples: int = 150000
+    betas: Tuple[float, float] = (0.9, 0.99)
+    test_strings: Sequence[str] = field(default_factory=list)
+    render_every: int = 5
+    grad_buckets: int = 8            # row buckets of fc_output.weight.grad (data parallel overlap)
+    max_steps: Optional[int] = None  # stop after this many optimizer steps (tests / smoke)
+    quiet: bool = False
+
+
+class _Indices(tud.Dataset):
+    """Index-only stand-in for the TensorDataset: the DataLoader / random_split machinery of torch
+    decides the order (model.py:239-266), the gather happens on the device."""
+
+    def __init__(self, n: int):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return int(i)
+
+    def __getitems__(self, idxs):
+        return [int(i) for i in idxs]
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of a global batch of n samples owned by `rank`."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
+    """Split fc_output's P rows into <= n buckets whose bounds are multiples of 128."""
+    n = max(1, n)
+    tiles = (P + 127) // 128
+    per = (tiles + n - 1) // n
+    out, lo = [], 0
+    while lo < P:
+        hi = min(P, lo + per * 128)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class Trainer:
+    def __init__(self, model, tokens: torch.Tensor, targets: torch.Tensor, batch_size: int,
+                 cfg: TrainConfig, device: torch.device):
+        self.model, self.cfg, self.device, self.batch_size = model, cfg, device, batch_size
+        self.rank, self.world = _world()
+        u8 = targets_as_u8(targets)
+        self.targets = (u8 if u8 is not None else targets.float()).to(device).contiguous()
+        self.tokens = tokens.long().to(device).contiguous()
+        n = tokens.shape[0]
+        # model.py:232-242
+        val_size = int(cfg.validation_split * n)
+        train_size = n - val_size
+        self.train_size, self.val_size = train_size, val_size
+        index_ds = _Indices(n)
+        train_ds, val_ds = tud.random_split(index_ds, [train_size, val_size],
+                                            generator=torch.Generator().manual_seed(cfg.seed))
+        # model.py:245-266: ONE generator shared by both loaders (its stream fixes the batch order)
+        g = torch.Generator()
+        g.manual_seed(cfg.seed)
+        self.train_loader = tud.DataLoader(train_ds, batch_size=batch_size, shuffle=True, generator=g,
+                                           num_workers=0)
+        self.val_loader = tud.DataLoader(val_ds, batch_size=batch_size, shuffle=False, generator=g,
+                                         num_workers=0)
+        self.optimizer = FusedAdamW(model, lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
+                                    betas=cfg.betas)                                  # model.py:273
+        self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(
+            self.optimizer, mode="min", factor=cfg.scheduler_factor,
+            patience=cfg.scheduler_patience, min_lr=cfg.min_learning_rate)            # model.py:276-278
+        self.P = cfg.sheet_height * cfg.sheet_width
+        self.buckets = row_buckets(self.P, cfg.grad_buckets if self.world > 1 else 1)
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------ one optimizer step
+    def train_batch(self, idx: torch.Tensor, loss_slot: torch.Tensor):
+        """model.py:292-311 for one global batch given by dataset indices `idx` (host int64)."""
+        model = self.model
+        gB = idx.numel()
+        lo, hi = shard_bounds(gB, self.rank, self.world)
+        local = idx[lo:hi].to(self.device, non_blocking=True)
+        x = self.tokens.index_select(0, local)
+        t = self.targets.index_select(0, local)
+        count = float(gB) * self.P
+        if hi > lo:
+            model.fused_forward_loss(x, t, loss_count=count, sample_offset=lo, loss_out=loss_slot)
+        else:   # this rank has no sample of a ragged last batch: contribute zeros
+            loss_slot.zero_()
+            for p in model._ordered_params():
+                if p.grad is not None:
+                    p.grad.zero_()
+        if self.world == 1:
+            model.fused_backward()
+            self.optimizer.step()
+        else:
+            model._param_grads()
+            wgrad = model.fc_output.weight.grad
+            works = []
+
+            def reduce_bucket(i, r0, r1):
+                # enqueued on NCCL's stream behind this bucket's wgrad GEMM; runs concurrently with
+                # the later buckets, the dgrad GEMM and the front-end backward
+                works.append(dist.all_reduce(wgrad[r0:r1], op=dist.ReduceOp.SUM, async_op=True))
+
+            if hi > lo:
+                model.fused_backward(self.buckets, reduce_bucket)
+            else:
+                for i, (r0, r1) in enumerate(self.buckets):
+                    reduce_bucket(i, r0, r1)
+            small = dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM, async_op=True)
+            t_step = self.optimizer.begin_step()
+            for w, (r0, r1) in zip(works, self.buckets):
+                w.wait()                                   # stream-level wait, no host sync on NCCL
+                self.optimizer.step_rows(t_step, r0, r1)   # overlaps the next bucket's all-reduce
+            small.wait()
+            self.optimizer.step_small(t_step)
+            self.optimizer.end_step()
+        self.steps_done += 1
+
+    @torch.no_grad()
+    def eval_batch(self, idx: torch.Tensor, loss_slot: torch.Tensor):
+        """model.py:318-330: eval forward + mse_loss for one global validation batch."""
+        model = self.model
+        gB = idx.numel()
+        lo, hi = shard_bounds(gB, self.rank, self.world)
+        if hi <= lo:
+            loss_slot.zero_()
+            return
+        local = idx[lo:hi].to(self.device, non_blocking=True)
+        x = self.tokens.index_select(0, local)
+        t = self.targets.index_select(0, local)
+        # eval forward + MSE in the fused GEMM epilogue (model.eval() => dropout off)
+        model.fused_forward_loss(x, t, loss_count=float(gB) * self.P, dropout=False,
+                                 loss_out=loss_slot)
+
+    def _epoch_losses(self, slots: torch.Tensor, n: int) -> float:
+        """Sum of the per-batch mean losses, added on the host in batch order in double precision
+        like `total += loss.item()` (model.py:311,330)."""
+        v = slots[:n].clone()
+        if self.world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        total = 0.0
+        for x in v.cpu().tolist():
+            total += x
+        return total
+
+    # ------------------------------------------------------------------ the run
+    def fit(self):
+        cfg, model = self.cfg, self.model
+        say = (lambda *a: None) if (cfg.quiet or self.rank != 0) else print
+        if self.rank == 0 and cfg.output_dir:
+            self._write_config()
+        say(f"Dataset split: {self.train_size} training samples, {self.val_size} validation samples")
+        best_val_loss = float("inf")
+        patience_counter = 0
+        best_model_state = None
+        n_train, n_val = len(self.train_loader), len(self.val_loader)
+        slots = torch.zeros(max(n_train, n_val, 1), dtype=torch.float32, device=self.device)
+        history = []
+        epoch = -1
+        for epoch in range(cfg.num_epochs):
+            model.train()
+            for i, idx in enumerate(self.train_loader):
+                self.train_batch(idx, slots[i])
+                if cfg.max_steps is not None and self.steps_done >= cfg.max_steps:
+                    n_train_done = i + 1
+                    break
+            else:
+                n_train_done = n_train
+            model.check_tokens_in_range()
+            total_train_loss = self._epoch_losses(slots, n_train_done)
+            model.eval()
+            for i, idx in enumerate(self.val_loader):
+                self.eval_batch(idx, slots[i])
+            total_val_loss = self._epoch_losses(slots, n_val)
+            avg_train_loss = total_train_loss / n_train_done            # model.py:333-334
+            avg_val_loss = total_val_loss / max(n_val, 1)
+            history.append((avg_train_loss, avg_val_loss))
+            self.scheduler.step(avg_val_loss)                           # model.py:337
+            is_best = avg_val_loss < best_val_loss                      # model.py:340-346
+            if is_best:
+                best_val_loss = avg_val_loss
+                patience_counter = 0
+                best_model_state = model.state_dict().copy()   # shallow, as in the reference
+            else:
+                patience_counter += 1
+            lr_now = self.optimizer.param_groups[0]["lr"]
+            if epoch % cfg.render_every == 0:                           # model.py:349-360
+                status = (f"Epoch {epoch}, Train Loss: {avg_train_loss:.6f}, "
+                          f"Val Loss: {avg_val_loss:.6f}, LR: {lr_now:.6f}")
+                if is_best:
+                    status += " (New Best)"
+                say(status)
+                if self.rank == 0 and cfg.output_dir and cfg.test_strings:
+                    render_strings(model, cfg.test_strings, output_dir=f"{cfg.output_dir}/epoch_{epoch}",
+                                   sheet_height=cfg.sheet_height, sheet_width=cfg.sheet_width,
+                                   device=self.device)
+            elif is_best:
+                say(f"Epoch {epoch}, New best validation loss: {avg_val_loss:.6f}")
+            if patience_counter >= cfg.early_stopping_patience:         # model.py:362-366
+                say(f"Early stopping at epoch {epoch}, Best Val Loss: {best_val_loss:.6f}")
+                model.load_state_dict(best_model_state)
+                break
+            if cfg.max_steps is not None and self.steps_done >= cfg.max_steps:
+                break
+        if best_model_state is not None and patience_counter < cfg.early_stopping_patience:
+            model.load_state_dict(best_model_state)                     # model.py:369-371
+            say(f"Training completed, Best Val Loss: {best_val_loss:.6f}")
+        if self.rank == 0 and cfg.output_dir:
+            final_epoch = epoch + 1 if patience_counter < cfg.early_stopping_patience else epoch
+            self._write_results(final_epoch, best_val_loss, patience_counter)
+        self.history = history
+        return model
+
+    def _write_config(self):
+        cfg = self.cfg
+        os.makedirs(cfg.output_dir, exist_ok=True)
+        rows = [("num_epochs", cfg.num_epochs), ("learning_rate", cfg.learning_rate),
+                ("batch_size", self.batch_size),
+                ("early_stopping_patience", cfg.early_stopping_patience),
+                ("validation_split", cfg.validation_split), ("weight_decay", cfg.weight_decay),
+                ("embedding_dim", cfg.embedding_dim), ("dropout_rate", cfg.dropout_rate),
+                ("num_attention_heads", cfg.num_attention_heads),
+                ("max_length", self.model.max_length),
+                ("max_chars_per_sheet", cfg.max_chars_per_sheet), ("num_samples", cfg.num_samples),
+                ("data_size", self.tokens.shape[0]), ("random_seed", cfg.seed),
+                ("sheet_height", cfg.sheet_height), ("sheet_width", cfg.sheet_width)]
+        with open(f"{cfg.output_dir}/config.txt", "w") as f:
+            f.write("# Training configuration\n")
+            for k, v in rows:
+                f.write(f"{k} = {v}\n")
+
+    def _write_results(self, final_epoch, best_val_loss, patience_counter):
+        cfg = self.cfg
+        stopped = patience_counter >= cfg.early_stopping_patience
+        with open(f"{cfg.output_dir}/training_results.txt", "w") as f:
+            f.write("# Training Results\n")
+            f.write(f"final_epoch = {final_epoch}\n")
+            f.write(f"best_validation_loss = {best_val_loss:.6f}\n")
+            f.write(f"final_learning_rate = {self.optimizer.param_groups[0]['lr']:.6f}\n")
+            f.write(f"early_stopped = {stopped}\n")
+            f.write(f"training_duration_epochs = {final_epoch}\n")
+            f.write(f"training_completed = {datetime.datetime.now().strftime('%Y-%m-%d %H:%M:%S')}\n")
+
+
+def train_attention_model(model, dataset, batch_size, cfg: Optional[TrainConfig] = None,
+                          device: Optional[torch.device] = None):
+    """Same call as model.py:209: `dataset` is the TensorDataset(int64 [N,L], fp32 [N,H,W]) that
+    helpers.load_string_dataset returns (or any (tokens, targets) pair)."""
+    cfg = cfg or TrainConfig()
+    if isinstance(dataset, tud.TensorDataset):
+        tokens, targets = dataset.tensors
+    else:
+        tokens, targets = dataset
+    device = device or next(model.parameters()).device
+    trainer = Trainer(model, tokens, targets, batch_size, cfg, device)
+    trainer.fit()
+    model._trainer = trainer
+    return model

@@ -149,8 +149,8 @@ int afr_backward(afr_ctx* ctx, const float* dsheet, void* stream);
 
 /* optimizer.step() of optim.AdamW (model.py:273,310), decoupled weight decay, torch's arithmetic.
  * step is 1-based. The fc_output.weight sweep also refreshes the bf16 shadow.
- * afr_adamw_rows updates fc_output.weight rows [row_begin,row_end) and the matching bias entries;
- * afr_adamw_small the other ten tensors; afr_adamw_step both over everything. */
+ * afr_adamw_rows updates fc_output.weight rows [row_begin,row_end); afr_adamw_small the other
+ * eleven tensors (fc_output.bias included); afr_adamw_step both, over everything. */
 int afr_adamw_step(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, void* stream);
 int afr_adamw_rows(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
@@ -166,10 +166,21 @@ int afr_check_tokens(afr_ctx* ctx, void* stream);
  * 1 = d(logits) residual bf16 [B, H*W] (unscaled (y-t)*mask), 2 = d(features) fp32,
  * 3 = bf16 shadow of fc_output.weight, 4 = logits fp32 of the generic path. */
 int afr_workspace_ptr(afr_ctx* ctx, int which, void** ptr, size_t* bytes);
+/* Device-to-device copy of the first `bytes` bytes of that workspace into caller memory. */
+int afr_workspace_copy(afr_ctx* ctx, int which, void* dst, size_t bytes, void* stream);
 /* Tile width (UMMA N) the three GEMMs will use for batch B: out[0..2] = forward, dgrad, wgrad. */
 int afr_gemm_tiles(afr_ctx* ctx, int B, int* out_bn3);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t afr_launch_count(const afr_ctx* ctx);
+
+/* Test hooks: the fp32 front-end (embedding / attention / LayerNorm / fc1, model.py:167-193) in
+ * isolation, so its forward and backward can be checked at fp32 tolerance without the bf16 GEMM
+ * in between. Forward writes the features as fp32 [B, 64*max_length]; backward takes
+ * d(loss)/d(features) fp32 [B, 64*max_length] and overwrites the ten small bound gradients. */
+int afr_debug_frontend_forward(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B,
+                               int S, const afr_dropout* dropout, float* feats_f32, void* stream);
+int afr_debug_frontend_backward(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B,
+                                int S, const afr_dropout* dropout, const float* dfeat, void* stream);
 
 /* Diagnostic: D[M,N] (fp32, ld = ldd) = alpha * A * B^T with bf16 operands on the tcgen05 path.
  * a_mn_major / b_mn_major: operand stored [K, M] resp. [K, N] row-major instead of [M, K] / [N, K].

@@ -163,22 +163,62 @@ def targets_to_f32(targets_u8) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- loss / backward
+class _Bf16OutputLayerLoss(torch.autograd.Function):
+    """fc_output + clamp + MSE with the GEMM operands rounded to bf16 (fp32 accumulation), i.e.
+    the arithmetic the B200 kernels declare: Z = bf16(A) bf16(W)^T + b;  dZ = bf16((y-t)*mask);
+    dA = s*dZ bf16(W);  dW = s*dZ^T bf16(A);  db = s*sum_b dZ  with s = 2/count. Used to pin the
+    CUDA implementation tightly; the fp32 path above stays the parity target."""
+
+    @staticmethod
+    def forward(ctx, feats, w, b, t, count):
+        fb = feats.to(torch.bfloat16).float()
+        wb = w.to(torch.bfloat16).float()
+        z = fb @ wb.t() + b
+        y = torch.clamp(z, 0.0, 1.0)
+        d = y - t
+        resid = (d * ((z >= 0) & (z <= 1))).to(torch.bfloat16).float()
+        ctx.save_for_backward(fb, wb, resid)
+        ctx.count = count
+        ctx.mark_non_differentiable(z)
+        return (d * d).sum() / count, z
+
+    @staticmethod
+    def backward(ctx, gl, _gz):
+        fb, wb, resid = ctx.saved_tensors
+        s = gl * (2.0 / ctx.count)
+        return s * (resid @ wb), s * (resid.t() @ fb), s * resid.sum(0), None, None
+
+
 def loss_and_grads(state, tokens, targets_f32, cfg: OracleConfig, masks=None,
-                   loss_count: Optional[float] = None):
+                   loss_count: Optional[float] = None, emulate_bf16: bool = False):
     """mse_loss(model(x), t) (model.py:270,304-306) and loss.backward() (model.py:309).
     loss_count overrides the mean's denominator (data-parallel shards pass global_B*H*W).
+    emulate_bf16 rounds the three GEMMs' operands to bf16 like the kernels do.
     Returns (loss, grads dict, logits)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in state.items()}
-    z = logits(params, tokens, cfg, masks)
-    y = torch.clamp(z, 0.0, 1.0).view(-1, cfg.sheet_h, cfg.sheet_w)
-    t = targets_f32.view(y.shape)
-    if loss_count is None:
-        loss = F.mse_loss(y, t)
+    if emulate_bf16:
+        feats = features(params, tokens, cfg, masks)
+        t = targets_f32.reshape(feats.shape[0], -1)
+        count = float(loss_count) if loss_count is not None else float(t.numel())
+        loss, z = _Bf16OutputLayerLoss.apply(feats, params["fc_output.weight"],
+                                             params["fc_output.bias"], t, count)
     else:
-        loss = ((y - t) ** 2).sum() / loss_count
+        z = logits(params, tokens, cfg, masks)
+        y = torch.clamp(z, 0.0, 1.0).view(-1, cfg.sheet_h, cfg.sheet_w)
+        t = targets_f32.view(y.shape)
+        if loss_count is None:
+            loss = F.mse_loss(y, t)
+        else:
+            loss = ((y - t) ** 2).sum() / loss_count
     loss.backward()
     grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
     return loss.detach(), grads, z.detach()
+
+
+def logits_bf16(state, tokens, cfg: OracleConfig, masks=None) -> torch.Tensor:
+    """logits() with the GEMM operands rounded to bf16 (see _Bf16OutputLayerLoss)."""
+    feats = features(state, tokens, cfg, masks).to(torch.bfloat16).float()
+    return feats @ state["fc_output.weight"].to(torch.bfloat16).float().t() + state["fc_output.bias"]
 
 
 # --------------------------------------------------------------------------- AdamW

@@ -1,0 +1,212 @@
+"""CPU: host-side logic of the drop-in surface (no kernels are executed here)."""
+import io
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.utils.data as tud
+
+from conftest import REPO, load_npz
+from oracle import afr_oracle as orc
+
+
+def test_lcg_text_known_answers():
+    from ai_font_renderer_b200.data import dataset_texts, seeded_text
+    lcg = load_npz("lcg.npz")
+    texts = dataset_texts(2000)
+    assert texts[0] == "P JAL WZ MQWPCDYYX EOGYVE MBANVV"          # SURVEY.md section 4 KATs
+    assert texts[1] == "GG U AJBHEQVVO ZFU TFI G PHRPSUL"
+    assert texts[2] == "YHS IYXCTW TBALZN YHXKESJ CHFW BM"
+    assert [str(s) for s in lcg["first"]] == texts[:16]
+    assert np.array_equal(np.array([len(t) for t in texts]), lcg["lengths"])
+    assert texts == orc.dataset_strings(2000)
+    for t in texts[:200]:
+        assert 10 <= len(t) <= 100 and set(t) <= set("ABCDEFGHIJKLMNOPQRSTUVWXYZ ")
+        assert not t.startswith(" ") and "  " not in t
+    assert seeded_text(42) == texts[0]
+
+
+def test_encode_matches_reference_padding():
+    from ai_font_renderer_b200.data import encode
+    from ai_font_renderer_b200.render import strings_to_tokens
+    t = encode(["AB C", "", "Z" * 7], 5)
+    assert t.dtype == torch.int64 and t.tolist() == [[65, 66, 32, 67, 0], [0] * 5, [90] * 5]
+    assert torch.equal(strings_to_tokens(["HELLO"], 8), torch.tensor([[72, 69, 76, 76, 79, 0, 0, 0]]))
+    assert torch.equal(encode(["AB C"], 5), orc.encode_strings(["AB C"], 5))
+
+
+def test_bmp_writer_is_byte_identical_to_pil_and_reader_round_trips(tmp_path):
+    from PIL import Image
+    from ai_font_renderer_b200.data import read_bmp_grey
+    from ai_font_renderer_b200.render import grey_bmp_bytes
+    rng = np.random.default_rng(0)
+    for shape in ((80, 240), (7, 13), (1, 1), (64, 64)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        buf = io.BytesIO()
+        Image.fromarray(img).save(buf, "BMP")                      # helpers.py:36,42
+        mine = grey_bmp_bytes(img)
+        assert mine == buf.getvalue()
+        p = tmp_path / "x.bmp"
+        p.write_bytes(mine)
+        assert np.array_equal(read_bmp_grey(str(p)), img)
+    assert len(grey_bmp_bytes(np.zeros((80, 240), np.uint8))) == 20278
+
+
+def test_reader_decodes_generate_font_ts_layout(tmp_path):
+    """24-bit, BGR, top-down (negative height), rows padded to 4 bytes (generate_font.ts:6-62)."""
+    from PIL import Image
+    from ai_font_renderer_b200.data import read_bmp_grey
+    import helpers
+    rng = np.random.default_rng(1)
+    h, w = 5, 7
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    stride = (w * 3 + 3) & ~3
+    rows = np.zeros((h, stride), np.uint8)
+    rows[:, : w * 3] = rgb[:, :, ::-1].reshape(h, w * 3)
+    header = b"BM" + (54 + stride * h).to_bytes(4, "little") + bytes(4) + (54).to_bytes(4, "little")
+    info = (40).to_bytes(4, "little") + w.to_bytes(4, "little") + (-h).to_bytes(4, "little", signed=True) \
+        + (1).to_bytes(2, "little") + (24).to_bytes(2, "little") + bytes(24)
+    p = tmp_path / "1.bmp"
+    p.write_bytes(header + info + rows.tobytes())
+    want = np.array(Image.open(str(p)).convert("L"))                 # helpers.py:118
+    assert np.array_equal(read_bmp_grey(str(p)), want)
+    assert np.array_equal(helpers.image_to_binary_array(str(p)), want.astype(np.float32) / 255.0)
+
+
+def test_load_string_dataset_conventions_and_errors(tmp_path):
+    import helpers
+    from ai_font_renderer_b200.render import grey_bmp_bytes
+    d = tmp_path / "train_input"
+    d.mkdir()
+    texts = ["AB", "HELLO WORLD", "XYZ"]
+    (d / "data.txt").write_text("\n".join(texts))
+    rng = np.random.default_rng(2)
+    imgs = rng.integers(0, 256, (3, 8, 32), dtype=np.uint8)
+    for i in range(3):
+        (d / f"{i + 1}.bmp").write_bytes(grey_bmp_bytes(imgs[i]))    # 1-based file names
+    ds = helpers.load_string_dataset(str(d), 3, 8, 32)
+    tok, tgt = ds.tensors
+    assert tok.shape == (3, 11) and tok.dtype == torch.int64 and tok[0].tolist() == [65, 66] + [0] * 9
+    assert np.array_equal(tgt.numpy(), imgs)
+    with pytest.raises(ValueError):
+        helpers.load_string_dataset(str(d), 4, 8, 32)
+    os.remove(d / "2.bmp")
+    with pytest.raises(FileNotFoundError):
+        helpers.load_string_dataset(str(d), 3, 8, 32)
+
+
+def test_targets_as_u8_is_lossless_or_declines():
+    from ai_font_renderer_b200.data import targets_as_u8
+    u = torch.randint(0, 256, (4, 8, 32), dtype=torch.uint8)
+    f = torch.from_numpy(u.numpy().astype(np.float32) / 255.0)        # helpers.py:121
+    assert torch.equal(targets_as_u8(f), u)
+    assert targets_as_u8(f + 1e-4) is None
+
+
+def test_state_dict_layout_is_the_references():
+    from ai_font_renderer_b200.renderer import AttentionFontRenderer
+    from ai_font_renderer_b200 import _lib
+    m = AttentionFontRenderer()
+    sd = m.state_dict()
+    assert tuple(sd.keys()) == _lib.STATE_DICT_KEYS == orc.STATE_KEYS
+    shapes = {k: tuple(v.shape) for k, v in sd.items()}
+    assert shapes == {
+        "positional_encoding": (100, 32), "embedding.weight": (128, 32),
+        "attention.in_proj_weight": (96, 32), "attention.in_proj_bias": (96,),
+        "attention.out_proj.weight": (32, 32), "attention.out_proj.bias": (32,),
+        "layer_norm.weight": (32,), "layer_norm.bias": (32,), "fc1.weight": (64, 32),
+        "fc1.bias": (64,), "fc_output.weight": (19200, 6400), "fc_output.bias": (19200,)}
+    assert sum(v.numel() for v in sd.values()) == 122912896
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    assert m.max_length == 100
+
+
+def test_checkpoint_round_trip(tmp_path):
+    import helpers
+    from ai_font_renderer_b200.renderer import AttentionFontRenderer
+    cls = lambda max_length: AttentionFontRenderer(max_length=max_length, sheet_height=8, sheet_width=32)
+    torch.manual_seed(5)
+    m = cls(12)
+    path = str(tmp_path / helpers.MODEL_FILENAME)
+    helpers.save_model(m, path)
+    loaded = helpers.load_model(cls, 12, filename=path)
+    assert not loaded.training
+    for (k, a), (_, b) in zip(m.state_dict().items(), loaded.state_dict().items()):
+        assert torch.equal(a, b), k
+    raw = torch.load(path)
+    assert tuple(raw.keys()) == orc.STATE_KEYS
+
+
+def test_cpu_inputs_fail_loudly_no_fallback():
+    from ai_font_renderer_b200.renderer import AttentionFontRenderer
+    m = AttentionFontRenderer(max_length=12, sheet_height=8, sheet_width=32).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros((1, 12), dtype=torch.long))
+
+
+def test_batch_order_equals_reference_loaders():
+    """The index-only DataLoader walks the same batches as the reference's TensorDataset loaders
+    (model.py:239-266): same split, same shuffles, shared generator consumed in the same order."""
+    from ai_font_renderer_b200.training import _Indices
+    n, bs, seed = 1000, 64, 42
+    tokens = torch.arange(n).view(n, 1)
+    ds = tud.TensorDataset(tokens, torch.zeros(n, 1))
+    tr, va = tud.random_split(ds, [800, 200], generator=torch.Generator().manual_seed(seed))
+    g = torch.Generator(); g.manual_seed(seed)
+    ref_train = tud.DataLoader(tr, batch_size=bs, shuffle=True, generator=g, num_workers=2)
+    ref_val = tud.DataLoader(va, batch_size=bs, shuffle=False, generator=g, num_workers=2)
+    tr2, va2 = tud.random_split(_Indices(n), [800, 200], generator=torch.Generator().manual_seed(seed))
+    g2 = torch.Generator(); g2.manual_seed(seed)
+    my_train = tud.DataLoader(tr2, batch_size=bs, shuffle=True, generator=g2, num_workers=0)
+    my_val = tud.DataLoader(va2, batch_size=bs, shuffle=False, generator=g2, num_workers=0)
+    for _epoch in range(3):
+        for (x, _), idx in zip(ref_train, my_train):
+            assert torch.equal(x.view(-1), idx)
+        for (x, _), idx in zip(ref_val, my_val):
+            assert torch.equal(x.view(-1), idx)
+    assert len(my_train) == 13 and len(my_val) == 4
+
+
+def test_shard_bounds_and_row_buckets():
+    from ai_font_renderer_b200.training import row_buckets, shard_bounds
+    for n in (1, 7, 192, 304, 1024):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    for nb in (1, 3, 8, 200):
+        b = row_buckets(19200, nb)
+        assert b[0][0] == 0 and b[-1][1] == 19200 and len(b) <= nb
+        assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(lo % 128 == 0 and (hi - lo) % 32 == 0 for lo, hi in b)
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "afr_sm100.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(afr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    from ai_font_renderer_b200 import _lib
+    lib = _lib.load()                                   # builds with nvcc if needed; no GPU calls
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    assert sorted(_lib.SIGNATURES.keys()) == declared   # the ctypes table covers the whole header
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (afr_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+    assert lib.afr_abi_version() == 1
+    sass = subprocess.run(["cuobjdump", "-lelf", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass                            # built for B200 and nothing else
+
+
+def test_cli_unknown_option_exits_1():
+    res = subprocess.run([sys.executable, os.path.join(REPO, "model.py"), "--bogus"],
+                         capture_output=True, text=True, cwd=REPO)
+    assert res.returncode == 1
+    assert "Unknown option: --bogus" in res.stdout and "Available options: --train" in res.stdout
