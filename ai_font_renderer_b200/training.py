@@ -100,6 +100,51 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
     return out
 
 
+def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool = True, marks=None):
+    """loss.backward(); optimizer.step() (model.py:309-310) for one rank of a data-parallel job.
+
+    world == 1: wgrad, dgrad + front-end backward, one AdamW sweep.
+    world  > 1: fc_output.weight.grad is produced bucket by bucket (row ranges); each bucket's
+    all-reduce is enqueued on NCCL's stream right behind its wgrad GEMM and runs under the later
+    buckets, the dgrad GEMM and the front-end backward; AdamW then consumes the buckets in order
+    while later reductions are still in flight. `marks`, if given, is called with a label between
+    phases (bench.py records CUDA events there)."""
+    mark = marks or (lambda label: None)
+    if world == 1:
+        model.fused_backward(buckets, (lambda i, lo, hi: mark("wgrad")) if marks else None)
+        mark("dgrad")
+        t_step = optimizer.begin_step()
+        optimizer.step_rows(t_step, 0, buckets[-1][1])
+        mark("adamw")                         # the fc_output.weight sweep alone
+        optimizer.step_small(t_step)
+        optimizer.end_step()
+        return
+    model._param_grads()
+    wgrad = model.fc_output.weight.grad
+    works = []
+
+    def reduce_bucket(i, r0, r1):
+        works.append(dist.all_reduce(wgrad[r0:r1], op=dist.ReduceOp.SUM, async_op=True))
+        if i == len(buckets) - 1:
+            mark("wgrad")
+
+    if has_samples:
+        model.fused_backward(buckets, reduce_bucket)
+    else:
+        for i, (r0, r1) in enumerate(buckets):
+            reduce_bucket(i, r0, r1)
+    mark("dgrad")
+    small = dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM, async_op=True)
+    t_step = optimizer.begin_step()
+    for w, (r0, r1) in zip(works, buckets):
+        w.wait()                              # stream-level wait on NCCL, no host sync
+        optimizer.step_rows(t_step, r0, r1)   # overlaps the next bucket's all-reduce
+    small.wait()
+    optimizer.step_small(t_step)
+    optimizer.end_step()
+    mark("adamw")
+
+
 class Trainer:
     def __init__(self, model, tokens: torch.Tensor, targets: torch.Tensor, batch_size: int,
                  cfg: TrainConfig, device: torch.device):
@@ -149,32 +194,7 @@ class Trainer:
             for p in model._ordered_params():
                 if p.grad is not None:
                     p.grad.zero_()
-        if self.world == 1:
-            model.fused_backward()
-            self.optimizer.step()
-        else:
-            model._param_grads()
-            wgrad = model.fc_output.weight.grad
-            works = []
-
-            def reduce_bucket(i, r0, r1):
-                # enqueued on NCCL's stream behind this bucket's wgrad GEMM; runs concurrently with
-                # the later buckets, the dgrad GEMM and the front-end backward
-                works.append(dist.all_reduce(wgrad[r0:r1], op=dist.ReduceOp.SUM, async_op=True))
-
-            if hi > lo:
-                model.fused_backward(self.buckets, reduce_bucket)
-            else:
-                for i, (r0, r1) in enumerate(self.buckets):
-                    reduce_bucket(i, r0, r1)
-            small = dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM, async_op=True)
-            t_step = self.optimizer.begin_step()
-            for w, (r0, r1) in zip(works, self.buckets):
-                w.wait()                                   # stream-level wait, no host sync on NCCL
-                self.optimizer.step_rows(t_step, r0, r1)   # overlaps the next bucket's all-reduce
-            small.wait()
-            self.optimizer.step_small(t_step)
-            self.optimizer.end_step()
+        backward_and_step(model, self.optimizer, self.buckets, self.world, has_samples=hi > lo)
         self.steps_done += 1
 
     @torch.no_grad()
