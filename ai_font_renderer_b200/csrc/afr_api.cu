@@ -30,6 +30,9 @@ struct afr_ctx {
   int loss_partials_cap = 0;
   float* bias_scratch = nullptr;     // [32, P]
   float* partials = nullptr;         // [num_sms, lay.total]
+  float* fstate = nullptr;           // [max_batch, fsl.stride] front-end records (forward -> backward)
+  FrontStateLayout fsl{};
+  bool state_valid = false;          // fstate holds the records of the batch in (tokens, B, S)
   // state carried from forward to backward
   const long long* tokens = nullptr;
   long long token_stride = 0;
@@ -143,11 +146,13 @@ int ensure_shadow(afr_ctx* c, cudaStream_t st) {
 }
 
 int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
-                 const Dropout& drop, cudaStream_t st) {
+                 const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32 = nullptr) {
+  float* state = save_state ? c->fstate : nullptr;
   AFR_CUDA(c, launch_frontend_forward(c->params, tokens, stride, B, S, c->cfg.max_length,
-                                      c->cfg.vocab, drop, c->feats, c->num_sms, st),
+                                      c->cfg.vocab, drop, c->feats, state, c->num_sms, st, feats_f32),
            "frontend_forward");
   c->launches += 1;
+  c->state_valid = state != nullptr;
   return AFR_OK;
 }
 
@@ -202,6 +207,14 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
   c->K = cfg->max_length * cfg->hidden;
   c->P = static_cast<int>(P);
   c->lay.init(cfg->max_length, cfg->vocab);
+  c->fsl.init(cfg->max_length);
+  if (cfg->training &&
+      frontend_backward_smem_bytes(cfg->max_length, cfg->vocab) > prop.sharedMemPerBlockOptin) {
+    delete c;
+    return fail(nullptr, AFR_ERR_INVALID,
+                "max_length too large for the training path (one sample's backward must fit in "
+                "the 227 KB of shared memory: max_length <= 120)");
+  }
   const size_t Bm = static_cast<size_t>(cfg->max_batch);
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
@@ -219,6 +232,7 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
     }
     alloc(reinterpret_cast<void**>(&c->partials),
           static_cast<size_t>(c->num_sms) * c->lay.total * 4);
+    alloc(reinterpret_cast<void**>(&c->fstate), Bm * c->fsl.stride * 4);
   }
   if (e != cudaSuccess) {
     std::string msg = std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e);
@@ -234,7 +248,7 @@ int afr_destroy(afr_ctx* c) {
   DeviceGuard guard(c->cfg.device);
   cudaFree(c->feats); cudaFree(c->wshadow); cudaFree(c->dz); cudaFree(c->dfeat);
   cudaFree(c->logits); cudaFree(c->loss_partials); cudaFree(c->bias_scratch);
-  cudaFree(c->partials);
+  cudaFree(c->partials); cudaFree(c->fstate);
   delete c;
   return AFR_OK;
 }
@@ -279,7 +293,8 @@ int afr_forward_eval(afr_ctx* c, const int64_t* tokens, int64_t token_stride, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((rc = ensure_shadow(c, st))) return rc;
   Dropout off{};
-  if ((rc = run_frontend(c, reinterpret_cast<const long long*>(tokens), token_stride, B, S, off, st)))
+  if ((rc = run_frontend(c, reinterpret_cast<const long long*>(tokens), token_stride, B, S, off,
+                         false, st)))
     return rc;
   GemmEpilogue ep{};
   ep.out = out; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
@@ -318,7 +333,7 @@ int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stri
   c->token_stride = token_stride;
   c->B = B; c->S = S;
   c->grad_scale = static_cast<float>(2.0 / loss_count);  // d/dy of mean((y-t)^2)
-  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, st))) return rc;
+  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, true, st))) return rc;
   const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
   const int tiles = gemm_num_tiles(B, c->P, bn);
   if ((rc = ensure_loss_partials(c, tiles * 4))) return rc;
@@ -380,10 +395,12 @@ int afr_train_dgrad(afr_ctx* c, void* stream) {
   cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow, c->K, true, c->B, c->K, c->P, bn,
                                    ep, c->num_sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(dgrad)");
+  if (!c->state_valid)
+    return fail(c, AFR_ERR_STATE, "front-end records of this batch were overwritten by another forward");
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
                                        c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
-                                       c->partials, c->num_sms, &grid, c->num_sms, st),
+                                       c->fstate, c->partials, c->num_sms, &grid, c->num_sms, st),
            "frontend_backward");
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce");
@@ -419,7 +436,7 @@ int afr_forward_train(afr_ctx* c, const int64_t* tokens, int64_t token_stride, i
   c->token_stride = token_stride;
   c->B = B; c->S = S;
   c->grad_scale = 1.f;
-  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, st))) return rc;
+  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, true, st))) return rc;
   GemmEpilogue ep{};
   ep.kind = kEpiF32; ep.out = c->logits; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
@@ -560,13 +577,11 @@ int afr_debug_frontend_forward(afr_ctx* c, const int64_t* tokens, int64_t token_
   if (rc) return rc;
   if (feats_f32 == nullptr) return fail(c, AFR_ERR_INVALID, "feats_f32 is NULL");
   DeviceGuard guard(c->cfg.device);
-  AFR_CUDA(c, launch_frontend_forward(c->params, reinterpret_cast<const long long*>(tokens),
-                                      token_stride, B, S, c->cfg.max_length, c->cfg.vocab,
-                                      to_dropout(dropout), c->feats, c->num_sms,
-                                      static_cast<cudaStream_t>(stream), feats_f32),
-           "frontend_forward(debug)");
-  c->launches += 1;
-  return AFR_OK;
+  c->tokens = reinterpret_cast<const long long*>(tokens);
+  c->token_stride = token_stride;
+  c->B = B; c->S = S;
+  return run_frontend(c, c->tokens, token_stride, B, S, to_dropout(dropout), c->cfg.training != 0,
+                      static_cast<cudaStream_t>(stream), feats_f32);
 }
 
 int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B,
@@ -578,13 +593,16 @@ int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token
   if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
   if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
   if (dfeat == nullptr) return fail(c, AFR_ERR_INVALID, "dfeat is NULL");
+  if (!c->state_valid || c->tokens != reinterpret_cast<const long long*>(tokens) || c->B != B || c->S != S)
+    return fail(c, AFR_ERR_STATE,
+                "afr_debug_frontend_backward needs afr_debug_frontend_forward on the same batch first");
   DeviceGuard guard(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, reinterpret_cast<const long long*>(tokens),
                                        token_stride, B, S, c->cfg.max_length, c->cfg.vocab,
-                                       to_dropout(dropout), dfeat, c->partials, c->num_sms, &grid,
-                                       c->num_sms, st),
+                                       to_dropout(dropout), dfeat, c->fstate, c->partials,
+                                       c->num_sms, &grid, c->num_sms, st),
            "frontend_backward(debug)");
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce(debug)");

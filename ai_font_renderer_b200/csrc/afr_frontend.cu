@@ -4,20 +4,41 @@
 // MHA follows torch.nn.functional.multi_head_attention_forward (packed in-proj, q scaled by
 // sqrt(1/head_dim), softmax over all S keys with no padding mask, dropout on probabilities).
 //
-// This part is ~1 % of the FLOPs (2.5 MFLOP/sample), S = 100 and head_dim = 8 do not tile onto
-// tensor cores, so it is fp32 SIMT: one CTA walks whole samples held in shared memory.
-// The backward kernel recomputes the forward per sample (nothing but the tokens and the
-// dropout seed is kept between forward and backward) and accumulates the ten small weight
-// gradients into a per-CTA partial buffer that a second kernel sums in a fixed order, so the
-// gradients are run-to-run deterministic.
+// 2.5 MFLOP/sample, S = 100 and head_dim = 8: this does not tile onto tcgen05, and it has to hold
+// the fp32 tolerance (1e-5), so it is fp32 SIMT built around what sm_100a's SIMT side is good at
+// (measured, tools/microbench/fp32_rates.cu): packed FFMA2 (118 FMA/clk/SM in half the issue
+// slots of FFMA) fed by warp-uniform LDS.128 (one clock per warp).
+//   * 13-warp CTAs (416 threads >= 4 heads x 100 queries), a whole sample in shared memory.
+//     Attention runs one thread per (query, head) with head-uniform warps, so every K/V row is a
+//     broadcast load; the soft-max is an online one over blocks of 8 keys in the log2 domain
+//     (MUFU.EX2); the linear layers run one warp per position with the lane's weight row/column
+//     in registers and the activation row broadcast.
+//   * The training forward leaves a 86 KB record per sample (e, q, k, v, context, normalised
+//     residual, soft-max statistics and every dropout decision as bit masks). The backward stages
+//     it into shared memory with cp.async.bulk + mbarriers while the previous phase computes:
+//     nothing is recomputed, no random number is drawn twice.
+//   * The ten small weight gradients accumulate in registers across all samples of a CTA and
+//     leave as per-CTA partials that a second kernel sums in a fixed order: deterministic, no
+//     float atomics. The embedding scatter-add is a per-CTA shared-memory table walked in
+//     position order by one warp.
 #include "afr_internal.h"
+#include "afr_ptx.cuh"
 
 namespace afr {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kLdW = kE + 1;  // padded leading dimension of weight matrices in smem
+using ptx::ex2;
+using ptx::fma2;
+using ptx::mul2;
+
+constexpr int kThreads = 416;
+constexpr int kWarps = kThreads / 32;                           // 13
+constexpr int kRowsPerWarp = (kMaxL + kWarps - 1) / kWarps;     // 10
+constexpr int kLdW = kE + 1;                                    // padded weight rows in smem
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kInvSqrtDh = 0.35355339059327373f;              // math.sqrt(1.0 / 8)
+constexpr int kEmbSmemMaxVocab = 256;                           // dEmb table in smem up to here
 
 struct FrontArgs {
   Tensors w;
@@ -26,68 +47,24 @@ struct FrontArgs {
   int B, S, L, vocab;
   Dropout drop;
   uint32_t thr_e, thr_a, thr_f;   // keep iff u16 >= thr
-  float inv_e, inv_a, inv_f;      // 1 / (1 - p)
+  float inv_e, inv_a, inv_f;      // 1 / (1 - p), or 1 with dropout off
   __nv_bfloat16* feats;           // forward
   float* feats_f32;               // forward, optional fp32 copy (test hook)
+  float* state;                   // forward: written when non-null; backward: read
+  FrontStateLayout sl;
   const float* dfeat;             // backward: [B, L*F]
   float* partials;                // backward: [grid, lay.total]
   SmallLayout lay;
   int* err_flag;
 };
 
-// ---- shared memory map (float offsets) ----------------------------------------------------
-struct Smem {
-  int win, bin, wo, bo, lnw, lnb, w1, b1;
-  int e, q, k, v, ctx, hbuf;
-  int xhat, df, dr, mrow, lrow, drow, rstd, maskbits, G;
-  int total;
-};
-__host__ __device__ inline Smem make_smem(int L, bool bwd) {
-  Smem s{};
-  int o = 0;
-  s.win = o; o += 3 * kE * kLdW;
-  s.bin = o; o += 3 * kE;
-  s.wo = o;  o += kE * kLdW;
-  s.bo = o;  o += kE;
-  s.lnw = o; o += kE;
-  s.lnb = o; o += kE;
-  s.w1 = o;  o += kF * kLdW;
-  s.b1 = o;  o += kF;
-  o = (o + 3) & ~3;
-  s.e = o;   o += L * kE;
-  s.q = o;   o += L * kE;
-  s.k = o;   o += L * kE;
-  s.v = o;   o += L * kE;
-  s.ctx = o; o += L * kE;
-  s.hbuf = o; o += kWarps * kE;
-  if (bwd) {
-    s.xhat = o; o += L * kE;
-    s.df = o;   o += L * kF;
-    s.dr = o;   o += L * kE;
-    s.mrow = o; o += L * kHeads;
-    s.lrow = o; o += L * kHeads;
-    s.drow = o; o += L * kHeads;
-    s.rstd = o; o += (L + 3) & ~3;
-    s.maskbits = o; o += L * kHeads * 4;
-    s.G = o;    o += 3 * kE * kE + 3 * kE + kE * kE + kE + kE + kE + kF * kE + kF;
-  }
-  s.total = o;
-  return s;
-}
-// offsets inside the smem gradient accumulator G (dense, unpadded)
-constexpr int kG_win = 0;
-constexpr int kG_bin = kG_win + 3 * kE * kE;
-constexpr int kG_wo = kG_bin + 3 * kE;
-constexpr int kG_bo = kG_wo + kE * kE;
-constexpr int kG_lnw = kG_bo + kE;
-constexpr int kG_lnb = kG_lnw + kE;
-constexpr int kG_w1 = kG_lnb + kE;
-constexpr int kG_b1 = kG_w1 + kF * kE;
-constexpr int kG_total = kG_b1 + kF;
-
 // ---- counter-based dropout RNG (Philox4x32-10) ---------------------------------------------
-// One call yields 8 x 16-bit uniforms for elements [8*block, 8*block+8) of one site of one
-// sample at one step. Keyed by (seed); counter = (block, site, global sample index, step).
+// One call yields 8 x 16-bit uniforms. Key = seed; counter = (block, site | row << 2, global
+// sample index, step):
+//   site 0 (embedding)  row = 0,         block = (s*E + c) / 8
+//   site 1 (attention)  row = h*S + s,   block = t / 8
+//   site 2 (fc1)        row = 0,         block = (s*F + j) / 8
+// and element i uses the (i % 8)-th 16-bit lane (low half of word i%8/2 first).
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -100,588 +77,792 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   }
   return make_uint4(c0, c1, c2, c3);
 }
-__device__ __forceinline__ uint32_t philox_u16(const uint4& r, int sub) {
-  const uint32_t word = (sub >> 1) == 0 ? r.x : (sub >> 1) == 1 ? r.y : (sub >> 1) == 2 ? r.z : r.w;
-  return (word >> ((sub & 1) * 16)) & 0xFFFFu;
-}
 struct Rng {
   uint32_t k0, k1, sample, step;
-  __device__ __forceinline__ uint4 block(uint32_t site, uint32_t blk) const {
-    return philox4x32_10(blk, site, sample, step, k0, k1);
+  __device__ __forceinline__ uint4 block(uint32_t site_row, uint32_t blk) const {
+    return philox4x32_10(blk, site_row, sample, step, k0, k1);
   }
 };
+template <int SUB>
+__device__ __forceinline__ uint32_t u16_of(const uint4& r) {
+  const uint32_t word = (SUB >> 1) == 0 ? r.x : (SUB >> 1) == 1 ? r.y : (SUB >> 1) == 2 ? r.z : r.w;
+  return (SUB & 1) ? (word >> 16) : (word & 0xFFFFu);
+}
+__device__ __forceinline__ uint32_t word_of(const uint4& r, int i) {
+  return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
+}
 
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
 
-// ---- weights -> smem (once per CTA) --------------------------------------------------------
-__device__ void load_weights(const Tensors& w, float* sm, const Smem& o) {
-  for (int i = threadIdx.x; i < 3 * kE * kE; i += kThreads)
-    sm[o.win + (i / kE) * kLdW + (i % kE)] = w.win[i];
-  for (int i = threadIdx.x; i < kE * kE; i += kThreads)
-    sm[o.wo + (i / kE) * kLdW + (i % kE)] = w.wo[i];
-  for (int i = threadIdx.x; i < kF * kE; i += kThreads)
-    sm[o.w1 + (i / kE) * kLdW + (i % kE)] = w.w1[i];
-  for (int i = threadIdx.x; i < 3 * kE; i += kThreads) sm[o.bin + i] = w.bin[i];
-  for (int i = threadIdx.x; i < kF; i += kThreads) sm[o.b1 + i] = w.b1[i];
-  if (threadIdx.x < kE) {
-    sm[o.bo + threadIdx.x] = w.bo[threadIdx.x];
-    sm[o.lnw + threadIdx.x] = w.lnw[threadIdx.x];
-    sm[o.lnb + threadIdx.x] = w.lnb[threadIdx.x];
+// Slot i in [0, 4S) -> (head, row). Full 32-row chunks are head-uniform per warp (K/V loads
+// become broadcasts); the S % 32 tail rows of all four heads are packed behind them.
+__device__ __forceinline__ void slot_to_pair(int i, int S, int& h, int& r) {
+  const int full = (S >> 5) << 7;
+  if (i < full) {
+    h = (i >> 5) & 3;
+    r = ((i >> 7) << 5) + (i & 31);
+  } else {
+    const int rem = S & 31, x = i - full;
+    h = x / rem;
+    r = (S & ~31) + x % rem;
   }
 }
 
-// ---- forward of one sample up to the LayerNorm output --------------------------------------
-// Leaves in smem: e, q (pre-scaled), k, v, ctx and, when BWD, xhat/rstd/softmax stats/mask bits.
-// Returns through the callback-free convention: the caller runs the fc1 stage itself because
-// forward and backward consume h differently.
-template <bool BWD>
-__device__ void forward_to_ctx(const FrontArgs& a, float* sm, const Smem& o, int b, const Rng& rng) {
-  const int S = a.S;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long* tok = a.tokens + static_cast<long long>(b) * a.token_stride;
-
-  // (1) e = dropout(Emb[tok]) + Pos           model.py:167-172 (dropout BEFORE positions)
-  for (int i = tid; i < S * kE; i += kThreads) {
-    const int s = i / kE, c = i % kE;
-    long long t = tok[s];
-    if (t < 0 || t >= a.vocab) { atomicOr(a.err_flag, 1); t = 0; }
-    float val = a.w.emb[t * kE + c];
-    if (a.drop.mode == 1) {
-      const uint4 r = rng.block(0u, static_cast<uint32_t>(i >> 3));
-      val = philox_u16(r, i & 7) >= a.thr_e ? val * a.inv_e : 0.f;
-    } else if (a.drop.mode == 2) {
-      val = a.drop.mask_embed[(static_cast<long long>(b) * S + s) * kE + c] ? val * a.inv_e : 0.f;
-    }
-    sm[o.e + i] = val + a.w.pos[i];
-  }
-  __syncthreads();
-
-  // (2) packed in-projection: q|k|v = e Win^T + bin ; q *= sqrt(1/head_dim)
-  {
-    float wr[3][kE];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int c = 0; c < kE; ++c) wr[j][c] = sm[o.win + (lane + 32 * j) * kLdW + c];
-    const float bq = sm[o.bin + lane], bk = sm[o.bin + 32 + lane], bv = sm[o.bin + 64 + lane];
-    const float qscale = 0.35355339059327373f;  // math.sqrt(1.0 / 8)
-    for (int s = warp; s < S; s += kWarps) {
-      float aq = bq, ak = bk, av = bv;
-      const float4* er = reinterpret_cast<const float4*>(sm + o.e + s * kE);
-#pragma unroll
-      for (int c4 = 0; c4 < kE / 4; ++c4) {
-        const float4 x = er[c4];
-        aq = fmaf(x.x, wr[0][4 * c4], aq); aq = fmaf(x.y, wr[0][4 * c4 + 1], aq);
-        aq = fmaf(x.z, wr[0][4 * c4 + 2], aq); aq = fmaf(x.w, wr[0][4 * c4 + 3], aq);
-        ak = fmaf(x.x, wr[1][4 * c4], ak); ak = fmaf(x.y, wr[1][4 * c4 + 1], ak);
-        ak = fmaf(x.z, wr[1][4 * c4 + 2], ak); ak = fmaf(x.w, wr[1][4 * c4 + 3], ak);
-        av = fmaf(x.x, wr[2][4 * c4], av); av = fmaf(x.y, wr[2][4 * c4 + 1], av);
-        av = fmaf(x.z, wr[2][4 * c4 + 2], av); av = fmaf(x.w, wr[2][4 * c4 + 3], av);
-      }
-      sm[o.q + s * kE + lane] = aq * qscale;
-      sm[o.k + s * kE + lane] = ak;
-      sm[o.v + s * kE + lane] = av;
-    }
-  }
-  __syncthreads();
-
-  // (3) per (query s, head h): softmax(q k^T) [dropout] v
-  for (int i = tid; i < S * kHeads; i += kThreads) {
-    const int s = i / kHeads, h = i % kHeads;
-    float qr[kDh];
-    {
-      const float4* qp = reinterpret_cast<const float4*>(sm + o.q + s * kE + h * kDh);
-      const float4 q0 = qp[0], q1 = qp[1];
-      qr[0] = q0.x; qr[1] = q0.y; qr[2] = q0.z; qr[3] = q0.w;
-      qr[4] = q1.x; qr[5] = q1.y; qr[6] = q1.z; qr[7] = q1.w;
-    }
-    float mx = -INFINITY;
-    for (int t = 0; t < S; ++t) {
-      const float4* kp = reinterpret_cast<const float4*>(sm + o.k + t * kE + h * kDh);
-      const float4 k0 = kp[0], k1 = kp[1];
-      float sc = qr[0] * k0.x;
-      sc = fmaf(qr[1], k0.y, sc); sc = fmaf(qr[2], k0.z, sc); sc = fmaf(qr[3], k0.w, sc);
-      sc = fmaf(qr[4], k1.x, sc); sc = fmaf(qr[5], k1.y, sc); sc = fmaf(qr[6], k1.z, sc);
-      sc = fmaf(qr[7], k1.w, sc);
-      mx = fmaxf(mx, sc);
-    }
-    float l = 0.f, acc[kDh];
-#pragma unroll
-    for (int j = 0; j < kDh; ++j) acc[j] = 0.f;
-    uint32_t bits = 0;
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    const uint32_t row_elem0 = static_cast<uint32_t>((h * S + s) * S);
-    for (int t = 0; t < S; ++t) {
-      const float4* kp = reinterpret_cast<const float4*>(sm + o.k + t * kE + h * kDh);
-      const float4 k0 = kp[0], k1 = kp[1];
-      float sc = qr[0] * k0.x;
-      sc = fmaf(qr[1], k0.y, sc); sc = fmaf(qr[2], k0.z, sc); sc = fmaf(qr[3], k0.w, sc);
-      sc = fmaf(qr[4], k1.x, sc); sc = fmaf(qr[5], k1.y, sc); sc = fmaf(qr[6], k1.z, sc);
-      sc = fmaf(qr[7], k1.w, sc);
-      const float p = expf(sc - mx);
-      l += p;
-      bool keep = true;
-      if (a.drop.mode == 1) {
-        const uint32_t el = row_elem0 + static_cast<uint32_t>(t);
-        if ((el & 7u) == 0u || t == 0) rnd = rng.block(1u, el >> 3);
-        keep = philox_u16(rnd, el & 7u) >= a.thr_a;
-      } else if (a.drop.mode == 2) {
-        keep = a.drop.mask_attn[((static_cast<long long>(b) * kHeads + h) * S + s) * S + t] != 0;
-      }
-      if (BWD) {
-        if (keep) bits |= 1u << (t & 31);
-        if ((t & 31) == 31 || t == S - 1) {
-          reinterpret_cast<uint32_t*>(sm + o.maskbits)[(h * S + s) * 4 + (t >> 5)] = bits;
-          bits = 0;
-        }
-      }
-      if (keep) {
-        const float4* vp = reinterpret_cast<const float4*>(sm + o.v + t * kE + h * kDh);
-        const float4 v0 = vp[0], v1 = vp[1];
-        acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]);
-        acc[2] = fmaf(p, v0.z, acc[2]); acc[3] = fmaf(p, v0.w, acc[3]);
-        acc[4] = fmaf(p, v1.x, acc[4]); acc[5] = fmaf(p, v1.y, acc[5]);
-        acc[6] = fmaf(p, v1.z, acc[6]); acc[7] = fmaf(p, v1.w, acc[7]);
-      }
-    }
-    const float scale = (a.drop.mode != 0 ? a.inv_a : 1.f) / l;
-#pragma unroll
-    for (int j = 0; j < kDh; ++j) sm[o.ctx + s * kE + h * kDh + j] = acc[j] * scale;
-    if (BWD) { sm[o.mrow + i] = mx; sm[o.lrow + i] = l; }
-  }
-  __syncthreads();
+// dot of the 8 head channels: a (4 packed pairs) . row (two float4)
+__device__ __forceinline__ float dot8(const float2 (&a)[4], const float4& r0, const float4& r1) {
+  float2 s = mul2(a[0], f2(r0.x, r0.y));
+  s = fma2(a[1], f2(r0.z, r0.w), s);
+  s = fma2(a[2], f2(r1.x, r1.y), s);
+  s = fma2(a[3], f2(r1.z, r1.w), s);
+  return s.x + s.y;
+}
+// acc += w * row
+__device__ __forceinline__ void axpy8(float2 (&acc)[4], float w, const float4& r0, const float4& r1) {
+  const float2 ww = f2(w, w);
+  acc[0] = fma2(ww, f2(r0.x, r0.y), acc[0]);
+  acc[1] = fma2(ww, f2(r0.z, r0.w), acc[1]);
+  acc[2] = fma2(ww, f2(r1.x, r1.y), acc[2]);
+  acc[3] = fma2(ww, f2(r1.z, r1.w), acc[3]);
 }
 
-// out-projection + residual + LayerNorm for position s (warp-wide, lane = channel).
-// Returns h[s][lane]; optionally xhat and rstd.
-__device__ __forceinline__ float attn_out_layernorm(const float* sm, const Smem& o, int s, int lane,
-                                                    const float (&wo_row)[kE], float& xhat,
-                                                    float& rstd) {
-  float acc = sm[o.bo + lane];
-  const float4* cr = reinterpret_cast<const float4*>(sm + o.ctx + s * kE);
-#pragma unroll
-  for (int j4 = 0; j4 < kE / 4; ++j4) {
-    const float4 x = cr[j4];
-    acc = fmaf(x.x, wo_row[4 * j4], acc); acc = fmaf(x.y, wo_row[4 * j4 + 1], acc);
-    acc = fmaf(x.z, wo_row[4 * j4 + 2], acc); acc = fmaf(x.w, wo_row[4 * j4 + 3], acc);
-  }
-  const float r = sm[o.e + s * kE + lane] + acc;        // residual, model.py:180
-  const float mean = warp_sum(r) * (1.f / kE);
-  const float d = r - mean;
-  const float var = warp_sum(d * d) * (1.f / kE);       // biased variance, eps = 1e-5
-  rstd = 1.f / sqrtf(var + 1e-5f);
-  xhat = d * rstd;
-  return fmaf(xhat, sm[o.lnw + lane], sm[o.lnb + lane]);
+// weights -> smem, rows padded to kLdW floats
+__device__ __forceinline__ void load_matrix(const float* __restrict__ g, float* sm, int rows) {
+  for (int i = threadIdx.x; i < rows * kE; i += kThreads) sm[(i / kE) * kLdW + (i % kE)] = g[i];
 }
 
 // ============================================================================ forward kernel
-__global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(FrontArgs a) {
+struct FwdSmem {
+  int win, wo, w1, bin, bo, lnw, lnb, b1, e, q, k, v, total;
+};
+__host__ __device__ inline FwdSmem make_fwd_smem(int L) {
+  FwdSmem s{};
+  int o = 0;
+  s.win = o; o += 3 * kE * kLdW;
+  s.wo = o;  o += kE * kLdW;
+  s.w1 = o;  o += kF * kLdW;
+  s.bin = o; o += 3 * kE;
+  s.bo = o;  o += kE;
+  s.lnw = o; o += kE;
+  s.lnb = o; o += kE;
+  s.b1 = o;  o += kF;
+  o = (o + 3) & ~3;
+  s.e = o; o += L * kE;
+  s.q = o; o += L * kE;
+  s.k = o; o += L * kE;
+  s.v = o; o += (L + 8) * kE;   // the last key block may read (never use) up to 7 rows past S
+  s.total = o;
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const FrontArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const Smem o = make_smem(a.L, false);
+  const FwdSmem o = make_fwd_smem(a.L);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  load_weights(a.w, sm, o);
+  const int S = a.S, KF = a.L * kF;
+  const int mode = a.drop.mode;
+
+  load_matrix(a.w.win, sm + o.win, 3 * kE);
+  load_matrix(a.w.wo, sm + o.wo, kE);
+  load_matrix(a.w.w1, sm + o.w1, kF);
+  for (int i = tid; i < 3 * kE; i += kThreads) sm[o.bin + i] = a.w.bin[i];
+  for (int i = tid; i < kF; i += kThreads) sm[o.b1 + i] = a.w.b1[i];
+  if (tid < kE) {
+    sm[o.bo + tid] = a.w.bo[tid];
+    sm[o.lnw + tid] = a.w.lnw[tid];
+    sm[o.lnb + tid] = a.w.lnb[tid];
+  }
   __syncthreads();
 
-  const int S = a.S, KF = a.L * kF;
+  float* se = sm + o.e;
+  float* sq = sm + o.q;
+  float* sk = sm + o.k;
+  float* sv = sm + o.v;
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    Rng rng{static_cast<uint32_t>(a.drop.seed), static_cast<uint32_t>(a.drop.seed >> 32),
-            static_cast<uint32_t>(a.drop.sample_offset + b), static_cast<uint32_t>(a.drop.step)};
-    forward_to_ctx<false>(a, sm, o, b, rng);
-    float wo_row[kE], w1a[kE], w1b[kE];
+    const Rng rng{static_cast<uint32_t>(a.drop.seed), static_cast<uint32_t>(a.drop.seed >> 32),
+                  static_cast<uint32_t>(a.drop.sample_offset + b), static_cast<uint32_t>(a.drop.step)};
+    const long long* tok = a.tokens + static_cast<long long>(b) * a.token_stride;
+    float* st = a.state != nullptr ? a.state + static_cast<long long>(b) * a.sl.stride : nullptr;
+
+    // ---- (1) e = dropout(Emb[tok]) + Pos        model.py:167-172 (dropout BEFORE positions)
+    // one thread per 8 channels = one Philox block
+    for (int base = 0; base < S * 4; base += kThreads) {
+      const int i8 = base + tid;
+      const bool valid = i8 < S * 4;
+      uint32_t keep8 = 0xFFu;
+      if (valid) {
+        const int s = i8 >> 2, c0 = (i8 & 3) * 8;
+        long long t = tok[s];
+        if (t < 0 || t >= a.vocab) { atomicOr(a.err_flag, 1); t = 0; }
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.w.emb + t * kE + c0));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.w.emb + t * kE + c0 + 4));
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.w.pos + s * kE + c0));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(a.w.pos + s * kE + c0 + 4));
+        if (mode == 1) {
+          const uint4 r = rng.block(0u, static_cast<uint32_t>(i8));
+          keep8 = (u16_of<0>(r) >= a.thr_e ? 1u : 0u) | (u16_of<1>(r) >= a.thr_e ? 2u : 0u) |
+                  (u16_of<2>(r) >= a.thr_e ? 4u : 0u) | (u16_of<3>(r) >= a.thr_e ? 8u : 0u) |
+                  (u16_of<4>(r) >= a.thr_e ? 16u : 0u) | (u16_of<5>(r) >= a.thr_e ? 32u : 0u) |
+                  (u16_of<6>(r) >= a.thr_e ? 64u : 0u) | (u16_of<7>(r) >= a.thr_e ? 128u : 0u);
+        } else if (mode == 2) {
+          const uint2 mk = *reinterpret_cast<const uint2*>(
+              a.drop.mask_embed + (static_cast<long long>(b) * S + s) * kE + c0);
+          keep8 = 0;
 #pragma unroll
-    for (int c = 0; c < kE; ++c) {
-      wo_row[c] = sm[o.wo + lane * kLdW + c];
-      w1a[c] = sm[o.w1 + lane * kLdW + c];
-      w1b[c] = sm[o.w1 + (lane + 32) * kLdW + c];
-    }
-    const float b1a = sm[o.b1 + lane], b1b = sm[o.b1 + 32 + lane];
-    __nv_bfloat16* out = a.feats + static_cast<long long>(b) * KF;
-    for (int s = warp; s < S; s += kWarps) {
-      float xhat, rstd;
-      const float hval = attn_out_layernorm(sm, o, s, lane, wo_row, xhat, rstd);
-      sm[o.hbuf + warp * kE + lane] = hval;
-      __syncwarp();
-      float fa = b1a, fb = b1b;
-      const float4* hr = reinterpret_cast<const float4*>(sm + o.hbuf + warp * kE);
+          for (int u = 0; u < 4; ++u) {
+            keep8 |= ((mk.x >> (8 * u)) & 0xFFu) ? (1u << u) : 0u;
+            keep8 |= ((mk.y >> (8 * u)) & 0xFFu) ? (16u << u) : 0u;
+          }
+        }
+        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        float ov[8];
 #pragma unroll
-      for (int c4 = 0; c4 < kE / 4; ++c4) {
-        const float4 x = hr[c4];
-        fa = fmaf(x.x, w1a[4 * c4], fa); fa = fmaf(x.y, w1a[4 * c4 + 1], fa);
-        fa = fmaf(x.z, w1a[4 * c4 + 2], fa); fa = fmaf(x.w, w1a[4 * c4 + 3], fa);
-        fb = fmaf(x.x, w1b[4 * c4], fb); fb = fmaf(x.y, w1b[4 * c4 + 1], fb);
-        fb = fmaf(x.z, w1b[4 * c4 + 2], fb); fb = fmaf(x.w, w1b[4 * c4 + 3], fb);
+        for (int u = 0; u < 8; ++u)
+          ov[u] = ((keep8 >> u) & 1u) ? fmaf(ev[u], a.inv_e, pv[u]) : pv[u];
+        *reinterpret_cast<float4*>(se + s * kE + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<float4*>(se + s * kE + c0 + 4) = make_float4(ov[4], ov[5], ov[6], ov[7]);
       }
-      __syncwarp();
-      fa = fmaxf(fa, 0.f); fb = fmaxf(fb, 0.f);          // ReLU, model.py:183
-      if (a.drop.mode == 1) {                            // dropout1, model.py:184
-        const uint32_t ea = static_cast<uint32_t>(s * kF + lane), eb = ea + 32u;
-        fa = philox_u16(rng.block(2u, ea >> 3), ea & 7u) >= a.thr_f ? fa * a.inv_f : 0.f;
-        fb = philox_u16(rng.block(2u, eb >> 3), eb & 7u) >= a.thr_f ? fb * a.inv_f : 0.f;
-      } else if (a.drop.mode == 2) {
-        const uint8_t* mk = a.drop.mask_fc1 + (static_cast<long long>(b) * S + s) * kF;
-        fa = mk[lane] ? fa * a.inv_f : 0.f;
-        fb = mk[lane + 32] ? fb * a.inv_f : 0.f;
-      }
-      out[s * kF + lane] = __float2bfloat16_rn(fa);
-      out[s * kF + 32 + lane] = __float2bfloat16_rn(fb);
-      if (a.feats_f32 != nullptr) {
-        a.feats_f32[static_cast<long long>(b) * KF + s * kF + lane] = fa;
-        a.feats_f32[static_cast<long long>(b) * KF + s * kF + 32 + lane] = fb;
+      if (st != nullptr) {   // 32 keep bits per position, assembled from the 4 threads of the row
+        uint32_t wbits = keep8 << (8 * (tid & 3));
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 1);
+        wbits |= __shfl_xor_sync(0xffffffffu, wbits, 2);
+        if (valid && (tid & 3) == 0) reinterpret_cast<uint32_t*>(st + a.sl.ebits)[i8 >> 2] = wbits;
       }
     }
-    // zero features for positions >= S (model.py:190-193)
-    for (int i = S * kF + tid; i < KF; i += kThreads) {
-      out[i] = __float2bfloat16_rn(0.f);
-      if (a.feats_f32 != nullptr) a.feats_f32[static_cast<long long>(b) * KF + i] = 0.f;
+    __syncthreads();
+
+    // ---- (2) packed in-projection q|k|v = e Win^T + bin  (torch functional.py:5836) -----------
+    // lane = output channel; its weight row lives in registers, the e row is broadcast.
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      float2 w2[kE / 2];
+#pragma unroll
+      for (int c = 0; c < kE / 2; ++c)
+        w2[c] = f2(sm[o.win + (32 * j + lane) * kLdW + 2 * c], sm[o.win + (32 * j + lane) * kLdW + 2 * c + 1]);
+      const float bias = sm[o.bin + 32 * j + lane];
+      const float scale = j == 0 ? kInvSqrtDh * kLog2e : 1.f;   // q also carries log2(e): ex2 soft-max
+      float* dst = j == 0 ? sq : (j == 1 ? sk : sv);
+      float* gdst = st != nullptr ? st + (j == 0 ? a.sl.q : (j == 1 ? a.sl.k : a.sl.v)) : nullptr;
+      for (int s = warp; s < S; s += kWarps) {
+        float2 acc = f2(bias, 0.f);
+#pragma unroll
+        for (int c4 = 0; c4 < kE / 4; ++c4) {
+          const float4 x = lds4(se + s * kE + 4 * c4);
+          acc = fma2(f2(x.x, x.y), w2[2 * c4], acc);
+          acc = fma2(f2(x.z, x.w), w2[2 * c4 + 1], acc);
+        }
+        const float r = (acc.x + acc.y) * scale;
+        dst[s * kE + lane] = r;
+        if (gdst != nullptr) gdst[s * kE + lane] = r;
+      }
+    }
+    __syncthreads();
+
+    // ---- (3) per (query s, head h): ctx = dropout(softmax(q k^T)) v   (functional.py:6642-6647)
+    for (int i = tid; i < S * kHeads; i += kThreads) {
+      int h, s;
+      slot_to_pair(i, S, h, s);
+      float2 q2[4];
+      {
+        const float4 q0 = lds4(sq + s * kE + h * kDh), q1 = lds4(sq + s * kE + h * kDh + 4);
+        q2[0] = f2(q0.x, q0.y); q2[1] = f2(q0.z, q0.w); q2[2] = f2(q1.x, q1.y); q2[3] = f2(q1.z, q1.w);
+      }
+      float m = -INFINITY, l = 0.f;
+      float2 acc[4] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+      const uint32_t row = static_cast<uint32_t>(h * S + s);
+      uint32_t* gbits = st != nullptr ? reinterpret_cast<uint32_t*>(st + a.sl.abits) + row * 4 : nullptr;
+      const uint8_t* mrow = mode == 2
+          ? a.drop.mask_attn + ((static_cast<long long>(b) * kHeads + h) * S + s) * S : nullptr;
+      uint32_t bits = 0;
+      const float* kh = sk + h * kDh;
+      const float* vh = sv + h * kDh;
+      const int nblk = (S + 7) >> 3;
+      for (int blk = 0; blk < nblk; ++blk) {
+        const int t0 = blk * 8;
+        float sc[8];
+        float bm = m;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 k0 = lds4(kh + (t0 + u) * kE), k1 = lds4(kh + (t0 + u) * kE + 4);
+          const float d = dot8(q2, k0, k1);
+          sc[u] = (t0 + u < S) ? d : -INFINITY;
+          bm = fmaxf(bm, sc[u]);
+        }
+        const float corr = ex2(m - bm);      // first block: ex2(-inf) = 0 (l and acc are 0 anyway)
+        m = bm;
+        l *= corr;
+        {
+          const float2 c2 = f2(corr, corr);
+          acc[0] = mul2(acc[0], c2); acc[1] = mul2(acc[1], c2);
+          acc[2] = mul2(acc[2], c2); acc[3] = mul2(acc[3], c2);
+        }
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (mode == 1) rnd = rng.block(1u | (row << 2), static_cast<uint32_t>(blk));
+        uint32_t keep8 = 0xFFu;
+        if (mode == 1) {
+          keep8 = (u16_of<0>(rnd) >= a.thr_a ? 1u : 0u) | (u16_of<1>(rnd) >= a.thr_a ? 2u : 0u) |
+                  (u16_of<2>(rnd) >= a.thr_a ? 4u : 0u) | (u16_of<3>(rnd) >= a.thr_a ? 8u : 0u) |
+                  (u16_of<4>(rnd) >= a.thr_a ? 16u : 0u) | (u16_of<5>(rnd) >= a.thr_a ? 32u : 0u) |
+                  (u16_of<6>(rnd) >= a.thr_a ? 64u : 0u) | (u16_of<7>(rnd) >= a.thr_a ? 128u : 0u);
+        } else if (mode == 2) {
+          keep8 = 0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (t0 + u < S && mrow[t0 + u] != 0) keep8 |= 1u << u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (t0 + u < S) {     // warp-uniform
+            const float p = ex2(sc[u] - m);
+            l += p;             // the soft-max denominator counts dropped keys too
+            const float pk = ((keep8 >> u) & 1u) ? p : 0.f;
+            const float4 v0 = lds4(vh + (t0 + u) * kE), v1 = lds4(vh + (t0 + u) * kE + 4);
+            axpy8(acc, pk, v0, v1);
+          }
+        }
+        bits |= keep8 << (8 * (blk & 3));
+        if ((blk & 3) == 3 || blk == nblk - 1) {
+          if (gbits != nullptr) gbits[blk >> 2] = bits;
+          bits = 0;
+        }
+      }
+      const float linv = 1.f / l;
+      const float scale = a.inv_a * linv;
+      // q of this (s, h) is dead: the context vector takes its place
+      *reinterpret_cast<float4*>(sq + s * kE + h * kDh) =
+          make_float4(acc[0].x * scale, acc[0].y * scale, acc[1].x * scale, acc[1].y * scale);
+      *reinterpret_cast<float4*>(sq + s * kE + h * kDh + 4) =
+          make_float4(acc[2].x * scale, acc[2].y * scale, acc[3].x * scale, acc[3].y * scale);
+      if (st != nullptr)
+        *reinterpret_cast<float4*>(st + a.sl.stat + (s * kHeads + h) * 4) = make_float4(m, linv, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    // ---- (4a) out-projection + residual + LayerNorm (model.py:180); h overwrites e ----------
+    {
+      float2 wo2[kE / 2];
+#pragma unroll
+      for (int c = 0; c < kE / 2; ++c)
+        wo2[c] = f2(sm[o.wo + lane * kLdW + 2 * c], sm[o.wo + lane * kLdW + 2 * c + 1]);
+      const float bo = sm[o.bo + lane], gam = sm[o.lnw + lane], bet = sm[o.lnb + lane];
+      for (int s = warp; s < S; s += kWarps) {
+        float2 acc = f2(bo, 0.f);
+#pragma unroll
+        for (int j4 = 0; j4 < kE / 4; ++j4) {
+          const float4 x = lds4(sq + s * kE + 4 * j4);
+          acc = fma2(f2(x.x, x.y), wo2[2 * j4], acc);
+          acc = fma2(f2(x.z, x.w), wo2[2 * j4 + 1], acc);
+        }
+        const float ev = se[s * kE + lane];
+        const float r = ev + (acc.x + acc.y);              // residual uses the dropped+positioned e
+        const float mean = warp_sum(r) * (1.f / kE);
+        const float d = r - mean;
+        const float var = warp_sum(d * d) * (1.f / kE);    // biased variance, eps = 1e-5
+        const float rstd = 1.f / sqrtf(var + 1e-5f);
+        const float xhat = d * rstd;
+        if (st != nullptr) {
+          st[a.sl.e + s * kE + lane] = ev;
+          st[a.sl.ctx + s * kE + lane] = sq[s * kE + lane];
+          st[a.sl.xhat + s * kE + lane] = xhat;
+          if (lane == 0) st[a.sl.rstd + s] = rstd;
+        }
+        se[s * kE + lane] = fmaf(xhat, gam, bet);
+      }
+    }
+    __syncwarp();   // (4b) reads only the rows this warp wrote in (4a)
+
+    // ---- (4b) f = dropout(relu(fc1(h)))  (model.py:183-184). lane owns features 2*lane, 2*lane+1
+    {
+      float2 acc[kRowsPerWarp];
+      const float2 bias = f2(sm[o.b1 + 2 * lane], sm[o.b1 + 2 * lane + 1]);
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) acc[i] = bias;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float2 w2[kE / 2];
+#pragma unroll
+        for (int c = 0; c < kE / 2; ++c)
+          w2[c] = f2(sm[o.w1 + (2 * lane) * kLdW + 16 * half + c],
+                     sm[o.w1 + (2 * lane + 1) * kLdW + 16 * half + c]);
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) {
+          const int s = warp + kWarps * i;
+          if (s < S) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 x = lds4(se + s * kE + 16 * half + 4 * u);
+              acc[i] = fma2(f2(x.x, x.x), w2[4 * u], acc[i]);
+              acc[i] = fma2(f2(x.y, x.y), w2[4 * u + 1], acc[i]);
+              acc[i] = fma2(f2(x.z, x.z), w2[4 * u + 2], acc[i]);
+              acc[i] = fma2(f2(x.w, x.w), w2[4 * u + 3], acc[i]);
+            }
+          }
+        }
+      }
+      __nv_bfloat16* out = a.feats + static_cast<long long>(b) * KF;
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int s = warp + kWarps * i;
+        if (s < S) {
+          float fa = fmaxf(acc[i].x, 0.f), fb = fmaxf(acc[i].y, 0.f);   // ReLU
+          bool ka = true, kb = true;
+          if (mode == 1) {
+            const uint4 r = rng.block(2u, static_cast<uint32_t>(s * (kF / 8) + (lane >> 2)));
+            const uint32_t word = word_of(r, lane & 3);
+            ka = (word & 0xFFFFu) >= a.thr_f;
+            kb = (word >> 16) >= a.thr_f;
+          } else if (mode == 2) {
+            const uint8_t* mk = a.drop.mask_fc1 + (static_cast<long long>(b) * S + s) * kF;
+            ka = mk[2 * lane] != 0;
+            kb = mk[2 * lane + 1] != 0;
+          }
+          const bool pa = ka && fa > 0.f, pb = kb && fb > 0.f;
+          fa = ka ? fa * a.inv_f : 0.f;
+          fb = kb ? fb * a.inv_f : 0.f;
+          *reinterpret_cast<__nv_bfloat162*>(out + s * kF + 2 * lane) = __floats2bfloat162_rn(fa, fb);
+          if (a.feats_f32 != nullptr)
+            *reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF + s * kF + 2 * lane) =
+                make_float2(fa, fb);
+          const uint32_t w0 = __ballot_sync(0xffffffffu, pa), w1 = __ballot_sync(0xffffffffu, pb);
+          if (st != nullptr && lane == 0)
+            *reinterpret_cast<uint2*>(st + a.sl.fbits + 2 * s) = make_uint2(w0, w1);
+        }
+      }
+      // zero features for positions >= S (model.py:190-193)
+      for (int i = S * kF / 2 + tid; i < KF / 2; i += kThreads) {
+        reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(0.f, 0.f);
+        if (a.feats_f32 != nullptr)
+          reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF)[i] = make_float2(0.f, 0.f);
+      }
     }
     __syncthreads();
   }
 }
 
 // =========================================================================== backward kernel
-__global__ void __launch_bounds__(kThreads) frontend_backward_kernel(FrontArgs a) {
+struct BwdSmem {
+  int w1, wo, win, lnw;
+  int xhat, df, dr, ctx, q, k, v, e, dctx, stat, abits, fbits, ebits, rstd, tok, hist, red, bars;
+  int total;
+};
+__host__ __device__ inline BwdSmem make_bwd_smem(int L, int vocab) {
+  const int L4 = (L + 3) & ~3;
+  BwdSmem s{};
+  int o = 0;
+  s.w1 = o;  o += kF * kLdW;
+  s.wo = o;  o += kE * kLdW;
+  s.win = o; o += 3 * kE * kLdW;
+  s.lnw = o; o += kE;
+  o = (o + 3) & ~3;
+  s.xhat = o; o += L * kE;        // xhat -> h (B1) -> dq (B3)
+  s.df = o;   o += L * kF;        // dfeat -> df (B1) ; second half -> dv (B3)
+  s.dr = o;   o += L * kE;        // d(residual) (B1) -> d(embedding rows) (B4)
+  s.ctx = o;  o += L * kE;        // ctx -> dk (B3)
+  s.q = o;    o += L * kE;
+  s.k = o;    o += L * kE;
+  s.v = o;    o += L * kE;
+  s.e = o;    o += L * kE;
+  s.dctx = o; o += L * kE;
+  s.stat = o; o += L * kHeads * 4;   // (m, 1/l, D, -)
+  s.abits = o; o += kHeads * L * 4;
+  s.fbits = o; o += L4 * 2;
+  s.ebits = o; o += L4;
+  s.rstd = o; o += L4;
+  s.tok = o;  o += L4;
+  s.hist = o; o += vocab <= kEmbSmemMaxVocab ? vocab * kE : 0;
+  s.red = o;  o += kWarps * kE * 2;
+  o = (o + 3) & ~3;
+  s.bars = o; o += 8;                // 4 mbarriers
+  s.total = o;
+  return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const FrontArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const Smem o = make_smem(a.L, true);
+  const BwdSmem o = make_bwd_smem(a.L, a.vocab);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = a.S, KF = a.L * kF;
-  load_weights(a.w, sm, o);
-  for (int i = tid; i < kG_total; i += kThreads) sm[o.G + i] = 0.f;
+  const int S = a.S, S4 = (S + 3) & ~3, KF = a.L * kF;
+  const bool hist_smem = a.vocab <= kEmbSmemMaxVocab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o.bars);
   float* part = a.partials + static_cast<long long>(blockIdx.x) * a.lay.total;
-  for (int i = tid; i < a.L * kE; i += kThreads) part[a.lay.off_pos + i] = 0.f;
-  for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = 0.f;
+
+  load_matrix(a.w.w1, sm + o.w1, kF);
+  load_matrix(a.w.wo, sm + o.wo, kE);
+  load_matrix(a.w.win, sm + o.win, 3 * kE);
+  if (tid < kE) sm[o.lnw + tid] = a.w.lnw[tid];
+  if (hist_smem) {
+    for (int i = tid; i < a.vocab * kE; i += kThreads) sm[o.hist + i] = 0.f;
+  } else {
+    for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = 0.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_mbar_init();
+  }
   __syncthreads();
 
-  float dgamma = 0.f, dbeta = 0.f;  // per (warp, lane = channel), reduced over warps at the end
+  float* s_xhat = sm + o.xhat;
+  float* s_df = sm + o.df;
+  float* s_dr = sm + o.dr;
+  float* s_ctx = sm + o.ctx;
+  float* s_q = sm + o.q;
+  float* s_k = sm + o.k;
+  float* s_v = sm + o.v;
+  float* s_e = sm + o.e;
+  float* s_dctx = sm + o.dctx;
+  float* s_stat = sm + o.stat;
+  const uint32_t* s_abits = reinterpret_cast<const uint32_t*>(sm + o.abits);
+  const uint32_t* s_fbits = reinterpret_cast<const uint32_t*>(sm + o.fbits);
+  const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + o.ebits);
+  int* s_tok = reinterpret_cast<int*>(sm + o.tok);
+  float* s_dq = s_xhat;
+  float* s_dk = s_ctx;
+  float* s_dv = s_df + a.L * kE;
 
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    Rng rng{static_cast<uint32_t>(a.drop.seed), static_cast<uint32_t>(a.drop.seed >> 32),
-            static_cast<uint32_t>(a.drop.sample_offset + b), static_cast<uint32_t>(a.drop.step)};
-    forward_to_ctx<true>(a, sm, o, b, rng);
-    const float* dfe = a.dfeat + static_cast<long long>(b) * KF;
+  // gradient accumulators that live in registers for the whole kernel
+  float2 g_w1[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};    // tid < 256: dW1[tid>>2][8*(tid&3)..]
+  float2 g_wo[2] = {f2(0, 0), f2(0, 0)};                        // tid < 256: dWo[tid>>3][4*(tid&7)..]
+  float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // tid < 384: dWin[tid>>2][8*(tid&3)..]
+  float g_vec = 0.f;               // tid 256..319: db1[tid-256]; tid 320..351: dbo[tid-320]
+  float g_bin[3] = {0.f, 0.f, 0.f};  // warp 12: dbin[lane], [32+lane], [64+lane]
+  float g_gam = 0.f, g_bet = 0.f;  // (warp, lane = channel) partial of d(LayerNorm weight / bias)
+  float g_pos[kRowsPerWarp];       // d(positional_encoding)[warp + 13 i][lane]
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) g_pos[i] = 0.f;
 
-    // ---- B1: LayerNorm output, fc1 recompute, d(fc1), d(LayerNorm) ------------------------
+  const float inv_e = a.inv_e, inv_a = a.inv_a, inv_f = a.inv_f;
+  uint32_t phase = 0;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x, phase ^= 1u) {
+    // ---- stage this sample's record: four groups, each waited for right before its first use
+    ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
+    __syncthreads();
+    if (tid == 0) {
+      const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
+      const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
+      ptx::mbar_arrive_expect_tx(&bars[0], row_bytes + 2u * row_bytes + S4 * 8u + S4 * 4u);
+      ptx::bulk_load_1d(s_xhat, st + a.sl.xhat, row_bytes, &bars[0]);
+      ptx::bulk_load_1d(s_df, a.dfeat + static_cast<long long>(b) * KF, 2u * row_bytes, &bars[0]);
+      ptx::bulk_load_1d(sm + o.fbits, st + a.sl.fbits, S4 * 8u, &bars[0]);
+      ptx::bulk_load_1d(sm + o.rstd, st + a.sl.rstd, S4 * 4u, &bars[0]);
+      ptx::mbar_arrive_expect_tx(&bars[1], row_bytes);
+      ptx::bulk_load_1d(s_ctx, st + a.sl.ctx, row_bytes, &bars[1]);
+      ptx::mbar_arrive_expect_tx(&bars[2], 3u * row_bytes + S * 64u + S * 64u);
+      ptx::bulk_load_1d(s_q, st + a.sl.q, row_bytes, &bars[2]);
+      ptx::bulk_load_1d(s_k, st + a.sl.k, row_bytes, &bars[2]);
+      ptx::bulk_load_1d(s_v, st + a.sl.v, row_bytes, &bars[2]);
+      ptx::bulk_load_1d(s_stat, st + a.sl.stat, S * 64u, &bars[2]);
+      ptx::bulk_load_1d(sm + o.abits, st + a.sl.abits, S * 64u, &bars[2]);
+      ptx::mbar_arrive_expect_tx(&bars[3], row_bytes + S4 * 4u);
+      ptx::bulk_load_1d(s_e, st + a.sl.e, row_bytes, &bars[3]);
+      ptx::bulk_load_1d(sm + o.ebits, st + a.sl.ebits, S4 * 4u, &bars[3]);
+    }
+    if (tid < S) {
+      long long t = a.tokens[static_cast<long long>(b) * a.token_stride + tid];
+      if (t < 0 || t >= a.vocab) t = 0;
+      s_tok[tid] = static_cast<int>(t);
+    }
+
+    // ---- B1: df = dfeat * ReLU' * dropout ; dh = df W1 ; LayerNorm backward -> dr ; h --------
+    ptx::mbar_wait(&bars[0], phase);
     {
-      float wo_row[kE], w1a[kE], w1b[kE];
+      float2 w1c[kF / 2];   // column `lane` of W1, packed along the feature index
 #pragma unroll
-      for (int c = 0; c < kE; ++c) {
-        wo_row[c] = sm[o.wo + lane * kLdW + c];
-        w1a[c] = sm[o.w1 + lane * kLdW + c];
-        w1b[c] = sm[o.w1 + (lane + 32) * kLdW + c];
-      }
-      const float b1a = sm[o.b1 + lane], b1b = sm[o.b1 + 32 + lane];
-      const float gam = sm[o.lnw + lane];
+      for (int j = 0; j < kF / 2; ++j)
+        w1c[j] = f2(sm[o.w1 + (2 * j) * kLdW + lane], sm[o.w1 + (2 * j + 1) * kLdW + lane]);
+      const float gam = sm[o.lnw + lane], bet = a.w.lnb[lane];
       for (int s = warp; s < S; s += kWarps) {
-        float xhat, rstd;
-        const float hval = attn_out_layernorm(sm, o, s, lane, wo_row, xhat, rstd);
-        sm[o.xhat + s * kE + lane] = xhat;
-        if (lane == 0) sm[o.rstd + s] = rstd;
-        sm[o.hbuf + warp * kE + lane] = hval;
+        const float xh = s_xhat[s * kE + lane];
+        const float rs = sm[o.rstd + s];
+        {
+          float2 d = *reinterpret_cast<const float2*>(s_df + s * kF + 2 * lane);
+          const uint32_t w0 = s_fbits[2 * s], w1 = s_fbits[2 * s + 1];
+          d.x = ((w0 >> lane) & 1u) ? d.x * inv_f : 0.f;
+          d.y = ((w1 >> lane) & 1u) ? d.y * inv_f : 0.f;
+          *reinterpret_cast<float2*>(s_df + s * kF + 2 * lane) = d;
+        }
         __syncwarp();
-        float fa = b1a, fb = b1b;
-        const float4* hr = reinterpret_cast<const float4*>(sm + o.hbuf + warp * kE);
+        float2 acc = f2(0.f, 0.f);
 #pragma unroll
-        for (int c4 = 0; c4 < kE / 4; ++c4) {
-          const float4 x = hr[c4];
-          fa = fmaf(x.x, w1a[4 * c4], fa); fa = fmaf(x.y, w1a[4 * c4 + 1], fa);
-          fa = fmaf(x.z, w1a[4 * c4 + 2], fa); fa = fmaf(x.w, w1a[4 * c4 + 3], fa);
-          fb = fmaf(x.x, w1b[4 * c4], fb); fb = fmaf(x.y, w1b[4 * c4 + 1], fb);
-          fb = fmaf(x.z, w1b[4 * c4 + 2], fb); fb = fmaf(x.w, w1b[4 * c4 + 3], fb);
+        for (int j4 = 0; j4 < kF / 4; ++j4) {
+          const float4 x = lds4(s_df + s * kF + 4 * j4);
+          acc = fma2(f2(x.x, x.y), w1c[2 * j4], acc);
+          acc = fma2(f2(x.z, x.w), w1c[2 * j4 + 1], acc);
         }
-        bool ka = true, kb = true;
-        if (a.drop.mode == 1) {
-          const uint32_t ea = static_cast<uint32_t>(s * kF + lane), eb = ea + 32u;
-          ka = philox_u16(rng.block(2u, ea >> 3), ea & 7u) >= a.thr_f;
-          kb = philox_u16(rng.block(2u, eb >> 3), eb & 7u) >= a.thr_f;
-        } else if (a.drop.mode == 2) {
-          const uint8_t* mk = a.drop.mask_fc1 + (static_cast<long long>(b) * S + s) * kF;
-          ka = mk[lane] != 0; kb = mk[lane + 32] != 0;
-        }
-        const float sc = a.drop.mode != 0 ? a.inv_f : 1.f;
-        const float dfa = (fa > 0.f && ka) ? dfe[s * kF + lane] * sc : 0.f;
-        const float dfb = (fb > 0.f && kb) ? dfe[s * kF + 32 + lane] * sc : 0.f;
-        sm[o.df + s * kF + lane] = dfa;
-        sm[o.df + s * kF + 32 + lane] = dfb;
-        __syncwarp();
-        // dh[c] = sum_j df[j] W1[j][c]     (lane = c)
-        float dh = 0.f;
-        const float* dfr = sm + o.df + s * kF;
-#pragma unroll 8
-        for (int j = 0; j < kF; ++j) dh = fmaf(dfr[j], sm[o.w1 + j * kLdW + lane], dh);
-        dgamma = fmaf(dh, xhat, dgamma);
-        dbeta += dh;
+        const float dh = acc.x + acc.y;
+        g_gam = fmaf(dh, xh, g_gam);
+        g_bet += dh;
         const float dhg = dh * gam;
         const float m1 = warp_sum(dhg) * (1.f / kE);
-        const float m2 = warp_sum(dhg * xhat) * (1.f / kE);
-        sm[o.dr + s * kE + lane] = rstd * (dhg - m1 - xhat * m2);
-        __syncwarp();
+        const float m2 = warp_sum(dhg * xh) * (1.f / kE);
+        s_dr[s * kE + lane] = rs * (dhg - m1 - xh * m2);
+        s_xhat[s * kE + lane] = fmaf(xh, gam, bet);   // h, for dW1
       }
     }
     __syncthreads();
 
-    // ---- B1w: dW1 += df^T h ; db1 += sum_s df -------------------------------------------
+    // ---- B2: dW1, dWo (warps 0-7) | db1, dbo, dctx = dr Wo, D = dctx . ctx (warps 8-12) -------
+    ptx::mbar_wait(&bars[1], phase);
+    if (tid < 256) {
+      {
+        const int j = tid >> 2, c0 = (tid & 3) * 8;
+#pragma unroll 4
+        for (int s = 0; s < S; ++s) {
+          const float d = s_df[s * kF + j];
+          const float4 h0 = lds4(s_xhat + s * kE + c0), h1 = lds4(s_xhat + s * kE + c0 + 4);
+          axpy8(g_w1, d, h0, h1);
+        }
+      }
+      {
+        const int c = tid >> 3, j0 = (tid & 7) * 4;
+#pragma unroll 4
+        for (int s = 0; s < S; ++s) {
+          const float d = s_dr[s * kE + c];
+          const float4 x = lds4(s_ctx + s * kE + j0);
+          g_wo[0] = fma2(f2(d, d), f2(x.x, x.y), g_wo[0]);
+          g_wo[1] = fma2(f2(d, d), f2(x.z, x.w), g_wo[1]);
+        }
+      }
+    } else {
+      if (tid < 320) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += s_df[s * kF + (tid - 256)];
+        g_vec += acc;
+      } else if (tid < 352) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += s_dr[s * kE + (tid - 320)];
+        g_vec += acc;
+      }
+      float2 woc[kE / 2];   // column `lane` of Wo, packed along the output channel
+#pragma unroll
+      for (int c = 0; c < kE / 2; ++c)
+        woc[c] = f2(sm[o.wo + (2 * c) * kLdW + lane], sm[o.wo + (2 * c + 1) * kLdW + lane]);
+      ptx::mbar_wait(&bars[2], phase);   // s_stat's (m, 1/l) arrive by bulk copy; D joins them below
+      for (int s = warp - 8; s < S; s += kWarps - 8) {
+        float2 acc = f2(0.f, 0.f);
+#pragma unroll
+        for (int c4 = 0; c4 < kE / 4; ++c4) {
+          const float4 x = lds4(s_dr + s * kE + 4 * c4);
+          acc = fma2(f2(x.x, x.y), woc[2 * c4], acc);
+          acc = fma2(f2(x.z, x.w), woc[2 * c4 + 1], acc);
+        }
+        const float dc = acc.x + acc.y;
+        s_dctx[s * kE + lane] = dc;
+        // D[s][h] = sum_{j in head h} dctx[s][j] * ctx[s][j]   (= sum_t P_dropped dP)
+        float prod = dc * s_ctx[s * kE + lane];
+        prod += __shfl_xor_sync(0xffffffffu, prod, 1);
+        prod += __shfl_xor_sync(0xffffffffu, prod, 2);
+        prod += __shfl_xor_sync(0xffffffffu, prod, 4);
+        if ((lane & 7) == 0) s_stat[(s * kHeads + (lane >> 3)) * 4 + 2] = prod;
+      }
+    }
+    __syncthreads();
+
+    // ---- B3: attention backward ---------------------------------------------------------------
+    ptx::mbar_wait(&bars[2], phase);
+    // pass A: thread = (query s, head h), stream over keys -> dq
+    for (int i = tid; i < S * kHeads; i += kThreads) {
+      int h, s;
+      slot_to_pair(i, S, h, s);
+      float2 q2[4], dc2[4];
+      {
+        const float4 q0 = lds4(s_q + s * kE + h * kDh), q1 = lds4(s_q + s * kE + h * kDh + 4);
+        q2[0] = f2(q0.x, q0.y); q2[1] = f2(q0.z, q0.w); q2[2] = f2(q1.x, q1.y); q2[3] = f2(q1.z, q1.w);
+        const float4 c0 = lds4(s_dctx + s * kE + h * kDh), c1 = lds4(s_dctx + s * kE + h * kDh + 4);
+        dc2[0] = f2(c0.x * inv_a, c0.y * inv_a); dc2[1] = f2(c0.z * inv_a, c0.w * inv_a);
+        dc2[2] = f2(c1.x * inv_a, c1.y * inv_a); dc2[3] = f2(c1.z * inv_a, c1.w * inv_a);
+      }
+      const float4 stt = lds4(s_stat + (s * kHeads + h) * 4);   // m, 1/l, D
+      const uint4 bw = *reinterpret_cast<const uint4*>(s_abits + (h * S + s) * 4);
+      float2 acc[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+      const float* kh = s_k + h * kDh;
+      const float* vh = s_v + h * kDh;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t word = w == 0 ? bw.x : w == 1 ? bw.y : w == 2 ? bw.z : bw.w;
+        const int t_end = min(S, 32 * w + 32);
+#pragma unroll 4
+        for (int t = 32 * w; t < t_end; ++t) {
+          const float4 k0 = lds4(kh + t * kE), k1 = lds4(kh + t * kE + 4);
+          const float4 v0 = lds4(vh + t * kE), v1 = lds4(vh + t * kE + 4);
+          const float p = ex2(dot8(q2, k0, k1) - stt.x) * stt.y;
+          const float dp = dot8(dc2, v0, v1);                   // already carries 1/(1-p_drop)
+          const float ds = p * ((((word >> (t & 31)) & 1u) ? dp : 0.f) - stt.z);
+          axpy8(acc, ds, k0, k1);
+        }
+      }
+      // d(q) of the unscaled projection: d(score) * k / sqrt(head_dim)
+      *reinterpret_cast<float4*>(s_dq + s * kE + h * kDh) = make_float4(
+          acc[0].x * kInvSqrtDh, acc[0].y * kInvSqrtDh, acc[1].x * kInvSqrtDh, acc[1].y * kInvSqrtDh);
+      *reinterpret_cast<float4*>(s_dq + s * kE + h * kDh + 4) = make_float4(
+          acc[2].x * kInvSqrtDh, acc[2].y * kInvSqrtDh, acc[3].x * kInvSqrtDh, acc[3].y * kInvSqrtDh);
+    }
+    // pass B: thread = (key t, head h), stream over queries -> dk, dv
+    for (int i = tid; i < S * kHeads; i += kThreads) {
+      int h, t;
+      slot_to_pair(i, S, h, t);
+      float2 k2[4], v2[4];
+      {
+        const float4 k0 = lds4(s_k + t * kE + h * kDh), k1 = lds4(s_k + t * kE + h * kDh + 4);
+        k2[0] = f2(k0.x, k0.y); k2[1] = f2(k0.z, k0.w); k2[2] = f2(k1.x, k1.y); k2[3] = f2(k1.z, k1.w);
+        const float4 v0 = lds4(s_v + t * kE + h * kDh), v1 = lds4(s_v + t * kE + h * kDh + 4);
+        v2[0] = f2(v0.x * inv_a, v0.y * inv_a); v2[1] = f2(v0.z * inv_a, v0.w * inv_a);
+        v2[2] = f2(v1.x * inv_a, v1.y * inv_a); v2[3] = f2(v1.z * inv_a, v1.w * inv_a);
+      }
+      float2 ak[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+      float2 av[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+      const float* qh = s_q + h * kDh;
+      const float* ch = s_dctx + h * kDh;
+      const uint32_t* bh = s_abits + h * S * 4 + (t >> 5);
+      const int sh = t & 31;
+#pragma unroll 4
+      for (int s = 0; s < S; ++s) {
+        const float4 q0 = lds4(qh + s * kE), q1 = lds4(qh + s * kE + 4);
+        const float4 c0 = lds4(ch + s * kE), c1 = lds4(ch + s * kE + 4);
+        const float4 stt = lds4(s_stat + (s * kHeads + h) * 4);
+        const bool keep = (bh[s * 4] >> sh) & 1u;
+        const float p = ex2(dot8(k2, q0, q1) - stt.x) * stt.y;
+        const float dp = dot8(v2, c0, c1);
+        const float pk = keep ? p : 0.f;
+        const float ds = p * ((keep ? dp : 0.f) - stt.z);
+        axpy8(av, pk, c0, c1);
+        axpy8(ak, ds, q0, q1);
+      }
+      // the stored q carries log2(e)/sqrt(head_dim): d(k) = sum ds * q / sqrt(head_dim)
+      *reinterpret_cast<float4*>(s_dk + t * kE + h * kDh) =
+          make_float4(ak[0].x * kLn2, ak[0].y * kLn2, ak[1].x * kLn2, ak[1].y * kLn2);
+      *reinterpret_cast<float4*>(s_dk + t * kE + h * kDh + 4) =
+          make_float4(ak[2].x * kLn2, ak[2].y * kLn2, ak[3].x * kLn2, ak[3].y * kLn2);
+      *reinterpret_cast<float4*>(s_dv + t * kE + h * kDh) =
+          make_float4(av[0].x * inv_a, av[0].y * inv_a, av[1].x * inv_a, av[1].y * inv_a);
+      *reinterpret_cast<float4*>(s_dv + t * kE + h * kDh + 4) =
+          make_float4(av[2].x * inv_a, av[2].y * inv_a, av[3].x * inv_a, av[3].y * inv_a);
+    }
+    __syncthreads();
+
+    // ---- B4: de = dr + [dq dk dv] Win ; dPos ; d(embedding rows) ------------------------------
+    ptx::mbar_wait(&bars[3], phase);
+    {
+      float de[kRowsPerWarp];
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) de[i] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const float* src = j == 0 ? s_dq : (j == 1 ? s_dk : s_dv);
+        float2 wc[kE / 2];   // column `lane` of the j-th block of Win, packed along its rows
+#pragma unroll
+        for (int r = 0; r < kE / 2; ++r)
+          wc[r] = f2(sm[o.win + (32 * j + 2 * r) * kLdW + lane], sm[o.win + (32 * j + 2 * r + 1) * kLdW + lane]);
+#pragma unroll
+        for (int i = 0; i < kRowsPerWarp; ++i) {
+          const int s = warp + kWarps * i;
+          if (s < S) {
+            float2 acc = f2(0.f, 0.f);
+#pragma unroll
+            for (int r4 = 0; r4 < kE / 4; ++r4) {
+              const float4 x = lds4(src + s * kE + 4 * r4);
+              acc = fma2(f2(x.x, x.y), wc[2 * r4], acc);
+              acc = fma2(f2(x.z, x.w), wc[2 * r4 + 1], acc);
+            }
+            de[i] += acc.x + acc.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kRowsPerWarp; ++i) {
+        const int s = warp + kWarps * i;
+        if (s < S) {
+          const float d = de[i] + s_dr[s * kE + lane];
+          g_pos[i] += d;
+          // through the embedding dropout: scale or zero
+          s_dr[s * kE + lane] = ((s_ebits[s] >> lane) & 1u) ? d * inv_e : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- B5: dWin (warps 0-11) | dbin, embedding scatter-add (warp 12) ------------------------
+    if (tid < 384) {
+      const int oo = tid >> 2, c0 = (tid & 3) * 8;
+      const float* src = (oo < 32 ? s_dq : (oo < 64 ? s_dk : s_dv)) + (oo & 31);
+#pragma unroll 4
+      for (int s = 0; s < S; ++s) {
+        const float d = src[s * kE];
+        const float4 e0 = lds4(s_e + s * kE + c0), e1 = lds4(s_e + s * kE + c0 + 4);
+        axpy8(g_win, d, e0, e1);
+      }
+    } else {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int s = 0; s < S; ++s) {
+        a0 += s_dq[s * kE + lane];
+        a1 += s_dk[s * kE + lane];
+        a2 += s_dv[s * kE + lane];
+      }
+      g_bin[0] += a0; g_bin[1] += a1; g_bin[2] += a2;
+      // rows hit by several positions are summed in position order: deterministic, no atomics
+      if (hist_smem) {
+        for (int s = 0; s < S; ++s) sm[o.hist + s_tok[s] * kE + lane] += s_dr[s * kE + lane];
+      } else {
+        for (int s = 0; s < S; ++s) {
+          float* pe = part + a.lay.off_emb + static_cast<long long>(s_tok[s]) * kE + lane;
+          __stcg(pe, __ldcg(pe) + s_dr[s * kE + lane]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- flush this CTA's partial sums ------------------------------------------------------
+  sm[o.red + warp * kE + lane] = g_gam;
+  sm[o.red + (kWarps + warp) * kE + lane] = g_bet;
+  __syncthreads();
+  if (tid < 2 * kE) {
+    const int which = tid >> 5, c = tid & 31;
+    float acc = 0.f;
+    for (int w = 0; w < kWarps; ++w) acc += sm[o.red + (which * kWarps + w) * kE + c];
+    part[(which == 0 ? a.lay.off_lnw : a.lay.off_lnb) + c] = acc;
+  }
+  if (tid < 256) {
     {
       const int j = tid >> 2, c0 = (tid & 3) * 8;
-      float acc[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-      float g8[8], bt8[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { g8[u] = sm[o.lnw + c0 + u]; bt8[u] = sm[o.lnb + c0 + u]; }
-      for (int s = 0; s < S; ++s) {
-        const float d = sm[o.df + s * kF + j];
-        const float4* xr = reinterpret_cast<const float4*>(sm + o.xhat + s * kE + c0);
-        const float4 x0 = xr[0], x1 = xr[1];
-        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = fmaf(d, fmaf(xs[u], g8[u], bt8[u]), acc[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) sm[o.G + kG_w1 + j * kE + c0 + u] += acc[u];
-      if (tid < kF) {
-        float sacc = 0.f;
-        for (int s = 0; s < S; ++s) sacc += sm[o.df + s * kF + tid];
-        sm[o.G + kG_b1 + tid] += sacc;
-      }
-    }
-    __syncthreads();
-
-    // ---- B2: dctx = dr Wo (into df[0 : S*E]) ; D = dctx . ctx ; dWo, dbo ------------------
-    float* dctx = sm + o.df;
-    for (int s = warp; s < S; s += kWarps) {
-      float acc = 0.f;
-      const float* drr = sm + o.dr + s * kE;
-#pragma unroll 8
-      for (int c = 0; c < kE; ++c) acc = fmaf(drr[c], sm[o.wo + c * kLdW + lane], acc);
-      dctx[s * kE + lane] = acc;
-      // D[s][h] = sum_{j in head h} dctx[s][j] * ctx[s][j]   (= sum_t P_dropped dP)
-      float prod = acc * sm[o.ctx + s * kE + lane];
-      prod += __shfl_xor_sync(0xffffffffu, prod, 1);
-      prod += __shfl_xor_sync(0xffffffffu, prod, 2);
-      prod += __shfl_xor_sync(0xffffffffu, prod, 4);
-      if ((lane & 7) == 0) sm[o.drow + s * kHeads + (lane >> 3)] = prod;
+      float* p = part + a.lay.off_w1 + j * kE + c0;
+      *reinterpret_cast<float4*>(p) = make_float4(g_w1[0].x, g_w1[0].y, g_w1[1].x, g_w1[1].y);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(g_w1[2].x, g_w1[2].y, g_w1[3].x, g_w1[3].y);
     }
     {
       const int c = tid >> 3, j0 = (tid & 7) * 4;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int s = 0; s < S; ++s) {
-        const float d = sm[o.dr + s * kE + c];
-        const float4 x = *reinterpret_cast<const float4*>(sm + o.ctx + s * kE + j0);
-        acc[0] = fmaf(d, x.x, acc[0]); acc[1] = fmaf(d, x.y, acc[1]);
-        acc[2] = fmaf(d, x.z, acc[2]); acc[3] = fmaf(d, x.w, acc[3]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) sm[o.G + kG_wo + c * kE + j0 + u] += acc[u];
-      if (tid < kE) {
-        float sacc = 0.f;
-        for (int s = 0; s < S; ++s) sacc += sm[o.dr + s * kE + tid];
-        sm[o.G + kG_bo + tid] += sacc;
-      }
+      *reinterpret_cast<float4*>(part + a.lay.off_wo + c * kE + j0) =
+          make_float4(g_wo[0].x, g_wo[0].y, g_wo[1].x, g_wo[1].y);
     }
-    __syncthreads();
-
-    // ---- B3: attention backward. dq -> xhat buffer, dk -> ctx buffer, dv -> df[S*E : 2*S*E]
-    float* dq = sm + o.xhat;
-    float* dk = sm + o.ctx;
-    float* dv = sm + o.df + a.L * kE;
-    const float inv_a = a.drop.mode != 0 ? a.inv_a : 1.f;
-    const uint32_t* mbits = reinterpret_cast<const uint32_t*>(sm + o.maskbits);
-    // pass A: per (query s, head h) -> dq
-    float dq_out[2][kDh];
-#pragma unroll
-    for (int npairs = 0; npairs < 2; ++npairs) {
-      const int i = tid + npairs * kThreads;
-      if (i >= S * kHeads) break;
-      const int s = i / kHeads, h = i % kHeads;
-      float qr[kDh], dc[kDh], acc[kDh];
-#pragma unroll
-      for (int j = 0; j < kDh; ++j) {
-        qr[j] = sm[o.q + s * kE + h * kDh + j];
-        dc[j] = dctx[s * kE + h * kDh + j];
-        acc[j] = 0.f;
-      }
-      const float mx = sm[o.mrow + i], linv = 1.f / sm[o.lrow + i], D = sm[o.drow + i];
-      for (int t = 0; t < S; ++t) {
-        const float4* kp = reinterpret_cast<const float4*>(sm + o.k + t * kE + h * kDh);
-        const float4* vp = reinterpret_cast<const float4*>(sm + o.v + t * kE + h * kDh);
-        const float4 k0 = kp[0], k1 = kp[1], v0 = vp[0], v1 = vp[1];
-        float sc = qr[0] * k0.x;
-        sc = fmaf(qr[1], k0.y, sc); sc = fmaf(qr[2], k0.z, sc); sc = fmaf(qr[3], k0.w, sc);
-        sc = fmaf(qr[4], k1.x, sc); sc = fmaf(qr[5], k1.y, sc); sc = fmaf(qr[6], k1.z, sc);
-        sc = fmaf(qr[7], k1.w, sc);
-        const float p = expf(sc - mx) * linv;
-        float dp = dc[0] * v0.x;
-        dp = fmaf(dc[1], v0.y, dp); dp = fmaf(dc[2], v0.z, dp); dp = fmaf(dc[3], v0.w, dp);
-        dp = fmaf(dc[4], v1.x, dp); dp = fmaf(dc[5], v1.y, dp); dp = fmaf(dc[6], v1.z, dp);
-        dp = fmaf(dc[7], v1.w, dp);
-        const bool keep = (mbits[(h * S + s) * 4 + (t >> 5)] >> (t & 31)) & 1u;
-        const float ds = p * ((keep ? dp * inv_a : 0.f) - D);
-        acc[0] = fmaf(ds, k0.x, acc[0]); acc[1] = fmaf(ds, k0.y, acc[1]);
-        acc[2] = fmaf(ds, k0.z, acc[2]); acc[3] = fmaf(ds, k0.w, acc[3]);
-        acc[4] = fmaf(ds, k1.x, acc[4]); acc[5] = fmaf(ds, k1.y, acc[5]);
-        acc[6] = fmaf(ds, k1.z, acc[6]); acc[7] = fmaf(ds, k1.w, acc[7]);
-      }
-#pragma unroll
-      for (int j = 0; j < kDh; ++j) dq_out[npairs][j] = acc[j] * 0.35355339059327373f;
-    }
-    // pass B: per (key t, head h) -> dk, dv   (reads q, k, v, dctx; writes after the barrier)
-    float dk_out[2][kDh], dv_out[2][kDh];
-#pragma unroll
-    for (int npairs = 0; npairs < 2; ++npairs) {
-      const int i = tid + npairs * kThreads;
-      if (i >= S * kHeads) break;
-      const int t = i / kHeads, h = i % kHeads;
-      float kr[kDh], vr[kDh], ak[kDh], av[kDh];
-#pragma unroll
-      for (int j = 0; j < kDh; ++j) {
-        kr[j] = sm[o.k + t * kE + h * kDh + j];
-        vr[j] = sm[o.v + t * kE + h * kDh + j];
-        ak[j] = 0.f; av[j] = 0.f;
-      }
-      for (int s = 0; s < S; ++s) {
-        const float4* qp = reinterpret_cast<const float4*>(sm + o.q + s * kE + h * kDh);
-        const float4* cp = reinterpret_cast<const float4*>(dctx + s * kE + h * kDh);
-        const float4 q0 = qp[0], q1 = qp[1], c0 = cp[0], c1 = cp[1];
-        float sc = q0.x * kr[0];
-        sc = fmaf(q0.y, kr[1], sc); sc = fmaf(q0.z, kr[2], sc); sc = fmaf(q0.w, kr[3], sc);
-        sc = fmaf(q1.x, kr[4], sc); sc = fmaf(q1.y, kr[5], sc); sc = fmaf(q1.z, kr[6], sc);
-        sc = fmaf(q1.w, kr[7], sc);
-        const int sh = s * kHeads + h;
-        const float p = expf(sc - sm[o.mrow + sh]) / sm[o.lrow + sh];
-        float dp = c0.x * vr[0];
-        dp = fmaf(c0.y, vr[1], dp); dp = fmaf(c0.z, vr[2], dp); dp = fmaf(c0.w, vr[3], dp);
-        dp = fmaf(c1.x, vr[4], dp); dp = fmaf(c1.y, vr[5], dp); dp = fmaf(c1.z, vr[6], dp);
-        dp = fmaf(c1.w, vr[7], dp);
-        const bool keep = (mbits[(h * S + s) * 4 + (t >> 5)] >> (t & 31)) & 1u;
-        const float pd = keep ? p * inv_a : 0.f;
-        const float ds = p * ((keep ? dp * inv_a : 0.f) - sm[o.drow + sh]);
-        av[0] = fmaf(pd, c0.x, av[0]); av[1] = fmaf(pd, c0.y, av[1]);
-        av[2] = fmaf(pd, c0.z, av[2]); av[3] = fmaf(pd, c0.w, av[3]);
-        av[4] = fmaf(pd, c1.x, av[4]); av[5] = fmaf(pd, c1.y, av[5]);
-        av[6] = fmaf(pd, c1.z, av[6]); av[7] = fmaf(pd, c1.w, av[7]);
-        ak[0] = fmaf(ds, q0.x, ak[0]); ak[1] = fmaf(ds, q0.y, ak[1]);
-        ak[2] = fmaf(ds, q0.z, ak[2]); ak[3] = fmaf(ds, q0.w, ak[3]);
-        ak[4] = fmaf(ds, q1.x, ak[4]); ak[5] = fmaf(ds, q1.y, ak[5]);
-        ak[6] = fmaf(ds, q1.z, ak[6]); ak[7] = fmaf(ds, q1.w, ak[7]);
-      }
-#pragma unroll
-      for (int j = 0; j < kDh; ++j) { dk_out[npairs][j] = ak[j]; dv_out[npairs][j] = av[j]; }
-    }
-    __syncthreads();  // every reader of ctx / xhat / dctx is done: now overwrite the aliases
-#pragma unroll
-    for (int npairs = 0; npairs < 2; ++npairs) {
-      const int i = tid + npairs * kThreads;
-      if (i >= S * kHeads) break;
-      const int s = i / kHeads, h = i % kHeads;
-#pragma unroll
-      for (int j = 0; j < kDh; ++j) {
-        dq[s * kE + h * kDh + j] = dq_out[npairs][j];
-        dk[s * kE + h * kDh + j] = dk_out[npairs][j];
-        dv[s * kE + h * kDh + j] = dv_out[npairs][j];
-      }
-    }
-    __syncthreads();
-
-    // ---- B4: de = dr + dqkv Win ; dPos, dEmb ; dWin, dbin --------------------------------
-    for (int s = warp; s < S; s += kWarps) {
-      float acc = sm[o.dr + s * kE + lane];
-      const float* r0 = dq + s * kE;
-      const float* r1 = dk + s * kE;
-      const float* r2 = dv + s * kE;
-#pragma unroll 8
-      for (int oo = 0; oo < kE; ++oo) {
-        acc = fmaf(r0[oo], sm[o.win + oo * kLdW + lane], acc);
-        acc = fmaf(r1[oo], sm[o.win + (32 + oo) * kLdW + lane], acc);
-        acc = fmaf(r2[oo], sm[o.win + (64 + oo) * kLdW + lane], acc);
-      }
-      // the same (warp, lane) owns (s, c) for every sample this CTA processes: plain RMW
-      float* pp = part + a.lay.off_pos + s * kE + lane;
-      __stcg(pp, __ldcg(pp) + acc);
-      // gradient wrt the embedding row: through the embedding dropout (scale or zero)
-      float de = acc;
-      const int i = s * kE + lane;
-      if (a.drop.mode == 1) {
-        const uint4 r = rng.block(0u, static_cast<uint32_t>(i >> 3));
-        de = philox_u16(r, i & 7) >= a.thr_e ? de * a.inv_e : 0.f;
-      } else if (a.drop.mode == 2) {
-        de = a.drop.mask_embed[(static_cast<long long>(b) * S + s) * kE + lane] ? de * a.inv_e : 0.f;
-      }
-      sm[o.dr + s * kE + lane] = de;   // dr is dead from here on: reuse it as d(embedding rows)
-    }
-    __syncthreads();
-    {
-      // dWin[o][c] += sum_s dqkv[s][o] e[s][c]: 96 x 4 (o, c-group) pairs of 8 outputs each
-      for (int idx = tid; idx < 3 * kE * 4; idx += kThreads) {
-        const int oo = idx >> 2, c0 = (idx & 3) * 8;
-        const float* src = oo < 32 ? dq : (oo < 64 ? dk : dv);
-        const int col = oo & 31;
-        float acc[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-        for (int s = 0; s < S; ++s) {
-          const float d = src[s * kE + col];
-          const float4* er = reinterpret_cast<const float4*>(sm + o.e + s * kE + c0);
-          const float4 x0 = er[0], x1 = er[1];
-          acc[0] = fmaf(d, x0.x, acc[0]); acc[1] = fmaf(d, x0.y, acc[1]);
-          acc[2] = fmaf(d, x0.z, acc[2]); acc[3] = fmaf(d, x0.w, acc[3]);
-          acc[4] = fmaf(d, x1.x, acc[4]); acc[5] = fmaf(d, x1.y, acc[5]);
-          acc[6] = fmaf(d, x1.z, acc[6]); acc[7] = fmaf(d, x1.w, acc[7]);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) sm[o.G + kG_win + oo * kE + c0 + u] += acc[u];
-      }
-      if (tid < 3 * kE) {
-        const float* src = tid < 32 ? dq : (tid < 64 ? dk : dv);
-        float sacc = 0.f;
-        for (int s = 0; s < S; ++s) sacc += src[s * kE + (tid & 31)];
-        sm[o.G + kG_bin + tid] += sacc;
-      }
-      // dEmb: scatter-add over token ids. One warp walks the positions in order (lane = c), so
-      // rows hit by several positions are summed in a fixed order (deterministic, no atomics).
-      if (warp == kWarps - 1) {
-        const long long* tok = a.tokens + static_cast<long long>(b) * a.token_stride;
-        for (int s = 0; s < S; ++s) {
-          long long t = tok[s];
-          if (t < 0 || t >= a.vocab) t = 0;
-          float* pe = part + a.lay.off_emb + t * kE + lane;
-          __stcg(pe, __ldcg(pe) + sm[o.dr + s * kE + lane]);
-        }
-      }
-    }
-    __syncthreads();
+  } else if (tid < 320) {
+    part[a.lay.off_b1 + tid - 256] = g_vec;
+  } else if (tid < 352) {
+    part[a.lay.off_bo + tid - 320] = g_vec;
   }
-
-  // ---- flush this CTA's partial sums ---------------------------------------------------
-  sm[o.hbuf + warp * kE + lane] = dgamma;
-  __syncthreads();
-  if (tid < kE) {
-    float sacc = 0.f;
-    for (int w = 0; w < kWarps; ++w) sacc += sm[o.hbuf + w * kE + tid];
-    sm[o.G + kG_lnw + tid] = sacc;
+  if (tid < 384) {
+    const int oo = tid >> 2, c0 = (tid & 3) * 8;
+    float* p = part + a.lay.off_win + oo * kE + c0;
+    *reinterpret_cast<float4*>(p) = make_float4(g_win[0].x, g_win[0].y, g_win[1].x, g_win[1].y);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(g_win[2].x, g_win[2].y, g_win[3].x, g_win[3].y);
+  } else {
+    part[a.lay.off_bin + lane] = g_bin[0];
+    part[a.lay.off_bin + 32 + lane] = g_bin[1];
+    part[a.lay.off_bin + 64 + lane] = g_bin[2];
   }
-  __syncthreads();
-  sm[o.hbuf + warp * kE + lane] = dbeta;
-  __syncthreads();
-  if (tid < kE) {
-    float sacc = 0.f;
-    for (int w = 0; w < kWarps; ++w) sacc += sm[o.hbuf + w * kE + tid];
-    sm[o.G + kG_lnb + tid] = sacc;
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) {
+    const int s = warp + kWarps * i;
+    if (s < a.L) part[a.lay.off_pos + s * kE + lane] = g_pos[i];
   }
-  __syncthreads();
-  for (int i = tid; i < 3 * kE * kE; i += kThreads) part[a.lay.off_win + i] = sm[o.G + kG_win + i];
-  for (int i = tid; i < 3 * kE; i += kThreads) part[a.lay.off_bin + i] = sm[o.G + kG_bin + i];
-  for (int i = tid; i < kE * kE; i += kThreads) part[a.lay.off_wo + i] = sm[o.G + kG_wo + i];
-  for (int i = tid; i < kF * kE; i += kThreads) part[a.lay.off_w1 + i] = sm[o.G + kG_w1 + i];
-  for (int i = tid; i < kF; i += kThreads) part[a.lay.off_b1 + i] = sm[o.G + kG_b1 + i];
-  if (tid < kE) {
-    part[a.lay.off_bo + tid] = sm[o.G + kG_bo + tid];
-    part[a.lay.off_lnw + tid] = sm[o.G + kG_lnw + tid];
-    part[a.lay.off_lnb + tid] = sm[o.G + kG_lnb + tid];
-  }
+  if (hist_smem)
+    for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = sm[o.hist + i];
 }
 
 // grads[i] = sum over CTAs of partials[cta][i], fixed order.
@@ -694,8 +875,16 @@ struct ReduceArgs {
 __global__ void __launch_bounds__(256) small_grad_reduce_kernel(ReduceArgs r) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= r.total) return;
-  float s = 0.f;
-  for (int c = 0; c < r.grid; ++c) s += r.partials[static_cast<long long>(c) * r.total + i];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains, fixed order
+  int c = 0;
+  for (; c + 4 <= r.grid; c += 4) {
+    s0 += r.partials[static_cast<long long>(c) * r.total + i];
+    s1 += r.partials[static_cast<long long>(c + 1) * r.total + i];
+    s2 += r.partials[static_cast<long long>(c + 2) * r.total + i];
+    s3 += r.partials[static_cast<long long>(c + 3) * r.total + i];
+  }
+  for (; c < r.grid; ++c) s0 += r.partials[static_cast<long long>(c) * r.total + i];
+  const float s = (s0 + s1) + (s2 + s3);
   const SmallLayout& L = r.lay;
   float* dst;
   if (i < L.off_emb) dst = r.g.pos + (i - L.off_pos);
@@ -715,7 +904,10 @@ void fill_dropout(FrontArgs& a) {
   auto thr = [](double p) { return static_cast<uint32_t>(p * 65536.0 + 0.5); };
   auto inv = [](double p) { return 1.0f / static_cast<float>(1.0 - p); };
   a.thr_e = thr(a.drop.p_embed); a.thr_a = thr(a.drop.p_attn); a.thr_f = thr(a.drop.p_fc1);
-  a.inv_e = inv(a.drop.p_embed); a.inv_a = inv(a.drop.p_attn); a.inv_f = inv(a.drop.p_fc1);
+  const bool on = a.drop.mode != 0;
+  a.inv_e = on ? inv(a.drop.p_embed) : 1.f;
+  a.inv_a = on ? inv(a.drop.p_attn) : 1.f;
+  a.inv_f = on ? inv(a.drop.p_fc1) : 1.f;
 }
 
 int* g_err_flag = nullptr;  // device word: bit 0 = token id out of range
@@ -730,12 +922,14 @@ cudaError_t ensure_err_flag() {
 
 int* frontend_error_flag() { return g_err_flag; }
 
-size_t frontend_backward_smem_bytes(int L) { return static_cast<size_t>(make_smem(L, true).total) * 4; }
+size_t frontend_backward_smem_bytes(int L, int vocab) {
+  return static_cast<size_t>(make_bwd_smem(L, vocab).total) * 4;
+}
 
 cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, long long token_stride,
                                     int B, int S, int L, int vocab, const Dropout& drop,
-                                    __nv_bfloat16* feats, int num_sms, cudaStream_t stream,
-                                    float* feats_f32) {
+                                    __nv_bfloat16* feats, float* state, int num_sms,
+                                    cudaStream_t stream, float* feats_f32) {
   if (S < 1 || S > L || L > kMaxL) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
@@ -743,9 +937,10 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
   a.w = w; a.tokens = tokens; a.token_stride = token_stride;
   a.B = B; a.S = S; a.L = L; a.vocab = vocab; a.drop = drop; a.feats = feats;
   a.feats_f32 = feats_f32;
+  a.state = state; a.sl.init(L);
   a.err_flag = g_err_flag;
   fill_dropout(a);
-  const size_t smem = static_cast<size_t>(make_smem(L, false).total) * 4;
+  const size_t smem = static_cast<size_t>(make_fwd_smem(L).total) * 4;
   static size_t configured = 0;
   if (smem > configured) {
     e = cudaFuncSetAttribute(frontend_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -761,18 +956,19 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
 
 cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, long long token_stride,
                                      int B, int S, int L, int vocab, const Dropout& drop,
-                                     const float* dfeat, float* partials, int max_grid,
-                                     int* grid_out, int num_sms, cudaStream_t stream) {
-  if (S < 1 || S > L || L > kMaxL) return cudaErrorInvalidValue;
+                                     const float* dfeat, const float* state, float* partials,
+                                     int max_grid, int* grid_out, int num_sms, cudaStream_t stream) {
+  if (S < 1 || S > L || L > kMaxL || state == nullptr) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
   FrontArgs a{};
   a.w = w; a.tokens = tokens; a.token_stride = token_stride;
   a.B = B; a.S = S; a.L = L; a.vocab = vocab; a.drop = drop;
   a.dfeat = dfeat; a.partials = partials; a.lay.init(L, vocab);
+  a.state = const_cast<float*>(state); a.sl.init(L);
   a.err_flag = g_err_flag;
   fill_dropout(a);
-  const size_t smem = frontend_backward_smem_bytes(L);
+  const size_t smem = frontend_backward_smem_bytes(L, vocab);
   static size_t configured = 0;
   if (smem > configured) {
     e = cudaFuncSetAttribute(frontend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

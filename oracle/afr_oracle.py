@@ -277,29 +277,51 @@ def _philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def builtin_masks(cfg: OracleConfig, B: int, S: int, seed: int, step: int, sample_offset: int = 0):
-    """The keep-masks the CUDA kernels generate in dropout mode 1 (afr_sm100.h: afr_dropout):
-    element i of site s of global sample g at optimizer step t keeps iff the (i % 8)-th 16-bit
-    lane of Philox(counter=(i // 8, s, g, t), key=seed) is >= round(p * 65536)."""
-    def site_mask(site: int, n_elem: int, p: float):
+    """The keep-masks the CUDA kernels generate in dropout mode 1 (afr_sm100.h: afr_dropout,
+    csrc/afr_frontend.cu): one Philox4x32-10 call, key = seed, counter = (block, site | row << 2,
+    global sample g, optimizer step t), yields eight 16-bit lanes; an element keeps iff its lane is
+    >= round(p * 65536).
+      embedding (site 0): row 0, element i = s*E + c   -> block i // 8, lane i % 8
+      attention (site 1): row h*S + s, key t           -> block t // 8, lane t % 8
+      fc1       (site 2): row 0, element i = s*F + j   -> block i // 8, lane i % 8"""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+
+    def lanes(blk, c1, g):
+        n = blk.shape[0]
+        r = _philox4x32_10(blk, c1, np.full(n, g, np.uint32),
+                           np.full(n, step & 0xFFFFFFFF, np.uint32), k0, k1)
+        words = np.stack(r, axis=1)                                  # [n, 4]
+        return np.stack([words & 0xFFFF, words >> 16], axis=2).reshape(n, 8)
+
+    def flat_site(site: int, n_elem: int, p: float):
         thr = int(p * 65536.0 + 0.5)
         out = np.zeros((B, n_elem), dtype=bool)
         nblk = (n_elem + 7) // 8
         blk = np.arange(nblk, dtype=np.uint32)
         for b in range(B):
             g = np.uint32((sample_offset + b) & 0xFFFFFFFF)
-            r = _philox4x32_10(blk, np.full(nblk, site, np.uint32), np.full(nblk, g, np.uint32),
-                               np.full(nblk, step & 0xFFFFFFFF, np.uint32),
-                               seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-            words = np.stack(r, axis=1)                                  # [nblk, 4]
-            halves = np.stack([words & 0xFFFF, words >> 16], axis=2)     # [nblk, 4, 2]
-            u16 = halves.reshape(nblk * 8)[:n_elem]
+            u16 = lanes(blk, np.full(nblk, site, np.uint32), g).reshape(nblk * 8)[:n_elem]
             out[b] = u16 >= thr
         return out
+
+    def attn_site(p: float, H: int):
+        thr = int(p * 65536.0 + 0.5)
+        out = np.zeros((B, H * S, S), dtype=bool)
+        nblk = (S + 7) // 8
+        rows = np.repeat(np.arange(H * S, dtype=np.uint32), nblk)
+        blk = np.tile(np.arange(nblk, dtype=np.uint32), H * S)
+        c1 = (np.uint32(1) | (rows << np.uint32(2))).astype(np.uint32)
+        for b in range(B):
+            g = np.uint32((sample_offset + b) & 0xFFFFFFFF)
+            u16 = lanes(blk, c1, g).reshape(H * S, nblk * 8)[:, :S]
+            out[b] = u16 >= thr
+        return out
+
     E, H, Fh = cfg.embed_dim, cfg.num_heads, cfg.hidden
     return {
-        "embed": torch.from_numpy(site_mask(0, S * E, cfg.p_embed).reshape(B, S, E)),
-        "attn": torch.from_numpy(site_mask(1, H * S * S, cfg.p_attn).reshape(B, H, S, S)),
-        "fc1": torch.from_numpy(site_mask(2, S * Fh, cfg.p_fc1).reshape(B, S, Fh)),
+        "embed": torch.from_numpy(flat_site(0, S * E, cfg.p_embed).reshape(B, S, E)),
+        "attn": torch.from_numpy(attn_site(cfg.p_attn, H).reshape(B, H, S, S)),
+        "fc1": torch.from_numpy(flat_site(2, S * Fh, cfg.p_fc1).reshape(B, S, Fh)),
     }
 
 
