@@ -96,6 +96,7 @@ SIGNATURES = {
     "afr_workspace_copy": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),
     "afr_gemm_tiles": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     "afr_launch_count": (C.c_int64, [_P]),
+    "afr_debug_phase_cycles": (C.c_int, [_P, C.c_int]),
     "afr_debug_frontend_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int,
                                              C.POINTER(AfrDropout), _P, _P]),
     "afr_debug_frontend_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int,

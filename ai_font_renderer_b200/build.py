@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-]
+] + os.environ.get("AFR_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DAFR_PHASE_TIMING (tools/phase_timing.py)
 
 
 def _nvcc() -> str:

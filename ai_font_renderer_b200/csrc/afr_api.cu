@@ -22,7 +22,13 @@ struct afr_ctx {
   bool has_params = false, has_grads = false, has_state = false, shadow_valid = false;
   // private device buffers
   __nv_bfloat16* feats = nullptr;    // [max_batch, K]
-  __nv_bfloat16* wshadow = nullptr;  // [P, K]
+  // bf16 copy of fc_output.weight [P, K], double buffered (training contexts): the AdamW sweep of
+  // step t writes buffer 1 - shadow_cur on its own stream while the dgrad GEMM of step t still
+  // reads the buffer the forward used; the buffers swap once a sweep has covered all P rows.
+  __nv_bfloat16* wshadow_buf[2] = {nullptr, nullptr};
+  int shadow_cur = 0;                // what the next forward reads
+  int shadow_fwd = 0;                // what the last training forward read (dgrad reads it too)
+  int shadow_rows_swept = 0;         // rows already rewritten in buffer 1 - shadow_cur
   __nv_bfloat16* dz = nullptr;       // [max_batch, P]   unscaled (y - t) * mask
   float* dfeat = nullptr;            // [max_batch, K]
   float* logits = nullptr;           // [max_batch, P]   generic path, allocated on first use
@@ -136,8 +142,11 @@ int check_batch(afr_ctx* c, int B, int S, const void* tokens) {
 }
 
 int ensure_shadow(afr_ctx* c, cudaStream_t st) {
+  if (c->shadow_rows_swept != 0)
+    return fail(c, AFR_ERR_STATE, "a forward pass in the middle of an AdamW sweep over fc_output.weight "
+                                  "(afr_adamw_rows must cover every row before the next forward)");
   if (c->shadow_valid) return AFR_OK;
-  AFR_CUDA(c, launch_f32_to_bf16(c->params.wout, c->wshadow,
+  AFR_CUDA(c, launch_f32_to_bf16(c->params.wout, c->wshadow_buf[c->shadow_cur],
                                  static_cast<long long>(c->P) * c->K, st),
            "f32_to_bf16(fc_output.weight)");
   c->launches += 1;
@@ -221,7 +230,9 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
   alloc(reinterpret_cast<void**>(&c->feats), Bm * c->K * 2);
-  alloc(reinterpret_cast<void**>(&c->wshadow), static_cast<size_t>(c->P) * c->K * 2);
+  alloc(reinterpret_cast<void**>(&c->wshadow_buf[0]), static_cast<size_t>(c->P) * c->K * 2);
+  if (cfg->training)
+    alloc(reinterpret_cast<void**>(&c->wshadow_buf[1]), static_cast<size_t>(c->P) * c->K * 2);
   if (cfg->training) {
     alloc(reinterpret_cast<void**>(&c->dz), Bm * c->P * 2);
     alloc(reinterpret_cast<void**>(&c->dfeat), Bm * c->K * 4);
@@ -246,7 +257,7 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
 int afr_destroy(afr_ctx* c) {
   if (c == nullptr) return AFR_OK;
   DeviceGuard guard(c->cfg.device);
-  cudaFree(c->feats); cudaFree(c->wshadow); cudaFree(c->dz); cudaFree(c->dfeat);
+  cudaFree(c->feats); cudaFree(c->wshadow_buf[0]); cudaFree(c->wshadow_buf[1]); cudaFree(c->dz); cudaFree(c->dfeat);
   cudaFree(c->logits); cudaFree(c->loss_partials); cudaFree(c->bias_scratch);
   cudaFree(c->partials); cudaFree(c->fstate);
   delete c;
@@ -305,7 +316,7 @@ int afr_forward_eval(afr_ctx* c, const int64_t* tokens, int64_t token_stride, in
   if (env_int("AFR_NO_TMA_STORE")) ep.use_tma_store = 0;
   const char* msg = nullptr;
   const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
-  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow, c->K, false, B, c->P, c->K, bn,
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
                                    ep, c->num_sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
   c->launches += 1;
@@ -328,6 +339,7 @@ int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stri
   DeviceGuard guard(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((rc = ensure_shadow(c, st))) return rc;
+  c->shadow_fwd = c->shadow_cur;
   c->drop = to_dropout(dropout);
   c->tokens = reinterpret_cast<const long long*>(tokens);
   c->token_stride = token_stride;
@@ -342,7 +354,7 @@ int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stri
   ep.target = targets; ep.target_is_f32 = target_kind == AFR_TARGET_F32;
   ep.loss_partials = c->loss_partials;
   const char* msg = nullptr;
-  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow, c->K, false, B, c->P, c->K, bn,
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
                                    ep, c->num_sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward+loss)");
   AFR_CUDA(c, launch_loss_finalize(c->loss_partials, tiles * 4, loss_count, loss_out, st),
@@ -392,7 +404,7 @@ int afr_train_dgrad(afr_ctx* c, void* stream) {
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
   const int bn = choose_bn(c->B, c->K, c->num_sms, "AFR_BN_DGRAD");
-  cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow, c->K, true, c->B, c->K, c->P, bn,
+  cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow_buf[c->shadow_fwd], c->K, true, c->B, c->K, c->P, bn,
                                    ep, c->num_sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(dgrad)");
   if (!c->state_valid)
@@ -431,6 +443,7 @@ int afr_forward_train(afr_ctx* c, const int64_t* tokens, int64_t token_stride, i
     AFR_CUDA(c, cudaMalloc(&c->logits, static_cast<size_t>(c->cfg.max_batch) * c->P * 4),
              "cudaMalloc(logits)");
   if ((rc = ensure_shadow(c, st))) return rc;
+  c->shadow_fwd = c->shadow_cur;
   c->drop = to_dropout(dropout);
   c->tokens = reinterpret_cast<const long long*>(tokens);
   c->token_stride = token_stride;
@@ -442,7 +455,7 @@ int afr_forward_train(afr_ctx* c, const int64_t* tokens, int64_t token_stride, i
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
   const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
-  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow, c->K, false, B, c->P, c->K, bn,
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
                                    ep, c->num_sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
   AFR_CUDA(c, launch_clamp01(c->logits, sheet_out, static_cast<long long>(B) * c->P, st), "clamp01");
@@ -472,6 +485,7 @@ int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps
   if (!c) return AFR_ERR_INVALID;
   if (!c->has_params || !c->has_grads || !c->has_state)
     return fail(c, AFR_ERR_STATE, "params / grads / adam state not bound");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
   if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
     return fail(c, AFR_ERR_INVALID, "bad step or row range");
   DeviceGuard guard(c->cfg.device);
@@ -480,9 +494,16 @@ int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps
   const long long off = static_cast<long long>(row_begin) * c->K;
   const long long n = static_cast<long long>(row_end - row_begin) * c->K;
   AFR_CUDA(c, launch_adamw(c->params.wout + off, c->grads.wout + off, c->m.wout + off,
-                           c->v.wout + off, n, h, c->wshadow + off, c->num_sms, st),
+                           c->v.wout + off, n, h, c->wshadow_buf[1 - c->shadow_cur] + off,
+                           c->num_sms, st),
            "adamw(fc_output.weight)");
   c->launches += 1;
+  c->shadow_rows_swept += row_end - row_begin;
+  if (c->shadow_rows_swept >= c->P) {   // sweep complete: the next forward reads the new weights
+    c->shadow_cur ^= 1;
+    c->shadow_rows_swept = 0;
+    c->shadow_valid = true;
+  }
   return AFR_OK;
 }
 
@@ -539,7 +560,7 @@ int afr_workspace_ptr(afr_ctx* c, int which, void** ptr, size_t* bytes) {
     case 0: *ptr = c->feats; *bytes = Bm * c->K * 2; break;
     case 1: *ptr = c->dz; *bytes = c->dz ? Bm * c->P * 2 : 0; break;
     case 2: *ptr = c->dfeat; *bytes = c->dfeat ? Bm * c->K * 4 : 0; break;
-    case 3: *ptr = c->wshadow; *bytes = static_cast<size_t>(c->P) * c->K * 2; break;
+    case 3: *ptr = c->wshadow_buf[c->shadow_cur]; *bytes = static_cast<size_t>(c->P) * c->K * 2; break;
     case 4: *ptr = c->logits; *bytes = c->logits ? Bm * c->P * 4 : 0; break;
     default: return fail(c, AFR_ERR_INVALID, "unknown workspace id");
   }
@@ -569,6 +590,16 @@ int afr_gemm_tiles(afr_ctx* c, int B, int* out) {
 }
 
 int64_t afr_launch_count(const afr_ctx* c) { return c ? c->launches : 0; }
+
+int afr_debug_phase_cycles(unsigned long long* out, int reset) {
+  if (out == nullptr) return fail(nullptr, AFR_ERR_INVALID, "afr_debug_phase_cycles: out is NULL");
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = read_phase_cycles(out, reset);
+  if (e == cudaErrorNotSupported)
+    return fail(nullptr, AFR_ERR_UNSUPPORTED, "library was not built with -DAFR_PHASE_TIMING");
+  if (e != cudaSuccess) return fail_cuda(nullptr, e, "afr_debug_phase_cycles");
+  return AFR_OK;
+}
 
 int afr_debug_frontend_forward(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
                                const afr_dropout* dropout, float* feats_f32, void* stream) {

@@ -2,6 +2,8 @@
 // model.py:273, stepped at model.py:310), the bf16 shadow refresh, the loss finalisation
 // (mean of model.py:270), the fc_output bias gradient and the clamp backward of the generic
 // autograd path. All are 128-bit vectorised, coalesced, grid sized in multiples of the SM count.
+#include <cstdlib>
+
 #include "afr_internal.h"
 
 namespace afr {
@@ -27,13 +29,49 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v
   p = __fadd_rn(p, __fmul_rn(h.neg_step, __fdiv_rn(m, denom)));
 }
 
+// Grid-stride sweep, two independent 16-byte groups per thread and iteration (8 loads in flight
+// per thread before the first use).
+__device__ __forceinline__ void adamw_store(float* p, float* m, float* v, __nv_bfloat16* shadow,
+                                            long long i, const float4& pv, const float4& mv,
+                                            const float4& vv) {
+  reinterpret_cast<float4*>(p)[i] = pv;
+  reinterpret_cast<float4*>(m)[i] = mv;
+  reinterpret_cast<float4*>(v)[i] = vv;
+  if (shadow != nullptr) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y);
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(pv.z, pv.w);
+    uint2 packed;
+    packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+    packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(shadow)[i] = packed;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, long long n4, long long n, AdamHyper h,
              __nv_bfloat16* __restrict__ shadow) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i < n4; i += stride) {
+  for (; i + stride < n4; i += 2 * stride) {
+    const long long j = i + stride;
+    float4 pa = reinterpret_cast<float4*>(p)[i], pb = reinterpret_cast<float4*>(p)[j];
+    const float4 ga = ld_stream(reinterpret_cast<const float4*>(g) + i);
+    const float4 gb = ld_stream(reinterpret_cast<const float4*>(g) + j);
+    float4 ma = reinterpret_cast<float4*>(m)[i], mb = reinterpret_cast<float4*>(m)[j];
+    float4 va = reinterpret_cast<float4*>(v)[i], vb = reinterpret_cast<float4*>(v)[j];
+    adamw_elem(pa.x, ga.x, ma.x, va.x, h);
+    adamw_elem(pa.y, ga.y, ma.y, va.y, h);
+    adamw_elem(pa.z, ga.z, ma.z, va.z, h);
+    adamw_elem(pa.w, ga.w, ma.w, va.w, h);
+    adamw_store(p, m, v, shadow, i, pa, ma, va);
+    adamw_elem(pb.x, gb.x, mb.x, vb.x, h);
+    adamw_elem(pb.y, gb.y, mb.y, vb.y, h);
+    adamw_elem(pb.z, gb.z, mb.z, vb.z, h);
+    adamw_elem(pb.w, gb.w, mb.w, vb.w, h);
+    adamw_store(p, m, v, shadow, j, pb, mb, vb);
+  }
+  if (i < n4) {
     float4 pv = reinterpret_cast<float4*>(p)[i];
     const float4 gv = ld_stream(reinterpret_cast<const float4*>(g) + i);
     float4 mv = reinterpret_cast<float4*>(m)[i];
@@ -42,17 +80,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     adamw_elem(pv.y, gv.y, mv.y, vv.y, h);
     adamw_elem(pv.z, gv.z, mv.z, vv.z, h);
     adamw_elem(pv.w, gv.w, mv.w, vv.w, h);
-    reinterpret_cast<float4*>(p)[i] = pv;
-    reinterpret_cast<float4*>(m)[i] = mv;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    if (shadow != nullptr) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y);
-      const __nv_bfloat162 hi = __floats2bfloat162_rn(pv.z, pv.w);
-      uint2 packed;
-      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
-      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
-      reinterpret_cast<uint2*>(shadow)[i] = packed;
-    }
+    adamw_store(p, m, v, shadow, i, pv, mv, vv);
   }
   // scalar tail (n not a multiple of 4)
   if (blockIdx.x == 0) {
@@ -180,7 +208,15 @@ int stream_grid(long long work_items, int threads, int num_sms) {
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n,
                          const AdamHyper& h, __nv_bfloat16* shadow, int num_sms, cudaStream_t s) {
   const long long n4 = n / 4;
-  adamw_kernel<<<stream_grid(n4, 256, num_sms), 256, 0, s>>>(p, g, m, v, n4, n, h, shadow);
+  static const int ctas_per_sm = [] {
+    const char* e = std::getenv("AFR_ADAMW_CTAS");   // tuning knob; 8 x 256 threads per SM by default
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 && v <= 8 ? v : 8;
+  }();
+  long long blocks = (n4 + 511) / 512;
+  if (blocks > static_cast<long long>(num_sms) * ctas_per_sm) blocks = static_cast<long long>(num_sms) * ctas_per_sm;
+  if (blocks < 1) blocks = 1;
+  adamw_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, m, v, n4, n, h, shadow);
   return cudaGetLastError();
 }
 

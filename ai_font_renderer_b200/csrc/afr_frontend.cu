@@ -40,6 +40,31 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kInvSqrtDh = 0.35355339059327373f;              // math.sqrt(1.0 / 8)
 constexpr int kEmbSmemMaxVocab = 256;                           // dEmb table in smem up to here
 
+// Optional per-phase cycle counters (nvcc -DAFR_PHASE_TIMING, see tools/phase_timing.py): thread 0
+// of every CTA accumulates clock64() deltas between the marks below; summed over CTAs at exit.
+#ifdef AFR_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[2][16];
+#define AFR_TICK_DECL long long tacc_[16] = {0}; long long tlast_ = clock64();
+#define AFR_TICK(k)                                                   \
+  do {                                                                \
+    if (threadIdx.x == 0) {                                           \
+      const long long now_ = clock64();                               \
+      tacc_[k] += now_ - tlast_;                                      \
+      tlast_ = now_;                                                  \
+    }                                                                 \
+  } while (0)
+#define AFR_TICK_FLUSH(kernel)                                        \
+  do {                                                                \
+    if (threadIdx.x == 0)                                             \
+      for (int k_ = 0; k_ < 16; ++k_)                                 \
+        atomicAdd(&g_phase_cycles[kernel][k_], static_cast<unsigned long long>(tacc_[k_])); \
+  } while (0)
+#else
+#define AFR_TICK_DECL
+#define AFR_TICK(k)
+#define AFR_TICK_FLUSH(kernel)
+#endif
+
 struct FrontArgs {
   Tensors w;
   const long long* tokens;
@@ -184,7 +209,9 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
   float* sk = sm + o.k;
   float* sv = sm + o.v;
 
+  AFR_TICK_DECL
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    AFR_TICK(0);
     const Rng rng{static_cast<uint32_t>(a.drop.seed), static_cast<uint32_t>(a.drop.seed >> 32),
                   static_cast<uint32_t>(a.drop.sample_offset + b), static_cast<uint32_t>(a.drop.step)};
     const long long* tok = a.tokens + static_cast<long long>(b) * a.token_stride;
@@ -236,7 +263,9 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
         if (valid && (tid & 3) == 0) reinterpret_cast<uint32_t*>(st + a.sl.ebits)[i8 >> 2] = wbits;
       }
     }
+    AFR_TICK(1);
     __syncthreads();
+    AFR_TICK(2);
 
     // ---- (2) packed in-projection q|k|v = e Win^T + bin  (torch functional.py:5836) -----------
     // lane = output channel; its weight row lives in registers, the e row is broadcast.
@@ -263,7 +292,9 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
         if (gdst != nullptr) gdst[s * kE + lane] = r;
       }
     }
+    AFR_TICK(3);
     __syncthreads();
+    AFR_TICK(4);
 
     // ---- (3) per (query s, head h): ctx = dropout(softmax(q k^T)) v   (functional.py:6642-6647)
     for (int i = tid; i < S * kHeads; i += kThreads) {
@@ -343,7 +374,9 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
       if (st != nullptr)
         *reinterpret_cast<float4*>(st + a.sl.stat + (s * kHeads + h) * 4) = make_float4(m, linv, 0.f, 0.f);
     }
+    AFR_TICK(5);
     __syncthreads();
+    AFR_TICK(6);
 
     // ---- (4a) out-projection + residual + LayerNorm (model.py:180); h overwrites e ----------
     {
@@ -377,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
       }
     }
     __syncwarp();   // (4b) reads only the rows this warp wrote in (4a)
+    AFR_TICK(7);
 
     // ---- (4b) f = dropout(relu(fc1(h)))  (model.py:183-184). lane owns features 2*lane, 2*lane+1
     {
@@ -442,8 +476,11 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
           reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF)[i] = make_float2(0.f, 0.f);
       }
     }
+    AFR_TICK(8);
     __syncthreads();
+    AFR_TICK(9);
   }
+  AFR_TICK_FLUSH(0);
 }
 
 // =========================================================================== backward kernel
@@ -539,6 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
 
   const float inv_e = a.inv_e, inv_a = a.inv_a, inv_f = a.inv_f;
   uint32_t phase = 0;
+  AFR_TICK_DECL
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x, phase ^= 1u) {
     // ---- stage this sample's record: four groups, each waited for right before its first use
@@ -569,9 +607,11 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
       if (t < 0 || t >= a.vocab) t = 0;
       s_tok[tid] = static_cast<int>(t);
     }
+    AFR_TICK(0);
 
     // ---- B1: df = dfeat * ReLU' * dropout ; dh = df W1 ; LayerNorm backward -> dr ; h --------
     ptx::mbar_wait(&bars[0], phase);
+    AFR_TICK(1);
     {
       float2 w1c[kF / 2];   // column `lane` of W1, packed along the feature index
 #pragma unroll
@@ -606,10 +646,13 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
         s_xhat[s * kE + lane] = fmaf(xh, gam, bet);   // h, for dW1
       }
     }
+    AFR_TICK(2);
     __syncthreads();
+    AFR_TICK(3);
 
     // ---- B2: dW1, dWo (warps 0-7) | db1, dbo, dctx = dr Wo, D = dctx . ctx (warps 8-12) -------
     ptx::mbar_wait(&bars[1], phase);
+    AFR_TICK(4);
     if (tid < 256) {
       {
         const int j = tid >> 2, c0 = (tid & 3) * 8;
@@ -663,10 +706,13 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
         if ((lane & 7) == 0) s_stat[(s * kHeads + (lane >> 3)) * 4 + 2] = prod;
       }
     }
+    AFR_TICK(5);
     __syncthreads();
+    AFR_TICK(6);
 
     // ---- B3: attention backward ---------------------------------------------------------------
     ptx::mbar_wait(&bars[2], phase);
+    AFR_TICK(7);
     // pass A: thread = (query s, head h), stream over keys -> dq
     for (int i = tid; i < S * kHeads; i += kThreads) {
       int h, s;
@@ -704,6 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
       *reinterpret_cast<float4*>(s_dq + s * kE + h * kDh + 4) = make_float4(
           acc[2].x * kInvSqrtDh, acc[2].y * kInvSqrtDh, acc[3].x * kInvSqrtDh, acc[3].y * kInvSqrtDh);
     }
+    AFR_TICK(8);
     // pass B: thread = (key t, head h), stream over queries -> dk, dv
     for (int i = tid; i < S * kHeads; i += kThreads) {
       int h, t;
@@ -745,10 +792,13 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
       *reinterpret_cast<float4*>(s_dv + t * kE + h * kDh + 4) =
           make_float4(av[2].x * inv_a, av[2].y * inv_a, av[3].x * inv_a, av[3].y * inv_a);
     }
+    AFR_TICK(9);
     __syncthreads();
+    AFR_TICK(10);
 
     // ---- B4: de = dr + [dq dk dv] Win ; dPos ; d(embedding rows) ------------------------------
     ptx::mbar_wait(&bars[3], phase);
+    AFR_TICK(11);
     {
       float de[kRowsPerWarp];
 #pragma unroll
@@ -786,7 +836,9 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
         }
       }
     }
+    AFR_TICK(12);
     __syncthreads();
+    AFR_TICK(13);
 
     // ---- B5: dWin (warps 0-11) | dbin, embedding scatter-add (warp 12) ------------------------
     if (tid < 384) {
@@ -816,8 +868,11 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
         }
       }
     }
+    AFR_TICK(14);
   }
   __syncthreads();
+  AFR_TICK(15);
+  AFR_TICK_FLUSH(1);
 
   // ---- flush this CTA's partial sums ------------------------------------------------------
   sm[o.red + warp * kE + lane] = g_gam;
@@ -921,6 +976,20 @@ cudaError_t ensure_err_flag() {
 }  // namespace
 
 int* frontend_error_flag() { return g_err_flag; }
+
+cudaError_t read_phase_cycles(unsigned long long* host, int reset) {
+#ifdef AFR_PHASE_TIMING
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_phase_cycles, sizeof(unsigned long long) * 32);
+  if (e == cudaSuccess && reset) {
+    static const unsigned long long zeros[32] = {0};
+    e = cudaMemcpyToSymbol(g_phase_cycles, zeros, sizeof(zeros));
+  }
+  return e;
+#else
+  (void)host; (void)reset;
+  return cudaErrorNotSupported;
+#endif
+}
 
 size_t frontend_backward_smem_bytes(int L, int vocab) {
   return static_cast<size_t>(make_bwd_smem(L, vocab).total) * 4;

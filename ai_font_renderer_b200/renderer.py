@@ -174,8 +174,18 @@ class AttentionFontRenderer(nn.Module):
         self.dropout_step = 0
         self._ctx: Optional[_Context] = None
         self._scratch: Optional[list] = None
+        self._side: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------ plumbing
+    def side_stream(self) -> torch.cuda.Stream:
+        """Second CUDA stream of the training step: the HBM-bound AdamW sweep over
+        fc_output.weight runs here, concurrently with the GEMMs / front-end backward that the
+        compute (current) stream runs (training.backward_and_step)."""
+        dev = self.fc_output.weight.device
+        if self._side is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
+
     def _ordered_params(self):
         sd = dict(self.named_parameters())
         return [sd[k] for k in _lib.STATE_DICT_KEYS]

@@ -53,6 +53,7 @@ class TrainConfig:
     test_strings: Sequence[str] = field(default_factory=list)
     render_every: int = 5
     grad_buckets: int = 8            # row buckets of fc_output.weight.grad (data parallel overlap)
+    adam_buckets: int = 1            # single GPU: row buckets of the wgrad GEMM / AdamW sweep
     max_steps: Optional[int] = None  # stop after this many optimizer steps (tests / smoke)
     quiet: bool = False
 
@@ -103,46 +104,55 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
 def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool = True, marks=None):
     """loss.backward(); optimizer.step() (model.py:309-310) for one rank of a data-parallel job.
 
-    world == 1: wgrad, dgrad + front-end backward, one AdamW sweep.
-    world  > 1: fc_output.weight.grad is produced bucket by bucket (row ranges); each bucket's
+    world == 1: wgrad, the AdamW sweep over fc_output.weight (right behind the gradient that is
+    still partly in L2), dgrad, the front-end backward, the small-tensor AdamW -- one stream.
+    (Measured on B200, tools/overlap_probe.py: running the HBM-bound sweep on a second stream
+    under the GEMMs / front-end backward buys nothing -- those kernels take the SM's whole
+    shared-memory carveout, the sweep then runs with ~no L1 and both slow down by what the
+    overlap saves.) The sweep writes the inactive copy of the bf16 shadow weights, so the dgrad
+    GEMM behind it still reads the weights the forward used.
+
+    world > 1: fc_output.weight.grad is produced bucket by bucket (row ranges); each bucket's
     all-reduce is enqueued on NCCL's stream right behind its wgrad GEMM and runs under the later
-    buckets, the dgrad GEMM and the front-end backward; AdamW then consumes the buckets in order
-    while later reductions are still in flight. `marks`, if given, is called with a label between
-    phases (bench.py records CUDA events there)."""
+    buckets, the dgrad GEMM and the front-end backward; the model's side stream waits for each
+    reduction and runs that bucket's AdamW sweep; the streams join at the end of the step.
+    `marks(label)`, if given, is called at phase boundaries with the stream to record on current
+    (bench.py records CUDA events there): 'wgrad', 'dgrad', 'tail' on the compute stream,
+    'adamw_begin' / 'adamw_end' around every sweep launch."""
     mark = marks or (lambda label: None)
-    if world == 1:
-        model.fused_backward(buckets, (lambda i, lo, hi: mark("wgrad")) if marks else None)
-        mark("dgrad")
-        t_step = optimizer.begin_step()
-        optimizer.step_rows(t_step, 0, buckets[-1][1])
-        mark("adamw")                         # the fc_output.weight sweep alone
-        optimizer.step_small(t_step)
-        optimizer.end_step()
-        return
+    dev = model.fc_output.weight.device
+    main = torch.cuda.current_stream(dev)
+    side = model.side_stream() if world > 1 else main
     model._param_grads()
     wgrad = model.fc_output.weight.grad
-    works = []
+    t_step = optimizer.begin_step()
+    last = len(buckets) - 1
 
-    def reduce_bucket(i, r0, r1):
-        works.append(dist.all_reduce(wgrad[r0:r1], op=dist.ReduceOp.SUM, async_op=True))
-        if i == len(buckets) - 1:
+    def after_bucket(i, r0, r1):
+        if world > 1:
+            work = dist.all_reduce(wgrad[r0:r1], op=dist.ReduceOp.SUM, async_op=True)
+            with torch.cuda.stream(side):
+                work.wait()                       # stream-level wait on NCCL, no host sync
+        if i == last:
             mark("wgrad")
+        with torch.cuda.stream(side):
+            mark("adamw_begin")
+            optimizer.step_rows(t_step, r0, r1)
+            mark("adamw_end")
 
     if has_samples:
-        model.fused_backward(buckets, reduce_bucket)
+        model.fused_backward(buckets, after_bucket)
     else:
         for i, (r0, r1) in enumerate(buckets):
-            reduce_bucket(i, r0, r1)
+            after_bucket(i, r0, r1)
     mark("dgrad")
-    small = dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM, async_op=True)
-    t_step = optimizer.begin_step()
-    for w, (r0, r1) in zip(works, buckets):
-        w.wait()                              # stream-level wait on NCCL, no host sync
-        optimizer.step_rows(t_step, r0, r1)   # overlaps the next bucket's all-reduce
-    small.wait()
+    if world > 1:
+        dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM)   # ordered on the compute stream
     optimizer.step_small(t_step)
+    if side is not main:
+        main.wait_stream(side)
     optimizer.end_step()
-    mark("adamw")
+    mark("tail")
 
 
 class Trainer:
@@ -174,7 +184,7 @@ class Trainer:
             self.optimizer, mode="min", factor=cfg.scheduler_factor,
             patience=cfg.scheduler_patience, min_lr=cfg.min_learning_rate)            # model.py:276-278
         self.P = cfg.sheet_height * cfg.sheet_width
-        self.buckets = row_buckets(self.P, cfg.grad_buckets if self.world > 1 else 1)
+        self.buckets = row_buckets(self.P, cfg.grad_buckets if self.world > 1 else cfg.adam_buckets)
         self.steps_done = 0
 
     # ------------------------------------------------------------------ one optimizer step

@@ -42,6 +42,7 @@ UNIT = "glyphs/s"
 K_FEAT, P_PIX, N_PARAMS_W = 6400, 19200, 19200 * 6400
 GEMM_FLOP_PER_GLYPH = 3 * 2 * K_FEAT * P_PIX          # fwd + dgrad + wgrad of fc_output
 ADAMW_BYTES_PER_PARAM = 30                            # p,g,m,v read; p,m,v write; bf16 shadow write
+ADAMW_TRAFFIC_NCU = 3629e6                            # dram read+write per full sweep, profiles/r01_ncu_summary.md
 
 
 def load_peaks():
@@ -172,6 +173,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--adam-buckets", type=int, default=1,
+                    help="single GPU: row buckets of the wgrad GEMM / AdamW sweep over fc_output.weight")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,23 +209,29 @@ def main():
     tok_h, tgt_h = fast_synthetic_batch(B * n_rot, seed=1234 + rank)
     tok_h, tgt_h = tok_h.pin_memory(), tgt_h.pin_memory()
     tok_d, tgt_d = tok_h.to(device), tgt_h.to(device)
-    buckets = row_buckets(P_PIX, 8 if world > 1 else 1)
+    buckets = row_buckets(P_PIX, 8 if world > 1 else args.adam_buckets)
     count = float(gB) * P_PIX
     loss_buf = torch.zeros(args.steps + args.warmup + 8, dtype=torch.float32, device=device)
-    phases = ("forward", "wgrad", "dgrad", "adamw")
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(phases) + 1)]
-          for _ in range(args.steps)]
 
-    def step_resident(i, events=None):
+    class Marks:
+        """CUDA events on whatever stream is current when a phase boundary is reached."""
+        def __init__(self):
+            self.ev = {}
+
+        def __call__(self, label):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.setdefault(label, []).append(e)
+
+    step_marks = [Marks() for _ in range(args.steps)]
+
+    def step_resident(i, marks=None):
         s = (i % n_rot) * B
         x, t = tok_d[s:s + B], tgt_d[s:s + B]
-        marks = None
-        if events is not None:
-            events[0].record()
-            order = {"forward": 1, "wgrad": 2, "dgrad": 3, "adamw": 4}
-            marks = lambda label: events[order[label]].record()
+        if marks is not None:
+            marks("start")
         model.fused_forward_loss(x, t, loss_count=count, sample_offset=rank * B, loss_out=loss_buf[i])
-        if marks:
+        if marks is not None:
             marks("forward")
         backward_and_step(model, opt, buckets, world, marks=marks)
 
@@ -250,7 +259,7 @@ def main():
         launches0 = model.kernel_launches()
         e0.record()
         for i in range(k):
-            fn(i, ev[i]) if with_events else fn(i)
+            fn(i, step_marks[i]) if with_events else fn(i)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -275,9 +284,35 @@ def main():
     model.check_tokens_in_range()
     final_loss = float(loss_buf[args.steps - 1])
 
-    # per-phase device times (this rank), averaged over the timed steps
-    phase_ms = {p: sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(args.steps)) / args.steps
-                for j, p in enumerate(phases)}
+    # per-phase device times (this rank), averaged over the timed steps. Compute stream:
+    # forward | wgrad | dgrad + front-end backward | tail (small AdamW + join with the side stream).
+    # Side stream: every AdamW sweep launch, begin -> end.
+    order = ("start", "forward", "wgrad", "dgrad", "tail")
+    phase_ms = {}
+    for a, b_ in zip(order, order[1:]):
+        phase_ms[b_] = sum(m.ev[a][0].elapsed_time(m.ev[b_][0]) for m in step_marks) / args.steps
+    # single GPU: the AdamW sweep sits between the 'wgrad' and 'dgrad' marks of the one stream
+    adam_launch_ms = [x.elapsed_time(y) for m in step_marks
+                      for x, y in zip(m.ev["adamw_begin"], m.ev["adamw_end"])]
+    adamw_ms_per_launch = sum(adam_launch_ms) / len(adam_launch_ms)
+    adamw_ms_per_step = sum(adam_launch_ms) / args.steps
+    phase_ms["adamw_side_stream"] = adamw_ms_per_step
+
+    # the same sweep alone on the device (nothing else running), for reference
+    iso = []
+    if world == 1:
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_step = opt.begin_step()
+            torch.cuda.synchronize()
+            e0.record()
+            opt.step_rows(t_step, 0, P_PIX)
+            e1.record()
+            opt.step_small(t_step)
+            opt.end_step()
+            torch.cuda.synchronize()
+            iso.append(e0.elapsed_time(e1))
+    adamw_iso_ms = min(iso) if iso else None
 
     if rank != 0:
         if world > 1:
@@ -288,7 +323,7 @@ def main():
     value = gB * args.steps / (ms_res / 1e3)
     e2e_value = gB * args.steps / (ms_e2e / 1e3)
     adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
-    adamw_gbs = adamw_bytes / (phase_ms["adamw"] / 1e3) / 1e9
+    adamw_gbs = adamw_bytes / (adamw_ms_per_step / 1e3) / 1e9
     gemm_tf = B * GEMM_FLOP_PER_GLYPH / ((phase_ms["forward"] + phase_ms["wgrad"] + phase_ms["dgrad"]) / 1e3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -300,10 +335,13 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "adamw_kernel (fc_output.weight sweep + bf16 shadow)", "bound": "hbm",
-                     "achieved": adamw_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": adamw_gbs / peaks["hbm"], "traffic": None,
-                     "algorithmic_bytes_per_launch": adamw_bytes, "ms_per_launch": phase_ms["adamw"],
+        "roofline": {"kernel": "adamw_kernel (fc_output.weight sweep + bf16 shadow)",
+                     "bound": "hbm", "achieved": adamw_gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": adamw_gbs / peaks["hbm"], "traffic": ADAMW_TRAFFIC_NCU,
+                     "algorithmic_bytes_per_launch": adamw_bytes // len(buckets),
+                     "launches_per_step": len(buckets), "ms_per_launch": adamw_ms_per_launch,
+                     "alone_ms_per_sweep": adamw_iso_ms,
+                     "alone_frac": (adamw_bytes / (adamw_iso_ms / 1e3) / 1e9 / peaks["hbm"]) if adamw_iso_ms else None,
                      "peak_source": peaks["source"]},
         "gemm": {"tflops_incl_frontend_and_epilogues": gemm_tf,
                  "frac_of_bf16_sustained_peak": gemm_tf / peaks["tf_sustained"],

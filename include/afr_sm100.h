@@ -173,6 +173,11 @@ int afr_gemm_tiles(afr_ctx* ctx, int B, int* out_bn3);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t afr_launch_count(const afr_ctx* ctx);
 
+/* Profiling builds only (nvcc -DAFR_PHASE_TIMING): copies 2 x 16 clock64() cycle counters (front-end
+ * forward, front-end backward; summed over CTAs) into `out` and optionally resets them.
+ * AFR_ERR_UNSUPPORTED in a normal build. Synchronises the device. */
+int afr_debug_phase_cycles(unsigned long long* out, int reset);
+
 /* Test hooks: the fp32 front-end (embedding / attention / LayerNorm / fc1, model.py:167-193) in
  * isolation, so its forward and backward can be checked at fp32 tolerance without the bf16 GEMM
  * in between. Forward writes the features as fp32 [B, 64*max_length]; backward takes

@@ -52,6 +52,36 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float x, float y
         const float4 v = sm[(it + r) & 255];
         a[r] += v.x + v.y + v.z + v.w;
       }
+    } else if (MODE == 5) {   // LDS.128, 4 distinct addresses per warp (lane & 3)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float4 v = sm[(it + r * 4 + (threadIdx.x & 3)) & 255];
+        a[r] += v.x + v.y + v.z + v.w;
+      }
+    } else if (MODE == 6) {   // LDS.128, 2 distinct addresses per warp (lane >> 4)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float4 v = sm[(it + r * 2 + ((threadIdx.x >> 4) & 1)) & 255];
+        a[r] += v.x + v.y + v.z + v.w;
+      }
+    } else if (MODE == 7) {   // LDS.32, conflict-free (lane-consecutive words)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float v = reinterpret_cast<const float*>(sm)[(it * 32 + r * 32 + (threadIdx.x & 31)) & 1023];
+        a[r] += v;
+      }
+    } else if (MODE == 8) {   // LDS.128, every lane its own 16 bytes (512 B per warp)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float4 v = sm[(it * 32 + r * 32 + (threadIdx.x & 31)) & 255];
+        a[r] += v.x + v.y + v.z + v.w;
+      }
+    } else if (MODE == 9) {   // LDS.64 uniform
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float2 v = reinterpret_cast<const float2*>(sm)[(it + r) & 511];
+        a[r] += v.x + v.y;
+      }
     }
   }
   float s = 0.f;
@@ -86,12 +116,17 @@ void run(const char* name, double ops_per_iter_per_thread, int ctas_per_sm) {
 }
 
 int main() {
-  for (int c : {2, 4, 8}) {
+  for (int c : {2, 8}) {
     run<0>("ffma", 32, c);
     run<1>("ffma2", 64, c);
     run<2>("ex2", 32, c);
     run<3>("lds+4fma", 8, c);      // counts LDS.128 per iter
     run<4>("lds+4add", 8, c);
+    run<5>("lds128x4a", 8, c);
+    run<6>("lds128x2a", 8, c);
+    run<7>("lds32", 8, c);
+    run<8>("lds128all", 8, c);
+    run<9>("lds64uni", 8, c);
   }
   return 0;
 }
