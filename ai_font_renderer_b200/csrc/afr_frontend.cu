@@ -122,6 +122,16 @@ __device__ __forceinline__ float warp_sum(float x) {
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
+// two independent butterfly sums at once (the shuffles of one hide the latency of the other)
+__device__ __forceinline__ void warp_sum2(float& x, float& y) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float xo = __shfl_xor_sync(0xffffffffu, x, o);
+    const float yo = __shfl_xor_sync(0xffffffffu, y, o);
+    x += xo;
+    y += yo;
+  }
+}
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
 
@@ -564,11 +574,12 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
   float* s_dv = s_df + a.L * kE;
 
   // gradient accumulators that live in registers for the whole kernel
-  float2 g_w1[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};    // tid < 256: dW1[tid>>2][8*(tid&3)..]
-  float2 g_wo[2] = {f2(0, 0), f2(0, 0)};                        // tid < 256: dWo[tid>>3][4*(tid&7)..]
-  float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // tid < 384: dWin[tid>>2][8*(tid&3)..]
-  float g_vec = 0.f;               // tid 256..319: db1[tid-256]; tid 320..351: dbo[tid-320]
-  float g_bin[3] = {0.f, 0.f, 0.f};  // warp 12: dbin[lane], [32+lane], [64+lane]
+  // (lane = input channel c; a warp owns a band of output rows)
+  float2 g_wa[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};    // warps 0-7: dW1[8w+2i, 8w+2i+1][c];
+                                                                // warps 8-11: dWo[8(w-8)+2i, +1][c]
+  float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // warps 0-11: dWin[8w+2i, 8w+2i+1][c]
+  float g_vec = 0.f;               // lanes 0-7 of warps 0-7: db1[8w+lane]; of warps 8-11: dbo[8(w-8)+lane]
+  float g_bin = 0.f;               // warps 0-11, lanes 0-7: dbin[8w+lane]
   float g_gam = 0.f, g_bet = 0.f;  // (warp, lane = channel) partial of d(LayerNorm weight / bias)
   float g_pos[kRowsPerWarp];       // d(positional_encoding)[warp + 13 i][lane]
 #pragma unroll
@@ -618,93 +629,135 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
       for (int j = 0; j < kF / 2; ++j)
         w1c[j] = f2(sm[o.w1 + (2 * j) * kLdW + lane], sm[o.w1 + (2 * j + 1) * kLdW + lane]);
       const float gam = sm[o.lnw + lane], bet = a.w.lnb[lane];
-      for (int s = warp; s < S; s += kWarps) {
-        const float xh = s_xhat[s * kE + lane];
-        const float rs = sm[o.rstd + s];
+      // two rows per iteration: their dependent chains (LDS -> FFMA2 chain -> butterflies) interleave
+      for (int s0 = warp; s0 < S; s0 += 2 * kWarps) {
+        const int s1 = s0 + kWarps;
+        const bool two = s1 < S;                  // warp-uniform
+        const int sb = two ? s1 : s0;             // row b aliases row a when there is no second row
+        const float xh_a = s_xhat[s0 * kE + lane], xh_b = s_xhat[sb * kE + lane];
+        const float rs_a = sm[o.rstd + s0], rs_b = sm[o.rstd + sb];
         {
-          float2 d = *reinterpret_cast<const float2*>(s_df + s * kF + 2 * lane);
-          const uint32_t w0 = s_fbits[2 * s], w1 = s_fbits[2 * s + 1];
-          d.x = ((w0 >> lane) & 1u) ? d.x * inv_f : 0.f;
-          d.y = ((w1 >> lane) & 1u) ? d.y * inv_f : 0.f;
-          *reinterpret_cast<float2*>(s_df + s * kF + 2 * lane) = d;
+          float2 da = *reinterpret_cast<const float2*>(s_df + s0 * kF + 2 * lane);
+          const uint32_t a0 = s_fbits[2 * s0], a1 = s_fbits[2 * s0 + 1];
+          da.x = ((a0 >> lane) & 1u) ? da.x * inv_f : 0.f;
+          da.y = ((a1 >> lane) & 1u) ? da.y * inv_f : 0.f;
+          *reinterpret_cast<float2*>(s_df + s0 * kF + 2 * lane) = da;
+          if (two) {
+            float2 db = *reinterpret_cast<const float2*>(s_df + s1 * kF + 2 * lane);
+            const uint32_t b0 = s_fbits[2 * s1], b1 = s_fbits[2 * s1 + 1];
+            db.x = ((b0 >> lane) & 1u) ? db.x * inv_f : 0.f;
+            db.y = ((b1 >> lane) & 1u) ? db.y * inv_f : 0.f;
+            *reinterpret_cast<float2*>(s_df + s1 * kF + 2 * lane) = db;
+          }
         }
         __syncwarp();
-        float2 acc = f2(0.f, 0.f);
+        float2 acc_a0 = f2(0.f, 0.f), acc_a1 = f2(0.f, 0.f), acc_b0 = f2(0.f, 0.f), acc_b1 = f2(0.f, 0.f);
 #pragma unroll
         for (int j4 = 0; j4 < kF / 4; ++j4) {
-          const float4 x = lds4(s_df + s * kF + 4 * j4);
-          acc = fma2(f2(x.x, x.y), w1c[2 * j4], acc);
-          acc = fma2(f2(x.z, x.w), w1c[2 * j4 + 1], acc);
+          const float4 xa = lds4(s_df + s0 * kF + 4 * j4);
+          const float4 xb = lds4(s_df + sb * kF + 4 * j4);
+          acc_a0 = fma2(f2(xa.x, xa.y), w1c[2 * j4], acc_a0);
+          acc_a1 = fma2(f2(xa.z, xa.w), w1c[2 * j4 + 1], acc_a1);
+          acc_b0 = fma2(f2(xb.x, xb.y), w1c[2 * j4], acc_b0);
+          acc_b1 = fma2(f2(xb.z, xb.w), w1c[2 * j4 + 1], acc_b1);
         }
-        const float dh = acc.x + acc.y;
-        g_gam = fmaf(dh, xh, g_gam);
-        g_bet += dh;
-        const float dhg = dh * gam;
-        const float m1 = warp_sum(dhg) * (1.f / kE);
-        const float m2 = warp_sum(dhg * xh) * (1.f / kE);
-        s_dr[s * kE + lane] = rs * (dhg - m1 - xh * m2);
-        s_xhat[s * kE + lane] = fmaf(xh, gam, bet);   // h, for dW1
+        const float dh_a = (acc_a0.x + acc_a0.y) + (acc_a1.x + acc_a1.y);
+        const float dh_b = (acc_b0.x + acc_b0.y) + (acc_b1.x + acc_b1.y);
+        g_gam = fmaf(dh_a, xh_a, g_gam);
+        g_bet += dh_a;
+        if (two) {
+          g_gam = fmaf(dh_b, xh_b, g_gam);
+          g_bet += dh_b;
+        }
+        const float dhg_a = dh_a * gam, dhg_b = dh_b * gam;
+        float m1a = dhg_a, m2a = dhg_a * xh_a, m1b = dhg_b, m2b = dhg_b * xh_b;
+        warp_sum2(m1a, m2a);
+        warp_sum2(m1b, m2b);
+        s_dr[s0 * kE + lane] = rs_a * (dhg_a - m1a * (1.f / kE) - xh_a * (m2a * (1.f / kE)));
+        s_xhat[s0 * kE + lane] = fmaf(xh_a, gam, bet);   // h, for dW1
+        if (two) {
+          s_dr[s1 * kE + lane] = rs_b * (dhg_b - m1b * (1.f / kE) - xh_b * (m2b * (1.f / kE)));
+          s_xhat[s1 * kE + lane] = fmaf(xh_b, gam, bet);
+        }
+      }
+    }
+    // ---- B1b: dctx = dr Wo and D = dctx . ctx for the rows this warp just produced --------------
+    ptx::mbar_wait(&bars[1], phase);   // ctx
+    ptx::mbar_wait(&bars[2], phase);   // s_stat's (m, 1/l) arrive by bulk copy; D joins them below
+    __syncwarp();
+    {
+      float2 woc[kE / 2];   // column `lane` of Wo, packed along the output channel
+#pragma unroll
+      for (int c = 0; c < kE / 2; ++c)
+        woc[c] = f2(sm[o.wo + (2 * c) * kLdW + lane], sm[o.wo + (2 * c + 1) * kLdW + lane]);
+      for (int s0 = warp; s0 < S; s0 += 2 * kWarps) {
+        const int s1 = s0 + kWarps;
+        const bool two = s1 < S;
+        const int sb = two ? s1 : s0;
+        float2 a0 = f2(0.f, 0.f), a1 = f2(0.f, 0.f), b0 = f2(0.f, 0.f), b1 = f2(0.f, 0.f);
+#pragma unroll
+        for (int c4 = 0; c4 < kE / 4; ++c4) {
+          const float4 xa = lds4(s_dr + s0 * kE + 4 * c4);
+          const float4 xb = lds4(s_dr + sb * kE + 4 * c4);
+          a0 = fma2(f2(xa.x, xa.y), woc[2 * c4], a0);
+          a1 = fma2(f2(xa.z, xa.w), woc[2 * c4 + 1], a1);
+          b0 = fma2(f2(xb.x, xb.y), woc[2 * c4], b0);
+          b1 = fma2(f2(xb.z, xb.w), woc[2 * c4 + 1], b1);
+        }
+        const float dca = (a0.x + a0.y) + (a1.x + a1.y), dcb = (b0.x + b0.y) + (b1.x + b1.y);
+        // D[s][h] = sum_{j in head h} dctx[s][j] * ctx[s][j]   (= sum_t P_dropped dP)
+        float pa = dca * s_ctx[s0 * kE + lane], pb = dcb * s_ctx[sb * kE + lane];
+#pragma unroll
+        for (int m = 1; m <= 4; m <<= 1) {
+          const float qa = __shfl_xor_sync(0xffffffffu, pa, m), qb = __shfl_xor_sync(0xffffffffu, pb, m);
+          pa += qa;
+          pb += qb;
+        }
+        s_dctx[s0 * kE + lane] = dca;
+        if ((lane & 7) == 0) s_stat[(s0 * kHeads + (lane >> 3)) * 4 + 2] = pa;
+        if (two) {
+          s_dctx[s1 * kE + lane] = dcb;
+          if ((lane & 7) == 0) s_stat[(s1 * kHeads + (lane >> 3)) * 4 + 2] = pb;
+        }
       }
     }
     AFR_TICK(2);
     __syncthreads();
     AFR_TICK(3);
 
-    // ---- B2: dW1, dWo (warps 0-7) | db1, dbo, dctx = dr Wo, D = dctx . ctx (warps 8-12) -------
-    ptx::mbar_wait(&bars[1], phase);
+    // ---- B2: dW1, db1 (warps 0-7) | dWo, dbo (warps 8-11) --------------------------------------
+    // lane = input channel c; a warp owns 8 output rows: per position one conflict-free scalar
+    // load of the lane's own operand and warp-uniform LDS.128 of the row operand (1 clock each;
+    // any non-uniform LDS.128 costs 4).
     AFR_TICK(4);
-    if (tid < 256) {
-      {
-        const int j = tid >> 2, c0 = (tid & 3) * 8;
+    if (warp < 8) {
+      const float* dfw = s_df + 8 * warp;
+      float sum_b = 0.f;                  // lanes 0-7: db1[8w + lane]
 #pragma unroll 4
-        for (int s = 0; s < S; ++s) {
-          const float d = s_df[s * kF + j];
-          const float4 h0 = lds4(s_xhat + s * kE + c0), h1 = lds4(s_xhat + s * kE + c0 + 4);
-          axpy8(g_w1, d, h0, h1);
-        }
+      for (int s = 0; s < S; ++s) {
+        const float h = s_xhat[s * kE + lane];
+        const float4 d0 = lds4(dfw + s * kF), d1 = lds4(dfw + s * kF + 4);
+        g_wa[0] = fma2(f2(d0.x, d0.y), f2(h, h), g_wa[0]);
+        g_wa[1] = fma2(f2(d0.z, d0.w), f2(h, h), g_wa[1]);
+        g_wa[2] = fma2(f2(d1.x, d1.y), f2(h, h), g_wa[2]);
+        g_wa[3] = fma2(f2(d1.z, d1.w), f2(h, h), g_wa[3]);
+        sum_b += dfw[s * kF + (lane & 7)];
       }
-      {
-        const int c = tid >> 3, j0 = (tid & 7) * 4;
+      g_vec += sum_b;
+    } else if (warp < 12) {
+      const float* drw = s_dr + 8 * (warp - 8);
+      float sum_b = 0.f;                  // lanes 0-7: dbo[8(w-8) + lane]
 #pragma unroll 4
-        for (int s = 0; s < S; ++s) {
-          const float d = s_dr[s * kE + c];
-          const float4 x = lds4(s_ctx + s * kE + j0);
-          g_wo[0] = fma2(f2(d, d), f2(x.x, x.y), g_wo[0]);
-          g_wo[1] = fma2(f2(d, d), f2(x.z, x.w), g_wo[1]);
-        }
+      for (int s = 0; s < S; ++s) {
+        const float x = s_ctx[s * kE + lane];
+        const float4 r0 = lds4(drw + s * kE), r1 = lds4(drw + s * kE + 4);
+        g_wa[0] = fma2(f2(r0.x, r0.y), f2(x, x), g_wa[0]);
+        g_wa[1] = fma2(f2(r0.z, r0.w), f2(x, x), g_wa[1]);
+        g_wa[2] = fma2(f2(r1.x, r1.y), f2(x, x), g_wa[2]);
+        g_wa[3] = fma2(f2(r1.z, r1.w), f2(x, x), g_wa[3]);
+        sum_b += drw[s * kE + (lane & 7)];
       }
-    } else {
-      if (tid < 320) {
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += s_df[s * kF + (tid - 256)];
-        g_vec += acc;
-      } else if (tid < 352) {
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += s_dr[s * kE + (tid - 320)];
-        g_vec += acc;
-      }
-      float2 woc[kE / 2];   // column `lane` of Wo, packed along the output channel
-#pragma unroll
-      for (int c = 0; c < kE / 2; ++c)
-        woc[c] = f2(sm[o.wo + (2 * c) * kLdW + lane], sm[o.wo + (2 * c + 1) * kLdW + lane]);
-      ptx::mbar_wait(&bars[2], phase);   // s_stat's (m, 1/l) arrive by bulk copy; D joins them below
-      for (int s = warp - 8; s < S; s += kWarps - 8) {
-        float2 acc = f2(0.f, 0.f);
-#pragma unroll
-        for (int c4 = 0; c4 < kE / 4; ++c4) {
-          const float4 x = lds4(s_dr + s * kE + 4 * c4);
-          acc = fma2(f2(x.x, x.y), woc[2 * c4], acc);
-          acc = fma2(f2(x.z, x.w), woc[2 * c4 + 1], acc);
-        }
-        const float dc = acc.x + acc.y;
-        s_dctx[s * kE + lane] = dc;
-        // D[s][h] = sum_{j in head h} dctx[s][j] * ctx[s][j]   (= sum_t P_dropped dP)
-        float prod = dc * s_ctx[s * kE + lane];
-        prod += __shfl_xor_sync(0xffffffffu, prod, 1);
-        prod += __shfl_xor_sync(0xffffffffu, prod, 2);
-        prod += __shfl_xor_sync(0xffffffffu, prod, 4);
-        if ((lane & 7) == 0) s_stat[(s * kHeads + (lane >> 3)) * 4 + 2] = prod;
-      }
+      g_vec += sum_b;
     }
     AFR_TICK(5);
     __syncthreads();
@@ -814,14 +867,14 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
         for (int i = 0; i < kRowsPerWarp; ++i) {
           const int s = warp + kWarps * i;
           if (s < S) {
-            float2 acc = f2(0.f, 0.f);
+            float2 acc0 = f2(0.f, 0.f), acc1 = f2(0.f, 0.f);
 #pragma unroll
             for (int r4 = 0; r4 < kE / 4; ++r4) {
               const float4 x = lds4(src + s * kE + 4 * r4);
-              acc = fma2(f2(x.x, x.y), wc[2 * r4], acc);
-              acc = fma2(f2(x.z, x.w), wc[2 * r4 + 1], acc);
+              acc0 = fma2(f2(x.x, x.y), wc[2 * r4], acc0);
+              acc1 = fma2(f2(x.z, x.w), wc[2 * r4 + 1], acc1);
             }
-            de[i] += acc.x + acc.y;
+            de[i] += (acc0.x + acc0.y) + (acc1.x + acc1.y);
           }
         }
       }
@@ -841,26 +894,38 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
     AFR_TICK(13);
 
     // ---- B5: dWin (warps 0-11) | dbin, embedding scatter-add (warp 12) ------------------------
-    if (tid < 384) {
-      const int oo = tid >> 2, c0 = (tid & 3) * 8;
-      const float* src = (oo < 32 ? s_dq : (oo < 64 ? s_dk : s_dv)) + (oo & 31);
+    if (warp < 12) {
+      // lane = input channel c; this warp owns rows [8w, 8w+8) of dWin (q | k | v blocks of 32)
+      const float* src = (warp < 4 ? s_dq : (warp < 8 ? s_dk : s_dv)) + 8 * (warp & 3);
+      float sum_b = 0.f;   // lanes 0-7: dbin[8w + lane]
 #pragma unroll 4
       for (int s = 0; s < S; ++s) {
-        const float d = src[s * kE];
-        const float4 e0 = lds4(s_e + s * kE + c0), e1 = lds4(s_e + s * kE + c0 + 4);
-        axpy8(g_win, d, e0, e1);
+        const float ev = s_e[s * kE + lane];
+        const float4 d0 = lds4(src + s * kE), d1 = lds4(src + s * kE + 4);
+        g_win[0] = fma2(f2(d0.x, d0.y), f2(ev, ev), g_win[0]);
+        g_win[1] = fma2(f2(d0.z, d0.w), f2(ev, ev), g_win[1]);
+        g_win[2] = fma2(f2(d1.x, d1.y), f2(ev, ev), g_win[2]);
+        g_win[3] = fma2(f2(d1.z, d1.w), f2(ev, ev), g_win[3]);
+        sum_b += src[s * kE + (lane & 7)];
       }
+      g_bin += sum_b;
     } else {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      for (int s = 0; s < S; ++s) {
-        a0 += s_dq[s * kE + lane];
-        a1 += s_dk[s * kE + lane];
-        a2 += s_dv[s * kE + lane];
-      }
-      g_bin[0] += a0; g_bin[1] += a1; g_bin[2] += a2;
-      // rows hit by several positions are summed in position order: deterministic, no atomics
+      // embedding scatter-add. Rows hit by several positions are summed in position order:
+      // deterministic, no atomics. Operands are fetched four positions ahead of the dependent
+      // read-modify-write chain on the table.
       if (hist_smem) {
-        for (int s = 0; s < S; ++s) sm[o.hist + s_tok[s] * kE + lane] += s_dr[s * kE + lane];
+        float* hist = sm + o.hist + lane;
+        int s = 0;
+        for (; s + 4 <= S; s += 4) {
+          const int t0 = s_tok[s], t1 = s_tok[s + 1], t2 = s_tok[s + 2], t3 = s_tok[s + 3];
+          const float v0 = s_dr[s * kE + lane], v1 = s_dr[(s + 1) * kE + lane];
+          const float v2 = s_dr[(s + 2) * kE + lane], v3 = s_dr[(s + 3) * kE + lane];
+          hist[t0 * kE] += v0;
+          hist[t1 * kE] += v1;
+          hist[t2 * kE] += v2;
+          hist[t3 * kE] += v3;
+        }
+        for (; s < S; ++s) hist[s_tok[s] * kE] += s_dr[s * kE + lane];
       } else {
         for (int s = 0; s < S; ++s) {
           float* pe = part + a.lay.off_emb + static_cast<long long>(s_tok[s]) * kE + lane;
@@ -884,32 +949,28 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
     for (int w = 0; w < kWarps; ++w) acc += sm[o.red + (which * kWarps + w) * kE + c];
     part[(which == 0 ? a.lay.off_lnw : a.lay.off_lnb) + c] = acc;
   }
-  if (tid < 256) {
-    {
-      const int j = tid >> 2, c0 = (tid & 3) * 8;
-      float* p = part + a.lay.off_w1 + j * kE + c0;
-      *reinterpret_cast<float4*>(p) = make_float4(g_w1[0].x, g_w1[0].y, g_w1[1].x, g_w1[1].y);
-      *reinterpret_cast<float4*>(p + 4) = make_float4(g_w1[2].x, g_w1[2].y, g_w1[3].x, g_w1[3].y);
+  if (warp < 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part[a.lay.off_w1 + (8 * warp + 2 * i) * kE + lane] = g_wa[i].x;
+      part[a.lay.off_w1 + (8 * warp + 2 * i + 1) * kE + lane] = g_wa[i].y;
     }
-    {
-      const int c = tid >> 3, j0 = (tid & 7) * 4;
-      *reinterpret_cast<float4*>(part + a.lay.off_wo + c * kE + j0) =
-          make_float4(g_wo[0].x, g_wo[0].y, g_wo[1].x, g_wo[1].y);
+    if (lane < 8) part[a.lay.off_b1 + 8 * warp + lane] = g_vec;
+  } else if (warp < 12) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i) * kE + lane] = g_wa[i].x;
+      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i + 1) * kE + lane] = g_wa[i].y;
     }
-  } else if (tid < 320) {
-    part[a.lay.off_b1 + tid - 256] = g_vec;
-  } else if (tid < 352) {
-    part[a.lay.off_bo + tid - 320] = g_vec;
+    if (lane < 8) part[a.lay.off_bo + 8 * (warp - 8) + lane] = g_vec;
   }
-  if (tid < 384) {
-    const int oo = tid >> 2, c0 = (tid & 3) * 8;
-    float* p = part + a.lay.off_win + oo * kE + c0;
-    *reinterpret_cast<float4*>(p) = make_float4(g_win[0].x, g_win[0].y, g_win[1].x, g_win[1].y);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(g_win[2].x, g_win[2].y, g_win[3].x, g_win[3].y);
-  } else {
-    part[a.lay.off_bin + lane] = g_bin[0];
-    part[a.lay.off_bin + 32 + lane] = g_bin[1];
-    part[a.lay.off_bin + 64 + lane] = g_bin[2];
+  if (warp < 12) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part[a.lay.off_win + (8 * warp + 2 * i) * kE + lane] = g_win[i].x;
+      part[a.lay.off_win + (8 * warp + 2 * i + 1) * kE + lane] = g_win[i].y;
+    }
+    if (lane < 8) part[a.lay.off_bin + 8 * warp + lane] = g_bin;
   }
 #pragma unroll
   for (int i = 0; i < kRowsPerWarp; ++i) {

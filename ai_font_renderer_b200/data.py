@@ -158,3 +158,54 @@ def load_string_dataset_u8(data_dir: str = "train_input", num_samples: int = 500
     strings = strings[:num_samples]
     max_len = max(len(s) for s in strings)
     return encode(strings, max_len), torch.from_numpy(targets)
+
+
+class HostBatchFeeder:
+    """Streams (tokens, uint8 sheets) batches from pinned host memory to the device on a copy
+    stream, one batch ahead of the training step that consumes them, so the 20 MB per-batch H2D
+    copy (model.py:295-296 does it synchronously in front of every step) hides under the previous
+    step's kernels. Double buffered: `get(i)` hands out the device tensors of batch i and starts
+    the copy of batch i+1; the compute stream is made to wait for the copy it consumes, and the
+    copy stream for the step that last read the buffer it overwrites."""
+
+    def __init__(self, tokens_host: torch.Tensor, targets_host: torch.Tensor, batch: int,
+                 device: torch.device):
+        if not (tokens_host.is_pinned() and targets_host.is_pinned()):
+            raise ValueError("HostBatchFeeder needs pinned host tensors (tensor.pin_memory())")
+        self.tok_h, self.tgt_h, self.batch, self.device = tokens_host, targets_host, batch, device
+        self.n_batches = tokens_host.shape[0] // batch
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.bufs = [(torch.empty((batch,) + tuple(tokens_host.shape[1:]), dtype=tokens_host.dtype, device=device),
+                      torch.empty((batch,) + tuple(targets_host.shape[1:]), dtype=targets_host.dtype, device=device))
+                     for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]     # copy into buffer k finished
+        self.consumed = [None, None]                               # last step reading buffer k finished
+        self.in_flight = None                                      # batch index being / already copied ahead
+        self.h2d_bytes_per_batch = (batch * tokens_host[0].numel() * tokens_host.element_size()
+                                    + batch * targets_host[0].numel() * targets_host.element_size())
+
+    def _start_copy(self, i: int):
+        k = i % 2
+        lo = (i % self.n_batches) * self.batch
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[k] is not None:
+                self.copy_stream.wait_event(self.consumed[k])
+            self.bufs[k][0].copy_(self.tok_h[lo:lo + self.batch], non_blocking=True)
+            self.bufs[k][1].copy_(self.tgt_h[lo:lo + self.batch], non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.in_flight = i
+
+    def get(self, i: int):
+        """Device (tokens, targets) of batch i for the current stream; prefetches batch i+1."""
+        if self.in_flight != i:
+            self._start_copy(i)
+        k = i % 2
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        self._start_copy(i + 1)
+        return self.bufs[k]
+
+    def done(self, i: int):
+        """Call after the last kernel reading batch i has been enqueued on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.consumed[i % 2] = ev

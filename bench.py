@@ -185,7 +185,7 @@ def main():
         return 0
 
     import torch.distributed as dist
-    from ai_font_renderer_b200.data import fast_synthetic_batch
+    from ai_font_renderer_b200.data import HostBatchFeeder, fast_synthetic_batch
     from ai_font_renderer_b200.optim import FusedAdamW
     from ai_font_renderer_b200.renderer import AttentionFontRenderer
     from ai_font_renderer_b200.training import backward_and_step, row_buckets
@@ -235,16 +235,16 @@ def main():
             marks("forward")
         backward_and_step(model, opt, buckets, world, marks=marks)
 
-    x_dev = torch.empty((B, 100), dtype=torch.int64, device=device)
-    t_dev = torch.empty((B, 80, 240), dtype=torch.uint8, device=device)
+    # end to end: every step's tokens + uint8 sheets come from pinned HOST memory through the
+    # package's HostBatchFeeder (copy stream, one batch ahead) and the step's loss is read back.
+    feeder = HostBatchFeeder(tok_h, tgt_h, B, device)
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def step_e2e(i):
-        s = (i % n_rot) * B
-        x_dev.copy_(tok_h[s:s + B], non_blocking=True)          # H2D from pinned memory
-        t_dev.copy_(tgt_h[s:s + B], non_blocking=True)
+        x_dev, t_dev = feeder.get(i)                             # H2D of batch i (and i+1 started)
         loss = model.fused_forward_loss(x_dev, t_dev, loss_count=count, sample_offset=rank * B)
         backward_and_step(model, opt, buckets, world)
+        feeder.done(i)
         loss_host.copy_(loss.view(1), non_blocking=False)        # D2H read of the step's loss (syncs)
         return float(loss_host[0])
 
@@ -331,7 +331,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": int(B * 100 * 8 + B * P_PIX), "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": int(feeder.h2d_bytes_per_batch), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
