@@ -29,6 +29,7 @@ struct afr_ctx {
   int shadow_cur = 0;                // what the next forward reads
   int shadow_fwd = 0;                // what the last training forward read (dgrad reads it too)
   int shadow_rows_swept = 0;         // rows already rewritten in buffer 1 - shadow_cur
+  bool shadow_external = false;      // the two copies belong to the caller (afr_bind_shadow)
   __nv_bfloat16* dz = nullptr;       // [max_batch, P]   unscaled (y - t) * mask
   float* dfeat = nullptr;            // [max_batch, K]
   float* logits = nullptr;           // [max_batch, P]   generic path, allocated on first use
@@ -257,7 +258,9 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
 int afr_destroy(afr_ctx* c) {
   if (c == nullptr) return AFR_OK;
   DeviceGuard guard(c->cfg.device);
-  cudaFree(c->feats); cudaFree(c->wshadow_buf[0]); cudaFree(c->wshadow_buf[1]); cudaFree(c->dz); cudaFree(c->dfeat);
+  cudaFree(c->feats);
+  if (!c->shadow_external) { cudaFree(c->wshadow_buf[0]); cudaFree(c->wshadow_buf[1]); }
+  cudaFree(c->dz); cudaFree(c->dfeat);
   cudaFree(c->logits); cudaFree(c->loss_partials); cudaFree(c->bias_scratch);
   cudaFree(c->partials); cudaFree(c->fstate);
   delete c;
@@ -292,6 +295,42 @@ int afr_sync_shadow(afr_ctx* c, void* stream) {
   DeviceGuard guard(c->cfg.device);
   c->shadow_valid = false;
   return ensure_shadow(c, static_cast<cudaStream_t>(stream));
+}
+
+int afr_bind_shadow(afr_ctx* c, void* copy0, void* copy1) {
+  if (!c || !copy0 || !copy1 || copy0 == copy1)
+    return fail(c, AFR_ERR_INVALID, "afr_bind_shadow: need two distinct buffers");
+  if ((reinterpret_cast<uintptr_t>(copy0) | reinterpret_cast<uintptr_t>(copy1)) & 15)
+    return fail(c, AFR_ERR_INVALID, "afr_bind_shadow: buffers must be 16-byte aligned");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (c->shadow_rows_swept != 0)
+    return fail(c, AFR_ERR_STATE, "afr_bind_shadow in the middle of an AdamW sweep");
+  DeviceGuard guard(c->cfg.device);
+  __nv_bfloat16* fresh[2] = {static_cast<__nv_bfloat16*>(copy0), static_cast<__nv_bfloat16*>(copy1)};
+  // A training step may be in flight (forward done, dgrad still to come): both copies move over
+  // with their contents and roles, synchronously.
+  AFR_CUDA(c, cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  const size_t bytes = static_cast<size_t>(c->P) * c->K * 2;
+  for (int i = 0; i < 2; ++i)
+    if (c->wshadow_buf[i] != nullptr && c->wshadow_buf[i] != fresh[i])
+      AFR_CUDA(c, cudaMemcpy(fresh[i], c->wshadow_buf[i], bytes, cudaMemcpyDeviceToDevice),
+               "cudaMemcpy(shadow)");
+  if (!c->shadow_external) { cudaFree(c->wshadow_buf[0]); cudaFree(c->wshadow_buf[1]); }
+  c->wshadow_buf[0] = fresh[0];
+  c->wshadow_buf[1] = fresh[1];
+  c->shadow_external = true;
+  return AFR_OK;
+}
+
+int afr_shadow_index(const afr_ctx* c) { return c ? c->shadow_cur : AFR_ERR_INVALID; }
+
+int afr_shadow_commit(afr_ctx* c) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  c->shadow_cur ^= 1;
+  c->shadow_rows_swept = 0;
+  c->shadow_valid = true;
+  return AFR_OK;
 }
 
 int afr_forward_eval(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,

@@ -175,6 +175,7 @@ class AttentionFontRenderer(nn.Module):
         self._ctx: Optional[_Context] = None
         self._scratch: Optional[list] = None
         self._side: Optional[torch.cuda.Stream] = None
+        self._shadow: Optional[list] = None     # caller-owned bf16 copies of fc_output.weight (DP)
 
     # ------------------------------------------------------------------ plumbing
     def side_stream(self) -> torch.cuda.Stream:
@@ -210,12 +211,35 @@ class AttentionFontRenderer(nn.Module):
                 c.close()
             c = _Context(self, dev, cap, training)
             self._ctx = c
+            if self._shadow is not None and training and self._shadow[0].device == dev:
+                c.check(c.lib.afr_bind_shadow(c.handle, self._shadow[0].data_ptr(), self._shadow[1].data_ptr()))
+                c.shadow_bound = tuple(t.data_ptr() for t in self._shadow)
         c.bind_params(params)
         w = self.fc_output.weight
         if c.shadow_version != w._version:      # torch wrote the master weights in place
             c.check(c.lib.afr_sync_shadow(c.handle, _stream_ptr(dev)))
             c.shadow_version = w._version
         return c
+
+    def own_shadow_copies(self, batch: int = 1):
+        """Data parallel with a row-sharded optimizer: the two bf16 copies of fc_output.weight the
+        GEMMs read become torch tensors (so NCCL can all-gather updated rows into the inactive
+        one). Returns [copy0, copy1]; `shadow_index()` tells which one the next forward reads."""
+        c = self._context(batch, training=True)
+        w = self.fc_output.weight
+        if self._shadow is None or self._shadow[0].device != w.device:
+            self._shadow = [torch.empty(w.shape, dtype=torch.bfloat16, device=w.device) for _ in range(2)]
+        if getattr(c, "shadow_bound", None) != tuple(t.data_ptr() for t in self._shadow):
+            c.check(c.lib.afr_bind_shadow(c.handle, self._shadow[0].data_ptr(), self._shadow[1].data_ptr()))
+            c.shadow_bound = tuple(t.data_ptr() for t in self._shadow)
+            c.shadow_version = w._version       # rebuilt from the master at the next forward
+        return self._shadow
+
+    def shadow_index(self) -> int:
+        return int(self._ctx.lib.afr_shadow_index(self._ctx.handle))
+
+    def shadow_commit(self):
+        self._ctx.check(self._ctx.lib.afr_shadow_commit(self._ctx.handle))
 
     def _param_grads(self):
         """p.grad for the 12 tensors in state_dict order, allocated on first use. The ten small
@@ -396,4 +420,5 @@ class AttentionFontRenderer(nn.Module):
             self._ctx.close()
             self._ctx = None
         self._scratch = None
+        self._shadow = None
         return out

@@ -101,7 +101,16 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
     return out
 
 
-def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool = True, marks=None):
+def owned_rows(P: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows of fc_output.weight whose optimizer state (and fp32 master) rank `rank` owns."""
+    if P % world != 0:
+        raise ValueError(f"fc_output has {P} rows: not divisible by world size {world}")
+    per = P // world
+    return rank * per, (rank + 1) * per
+
+
+def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool = True, marks=None,
+                      rank: Optional[int] = None):
     """loss.backward(); optimizer.step() (model.py:309-310) for one rank of a data-parallel job.
 
     world == 1: wgrad, the AdamW sweep over fc_output.weight (right behind the gradient that is
@@ -112,45 +121,72 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     overlap saves.) The sweep writes the inactive copy of the bf16 shadow weights, so the dgrad
     GEMM behind it still reads the weights the forward used.
 
-    world > 1: fc_output.weight.grad is produced bucket by bucket (row ranges); each bucket's
-    all-reduce is enqueued on NCCL's stream right behind its wgrad GEMM and runs under the later
-    buckets, the dgrad GEMM and the front-end backward; the model's side stream waits for each
-    reduction and runs that bucket's AdamW sweep; the streams join at the end of the step.
+    world > 1: the optimizer over fc_output.weight (99.97 % of the parameters) is sharded by rows:
+      compute stream : wgrad | dgrad, front-end backward | all-reduce + AdamW of the 33 k small
+                       parameters | join
+      side stream    : reduce-scatter of dW (each rank receives the sum of ITS rows, in place) ->
+                       AdamW sweep over the owned rows only (1/world of the 3.7 GB sweep) ->
+                       all-gather of the updated bf16 rows into the inactive shadow copy
+    so the wire carries 491 MB fp32 + 246 MB bf16 per step instead of the 2 x 491 MB of an
+    all-reduce, under dgrad and the front-end backward, and the HBM-bound sweep shrinks with the
+    number of ranks. Each rank's fp32 master / Adam moments are current for its own rows only
+    (Trainer.gather_master gathers them for checkpoints).
     `marks(label)`, if given, is called at phase boundaries with the stream to record on current
     (bench.py records CUDA events there): 'wgrad', 'dgrad', 'tail' on the compute stream,
     'adamw_begin' / 'adamw_end' around every sweep launch."""
     mark = marks or (lambda label: None)
     dev = model.fc_output.weight.device
     main = torch.cuda.current_stream(dev)
-    side = model.side_stream() if world > 1 else main
     model._param_grads()
     wgrad = model.fc_output.weight.grad
     t_step = optimizer.begin_step()
-    last = len(buckets) - 1
+    P = wgrad.shape[0]
 
-    def after_bucket(i, r0, r1):
-        if world > 1:
-            work = dist.all_reduce(wgrad[r0:r1], op=dist.ReduceOp.SUM, async_op=True)
-            with torch.cuda.stream(side):
-                work.wait()                       # stream-level wait on NCCL, no host sync
-        if i == last:
-            mark("wgrad")
-        with torch.cuda.stream(side):
+    if world == 1:
+        last = len(buckets) - 1
+
+        def after_bucket(i, r0, r1):
+            if i == last:
+                mark("wgrad")
             mark("adamw_begin")
             optimizer.step_rows(t_step, r0, r1)
             mark("adamw_end")
 
-    if has_samples:
         model.fused_backward(buckets, after_bucket)
+        mark("dgrad")
+        optimizer.step_small(t_step)
+        optimizer.end_step()
+        mark("tail")
+        return
+
+    side = model.side_stream()
+    rank = dist.get_rank() if rank is None else rank
+    lo, hi = owned_rows(P, rank, world)
+    shadows = model.own_shadow_copies()
+    nxt = shadows[1 - model.shadow_index()]
+
+    def after_wgrad(i, r0, r1):
+        mark("wgrad")
+        # sum over ranks of dW[lo:hi] lands in place; ordered behind the wgrad GEMM on `main`
+        rs = dist.reduce_scatter_tensor(wgrad[lo:hi], wgrad, op=dist.ReduceOp.SUM, async_op=True)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            rs.wait()                                   # stream-level wait on NCCL, no host sync
+            mark("adamw_begin")
+            optimizer.step_rows(t_step, lo, hi)          # writes nxt[lo:hi]
+            mark("adamw_end")
+            ag = dist.all_gather_into_tensor(nxt, nxt[lo:hi], async_op=True)
+            ag.wait()
+
+    if has_samples:
+        model.fused_backward([(0, P)], after_wgrad)
     else:
-        for i, (r0, r1) in enumerate(buckets):
-            after_bucket(i, r0, r1)
+        after_wgrad(0, 0, P)
     mark("dgrad")
-    if world > 1:
-        dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM)   # ordered on the compute stream
+    dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM)   # ordered on the compute stream
     optimizer.step_small(t_step)
-    if side is not main:
-        main.wait_stream(side)
+    main.wait_stream(side)
+    model.shadow_commit()
     optimizer.end_step()
     mark("tail")
 
@@ -296,11 +332,28 @@ class Trainer:
         if best_model_state is not None and patience_counter < cfg.early_stopping_patience:
             model.load_state_dict(best_model_state)                     # model.py:369-371
             say(f"Training completed, Best Val Loss: {best_val_loss:.6f}")
+        self.gather_master()
         if self.rank == 0 and cfg.output_dir:
             final_epoch = epoch + 1 if patience_counter < cfg.early_stopping_patience else epoch
             self._write_results(final_epoch, best_val_loss, patience_counter)
         self.history = history
         return model
+
+    @torch.no_grad()
+    def gather_master(self):
+        """Row-sharded optimizer (world > 1): every rank holds current fp32 values of
+        fc_output.weight and its Adam moments only for the rows it owns; all-gather them so
+        state_dict() / optimizer.state_dict() are complete on every rank (checkpoint contract)."""
+        if self.world == 1:
+            return
+        w = self.model.fc_output.weight
+        lo, hi = owned_rows(w.shape[0], self.rank, self.world)
+        tensors = [w.data]
+        st = self.optimizer.state.get(w, {})
+        tensors += [st[k] for k in ("exp_avg", "exp_avg_sq") if k in st]
+        for t in tensors:
+            dist.all_gather_into_tensor(t, t[lo:hi])
+        torch.cuda.synchronize(self.device)
 
     def _write_config(self):
         cfg = self.cfg

@@ -159,7 +159,8 @@ def workload_config(n_gpus):
                         "1024 glyphs per GPU per step (model.py:409)",
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
             "max_length": 100, "sheet": "80x240", "params": 122912896,
-            "parallelism": f"dp{n_gpus}" if n_gpus > 1 else "single",
+            "parallelism": (f"dp{n_gpus}: batch sharded, dW reduce-scattered, AdamW of fc_output.weight "
+                            f"sharded by rows, bf16 weights all-gathered") if n_gpus > 1 else "single",
             "l2": "no flush: one step streams 3.9 GB (fp32 master, grads, Adam moments, bf16 shadow) "
                   "through the 126 MB L2 and rotates over 8 resident batches"}
 
@@ -196,6 +197,7 @@ def main():
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     args.warmup = max(3, args.warmup)
     B = args.batch

@@ -115,6 +115,16 @@ int afr_bind_adam_state(afr_ctx* ctx, const afr_tensors* exp_avg, const afr_tens
 /* Rebuild the private bf16 copy of fc_output.weight from the fp32 master; call after the caller
  * wrote the master itself (load_state_dict at helpers.py:101, a torch optimizer, init). */
 int afr_sync_shadow(afr_ctx* ctx, void* stream);
+/* Data-parallel runs with a row-sharded optimizer (training.py): the two bf16 copies of
+ * fc_output.weight ([H*W, 64*max_length] each, 16-byte aligned) live in caller-owned memory, so
+ * the caller's collective can all-gather the rows other ranks updated straight into the inactive
+ * copy. afr_shadow_index returns which copy (0/1) the next forward reads; the AdamW sweep
+ * (afr_adamw_rows) always writes the other one. A sweep that covered every row activates the
+ * written copy by itself; a sharded sweep (own rows only) is completed by the caller's
+ * all-gather and then activated with afr_shadow_commit. */
+int afr_bind_shadow(afr_ctx* ctx, void* copy0, void* copy1);
+int afr_shadow_index(const afr_ctx* ctx);
+int afr_shadow_commit(afr_ctx* ctx);
 
 /* Eval forward: model.py:158-204 under model.eval(), for validation (model.py:317-330) and
  * render_strings (helpers.py:62-64), batched. tokens: int64 [B, token_stride], first S columns

@@ -1,0 +1,34 @@
+"""Data-parallel step on real GPUs (needs >= 2 visible B200s; skipped on a one-GPU box): the
+row-sharded step of training.backward_and_step (reduce-scatter of dW, AdamW on the owned rows,
+all-gather of the bf16 weights) against the single-GPU step on the same global batch.
+tools/dp_check.py is the worker; this test launches it under torchrun."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import REPO
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_row_sharded_data_parallel_step_equals_single_gpu_step():
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(REPO, "tools", "dp_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("dp_check")]
+    assert res.returncode == 0 and lines and lines[-1].endswith("-> OK"), res.stdout[-2000:] + res.stderr[-2000:]

@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Data-parallel parity on real GPUs (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py
+
+Every rank trains two copies of the model for a few steps on the same GLOBAL batch:
+  (a) alone, on the whole global batch (the single-GPU step), and
+  (b) as one rank of the row-sharded data-parallel step (training.backward_and_step, world > 1),
+and rank 0 reports how far (b) is from (a): per-step loss, the bf16 weights every rank ends up
+reading, and the fp32 master rows after gather. fp32 sums are re-associated across ranks, so the
+expected distance is ~1e-6, not 0."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from ai_font_renderer_b200.data import fast_synthetic_batch  # noqa: E402
+from ai_font_renderer_b200.optim import FusedAdamW  # noqa: E402
+from ai_font_renderer_b200.renderer import AttentionFontRenderer  # noqa: E402
+from ai_font_renderer_b200.training import backward_and_step, owned_rows, shard_bounds  # noqa: E402
+
+
+def main(steps=3, per_rank=96):
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
+    torch.cuda.set_device(dev)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+    gB, P = per_rank * world, 19200
+    tok, tgt = fast_synthetic_batch(gB, seed=77)
+    tok, tgt = tok.to(dev), tgt.to(dev)
+    count = float(gB) * P
+
+    def make():
+        torch.manual_seed(42)
+        m = AttentionFontRenderer().to(dev).train()
+        m.dropout_seed = 1234
+        return m, FusedAdamW(m, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
+
+    solo, solo_opt = make()
+    dp, dp_opt = make()
+    lo, hi = shard_bounds(gB, rank, world)
+    worst_loss = 0.0
+    for _ in range(steps):
+        l_solo = solo.fused_forward_loss(tok, tgt, loss_count=count)
+        backward_and_step(solo, solo_opt, [(0, P)], 1)
+        l_dp = dp.fused_forward_loss(tok[lo:hi], tgt[lo:hi], loss_count=count, sample_offset=lo).clone()
+        backward_and_step(dp, dp_opt, [(0, P)], world)
+        dist.all_reduce(l_dp)
+        worst_loss = max(worst_loss, abs(float(l_dp) - float(l_solo)) / float(l_solo))
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+    # the bf16 weights both models will read in their next forward
+    w_solo = solo._ctx.workspace_tensor(3, (P, 6400), torch.bfloat16)
+    w_dp = dp._shadow[dp.shadow_index()]
+    r0, r1 = owned_rows(P, rank, world)
+    res = torch.tensor([
+        worst_loss,
+        rel(w_dp, w_solo),
+        float((w_dp != w_solo).float().mean()),
+        rel(dp.fc_output.weight.detach()[r0:r1], solo.fc_output.weight.detach()[r0:r1]),
+        max(rel(a.detach(), b.detach()) for (k, a), (_, b) in zip(dp.named_parameters(), solo.named_parameters())
+            if a.numel() < 1e6 and k != "attention.in_proj_bias"),   # key-bias slice: zero true gradient
+    ], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MAX)
+    ok = res[0] < 1e-5 and res[1] < 1e-4 and res[3] < 1e-5 and res[4] < 1e-3
+    if rank == 0:
+        print(f"dp_check world={world}: loss rel {res[0]:.2e}, bf16 weights rel {res[1]:.2e} "
+              f"({100 * res[2]:.3f}% of elements differ by a bf16 ulp), owned fp32 rows rel {res[3]:.2e}, "
+              f"small params rel {res[4]:.2e} -> {'OK' if ok else 'MISMATCH'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
