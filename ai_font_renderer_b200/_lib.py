@@ -76,9 +76,12 @@ SIGNATURES = {
     "afr_bind_adam_state": (C.c_int, [_P, C.POINTER(AfrTensors), C.POINTER(AfrTensors)]),
     "afr_sync_shadow": (C.c_int, [_P, _P]),
     "afr_bind_shadow": (C.c_int, [_P, _P, _P]),
+    "afr_set_sm_limit": (C.c_int, [_P, C.c_int]),
     "afr_shadow_index": (C.c_int, [_P]),
     "afr_shadow_commit": (C.c_int, [_P]),
     "afr_forward_eval": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "afr_train_frontend": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(AfrDropout), _P]),
+    "afr_train_loss": (C.c_int, [_P, _P, C.c_int, C.c_double, _P, _P]),
     "afr_train_forward_loss": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_int,
                                          C.POINTER(AfrDropout), C.c_double, _P, _P]),
     "afr_train_wgrad": (C.c_int, [_P, C.c_int, C.c_int, _P]),

@@ -14,7 +14,8 @@ using namespace afr;
 
 struct afr_ctx {
   afr_config cfg{};
-  int num_sms = 0;
+  int num_sms = 0;                   // SMs of the device (workspace sizing)
+  int sms = 0;                       // SMs the persistent kernels may occupy (afr_set_sm_limit)
   int K = 0;  // max_length * hidden : fc_output in_features
   int P = 0;  // sheet_h * sheet_w   : fc_output out_features
   SmallLayout lay{};
@@ -47,6 +48,7 @@ struct afr_ctx {
   Dropout drop{};
   float grad_scale = 0.f;
   bool fwd_done = false;
+  bool frontend_done = false;        // afr_train_frontend ran, afr_train_loss still to come
   long long launches = 0;
   std::string err;
 };
@@ -159,7 +161,7 @@ int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, i
                  const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32 = nullptr) {
   float* state = save_state ? c->fstate : nullptr;
   AFR_CUDA(c, launch_frontend_forward(c->params, tokens, stride, B, S, c->cfg.max_length,
-                                      c->cfg.vocab, drop, c->feats, state, c->num_sms, st, feats_f32),
+                                      c->cfg.vocab, drop, c->feats, state, c->sms, st, feats_f32),
            "frontend_forward");
   c->launches += 1;
   c->state_valid = state != nullptr;
@@ -214,6 +216,7 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
   afr_ctx* c = new afr_ctx();
   c->cfg = *cfg;
   c->num_sms = prop.multiProcessorCount;
+  c->sms = c->num_sms;
   c->K = cfg->max_length * cfg->hidden;
   c->P = static_cast<int>(P);
   c->lay.init(cfg->max_length, cfg->vocab);
@@ -322,6 +325,13 @@ int afr_bind_shadow(afr_ctx* c, void* copy0, void* copy1) {
   return AFR_OK;
 }
 
+int afr_set_sm_limit(afr_ctx* c, int sms) {
+  if (!c) return AFR_ERR_INVALID;
+  if (sms < 1 || sms > c->num_sms) sms = c->num_sms;
+  c->sms = sms;
+  return AFR_OK;
+}
+
 int afr_shadow_index(const afr_ctx* c) { return c ? c->shadow_cur : AFR_ERR_INVALID; }
 
 int afr_shadow_commit(afr_ctx* c) {
@@ -354,21 +364,37 @@ int afr_forward_eval(afr_ctx* c, const int64_t* tokens, int64_t token_stride, in
   else return fail(c, AFR_ERR_INVALID, "unknown out_kind");
   if (env_int("AFR_NO_TMA_STORE")) ep.use_tma_store = 0;
   const char* msg = nullptr;
-  const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
   cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
-                                   ep, c->num_sms, st, nullptr, &msg);
+                                   ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
   c->launches += 1;
   return AFR_OK;
 }
 
-int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
-                           const void* targets, int target_kind, const afr_dropout* dropout,
-                           double loss_count, float* loss_out, void* stream) {
+int afr_train_frontend(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                       const afr_dropout* dropout, void* stream) {
   if (!c) return AFR_ERR_INVALID;
   int rc = check_batch(c, B, S, tokens);
   if (rc) return rc;
   if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  c->drop = to_dropout(dropout);
+  c->tokens = reinterpret_cast<const long long*>(tokens);
+  c->token_stride = token_stride;
+  c->B = B; c->S = S;
+  c->fwd_done = false;
+  c->frontend_done = false;
+  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, true, st))) return rc;
+  c->frontend_done = true;
+  return AFR_OK;
+}
+
+int afr_train_loss(afr_ctx* c, const void* targets, int target_kind, double loss_count,
+                   float* loss_out, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->frontend_done) return fail(c, AFR_ERR_STATE, "afr_train_loss before afr_train_frontend");
   if (targets == nullptr || loss_out == nullptr || !(loss_count > 0))
     return fail(c, AFR_ERR_INVALID, "targets/loss_out NULL or loss_count <= 0");
   if (target_kind != AFR_TARGET_U8 && target_kind != AFR_TARGET_F32)
@@ -377,15 +403,12 @@ int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stri
     return fail(c, AFR_ERR_INVALID, "targets must be 16-byte aligned");
   DeviceGuard guard(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if ((rc = ensure_shadow(c, st))) return rc;
+  int rc = ensure_shadow(c, st);
+  if (rc) return rc;
   c->shadow_fwd = c->shadow_cur;
-  c->drop = to_dropout(dropout);
-  c->tokens = reinterpret_cast<const long long*>(tokens);
-  c->token_stride = token_stride;
-  c->B = B; c->S = S;
   c->grad_scale = static_cast<float>(2.0 / loss_count);  // d/dy of mean((y-t)^2)
-  if ((rc = run_frontend(c, c->tokens, token_stride, B, S, c->drop, true, st))) return rc;
-  const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  const int B = c->B;
+  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
   const int tiles = gemm_num_tiles(B, c->P, bn);
   if ((rc = ensure_loss_partials(c, tiles * 4))) return rc;
   GemmEpilogue ep{};
@@ -393,14 +416,23 @@ int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stri
   ep.target = targets; ep.target_is_f32 = target_kind == AFR_TARGET_F32;
   ep.loss_partials = c->loss_partials;
   const char* msg = nullptr;
-  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
-                                   ep, c->num_sms, st, nullptr, &msg);
+  cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false,
+                                   B, c->P, c->K, bn, ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward+loss)");
   AFR_CUDA(c, launch_loss_finalize(c->loss_partials, tiles * 4, loss_count, loss_out, st),
            "loss_finalize");
   c->launches += 2;
   c->fwd_done = true;
+  c->frontend_done = false;
   return AFR_OK;
+}
+
+int afr_train_forward_loss(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
+                           const void* targets, int target_kind, const afr_dropout* dropout,
+                           double loss_count, float* loss_out, void* stream) {
+  int rc = afr_train_frontend(c, tokens, token_stride, B, S, dropout, stream);
+  if (rc) return rc;
+  return afr_train_loss(c, targets, target_kind, loss_count, loss_out, stream);
 }
 
 int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
@@ -419,9 +451,9 @@ int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
   ep.out = c->grads.wout + static_cast<long long>(row_begin) * c->K;
   ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  const int bn = choose_bn(rows, c->K, c->num_sms, "AFR_BN_WGRAD");
+  const int bn = choose_bn(rows, c->K, c->sms, "AFR_BN_WGRAD");
   cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
-                                   c->B, bn, ep, c->num_sms, st, nullptr, &msg);
+                                   c->B, bn, ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(wgrad)");
   // db[rows] = scale * sum_b dZ[b, rows]
   AFR_CUDA(c, launch_bias_grad(c->dz + row_begin, c->B, rows, c->grad_scale, c->bias_scratch,
@@ -442,16 +474,16 @@ int afr_train_dgrad(afr_ctx* c, void* stream) {
   ep.kind = kEpiF32; ep.out = c->dfeat; ep.ldo = c->K; ep.alpha = c->grad_scale;
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  const int bn = choose_bn(c->B, c->K, c->num_sms, "AFR_BN_DGRAD");
+  const int bn = choose_bn(c->B, c->K, c->sms, "AFR_BN_DGRAD");
   cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow_buf[c->shadow_fwd], c->K, true, c->B, c->K, c->P, bn,
-                                   ep, c->num_sms, st, nullptr, &msg);
+                                   ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(dgrad)");
   if (!c->state_valid)
     return fail(c, AFR_ERR_STATE, "front-end records of this batch were overwritten by another forward");
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
                                        c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
-                                       c->fstate, c->partials, c->num_sms, &grid, c->num_sms, st),
+                                       c->fstate, c->partials, c->sms, &grid, c->sms, st),
            "frontend_backward");
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce");
@@ -493,9 +525,9 @@ int afr_forward_train(afr_ctx* c, const int64_t* tokens, int64_t token_stride, i
   ep.kind = kEpiF32; ep.out = c->logits; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  const int bn = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
+  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
   cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
-                                   ep, c->num_sms, st, nullptr, &msg);
+                                   ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
   AFR_CUDA(c, launch_clamp01(c->logits, sheet_out, static_cast<long long>(B) * c->P, st), "clamp01");
   c->launches += 2;
@@ -622,9 +654,9 @@ int afr_workspace_copy(afr_ctx* c, int which, void* dst, size_t bytes, void* str
 
 int afr_gemm_tiles(afr_ctx* c, int B, int* out) {
   if (!c || !out || B < 1) return AFR_ERR_INVALID;
-  out[0] = choose_bn(B, c->P, c->num_sms, "AFR_BN_FWD");
-  out[1] = choose_bn(B, c->K, c->num_sms, "AFR_BN_DGRAD");
-  out[2] = choose_bn(c->P, c->K, c->num_sms, "AFR_BN_WGRAD");
+  out[0] = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
+  out[1] = choose_bn(B, c->K, c->sms, "AFR_BN_DGRAD");
+  out[2] = choose_bn(c->P, c->K, c->sms, "AFR_BN_WGRAD");
   return AFR_OK;
 }
 
@@ -672,7 +704,7 @@ int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token
   AFR_CUDA(c, launch_frontend_backward(c->params, reinterpret_cast<const long long*>(tokens),
                                        token_stride, B, S, c->cfg.max_length, c->cfg.vocab,
                                        to_dropout(dropout), dfeat, c->fstate, c->partials,
-                                       c->num_sms, &grid, c->num_sms, st),
+                                       c->sms, &grid, c->sms, st),
            "frontend_backward(debug)");
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce(debug)");

@@ -211,6 +211,8 @@ class AttentionFontRenderer(nn.Module):
                 c.close()
             c = _Context(self, dev, cap, training)
             self._ctx = c
+            if getattr(self, "_sm_limit", 0):
+                c.check(c.lib.afr_set_sm_limit(c.handle, self._sm_limit))
             if self._shadow is not None and training and self._shadow[0].device == dev:
                 c.check(c.lib.afr_bind_shadow(c.handle, self._shadow[0].data_ptr(), self._shadow[1].data_ptr()))
                 c.shadow_bound = tuple(t.data_ptr() for t in self._shadow)
@@ -234,6 +236,26 @@ class AttentionFontRenderer(nn.Module):
             c.shadow_bound = tuple(t.data_ptr() for t in self._shadow)
             c.shadow_version = w._version       # rebuilt from the master at the next forward
         return self._shadow
+
+    def defer_join(self, side: torch.cuda.Stream):
+        """End of a data-parallel step: the all-gather of the updated bf16 rows is still running on
+        `side`. Nothing needs those weights before the next fc_output GEMM, so the join (stream
+        wait + activating the gathered copy) is postponed until then; the next step's front-end
+        kernel runs under the collective."""
+        self._pending = side
+
+    def join_pending(self):
+        side = getattr(self, "_pending", None)
+        if side is not None:
+            torch.cuda.current_stream(side.device).wait_stream(side)
+            self.shadow_commit()
+            self._pending = None
+
+    def set_sm_limit(self, sms: int):
+        """Data parallel: leave `#SMs - sms` SMs to the collective's CTAs (0 = all SMs)."""
+        self._sm_limit = sms
+        if self._ctx is not None:
+            self._ctx.check(self._ctx.lib.afr_set_sm_limit(self._ctx.handle, sms))
 
     def shadow_index(self) -> int:
         return int(self._ctx.lib.afr_shadow_index(self._ctx.handle))
@@ -309,6 +331,7 @@ class AttentionFontRenderer(nn.Module):
 
     # ------------------------------------------------------------------ forward paths
     def _eval_forward(self, x: torch.Tensor, kind: int) -> torch.Tensor:
+        self.join_pending()
         x = self._check_tokens(x)
         B, S = x.shape[0], min(x.shape[1], self.max_length)
         c = self._context(B, training=False)
@@ -325,6 +348,7 @@ class AttentionFontRenderer(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """model.py:158-204. Eval mode (or no_grad) -> fused render; train mode -> differentiable."""
         if self.training:
+            self.join_pending()
             x = self._check_tokens(x)
             S = min(x.shape[1], self.max_length)
             drop = self.make_dropout(x.shape[0], S)
@@ -376,9 +400,11 @@ class AttentionFontRenderer(nn.Module):
         if loss_out is None:
             loss_out = torch.empty((), dtype=torch.float32, device=tokens.device)
         count = float(loss_count) if loss_count is not None else float(B * self.sheet_height * self.sheet_width)
-        c.check(c.lib.afr_train_forward_loss(c.handle, tokens.data_ptr(), tokens.stride(0), B, S,
-                                             targets.data_ptr(), kind, C.byref(drop), count,
-                                             loss_out.data_ptr(), _stream_ptr(tokens.device)))
+        st = _stream_ptr(tokens.device)
+        c.check(c.lib.afr_train_frontend(c.handle, tokens.data_ptr(), tokens.stride(0), B, S,
+                                         C.byref(drop), st))
+        self.join_pending()          # fc_output weights of the previous data-parallel step
+        c.check(c.lib.afr_train_loss(c.handle, targets.data_ptr(), kind, count, loss_out.data_ptr(), st))
         self._live = (tokens, targets, drop)   # the library reads tokens / masks again in backward
         if drop.mode == 1:
             self.dropout_step += 1

@@ -101,6 +101,17 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
     return out
 
 
+_SMALL_GROUP = None
+
+
+def _small_group():
+    """Second NCCL communicator (all ranks) for the 0.13 MB all-reduce of the small gradients."""
+    global _SMALL_GROUP
+    if _SMALL_GROUP is None:
+        _SMALL_GROUP = dist.new_group()
+    return _SMALL_GROUP
+
+
 def owned_rows(P: int, rank: int, world: int) -> Tuple[int, int]:
     """Rows of fc_output.weight whose optimizer state (and fp32 master) rank `rank` owns."""
     if P % world != 0:
@@ -159,6 +170,7 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
         mark("tail")
         return
 
+    model.join_pending()
     side = model.side_stream()
     rank = dist.get_rank() if rank is None else rank
     lo, hi = owned_rows(P, rank, world)
@@ -183,10 +195,11 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     else:
         after_wgrad(0, 0, P)
     mark("dgrad")
-    dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM)   # ordered on the compute stream
+    # its own communicator: on the default one it would queue behind the all-gather above, which
+    # waits for the sharded AdamW sweep, which waits for the reduce-scatter
+    dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM, group=_small_group())
     optimizer.step_small(t_step)
-    main.wait_stream(side)
-    model.shadow_commit()
+    model.defer_join(side)      # joined right before the next fc_output GEMM (renderer.join_pending)
     optimizer.end_step()
     mark("tail")
 
@@ -346,6 +359,7 @@ class Trainer:
         state_dict() / optimizer.state_dict() are complete on every rank (checkpoint contract)."""
         if self.world == 1:
             return
+        self.model.join_pending()
         w = self.model.fc_output.weight
         lo, hi = owned_rows(w.shape[0], self.rank, self.world)
         tensors = [w.data]

@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--nccl-ctas", type=int, default=16,
+                    help="N > 1: SMs left to NCCL (NCCL_MAX_CTAS); the persistent kernels use the rest")
     ap.add_argument("--adam-buckets", type=int, default=1,
                     help="single GPU: row buckets of the wgrad GEMM / AdamW sweep over fc_output.weight")
     args = ap.parse_args()
@@ -198,6 +200,7 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=device)
     args.warmup = max(3, args.warmup)
     B = args.batch
@@ -207,6 +210,9 @@ def main():
     torch.manual_seed(SEED)
     model = AttentionFontRenderer().to(device).train()
     opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
+    if world > 1:
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        model.set_sm_limit(sms - int(os.environ["NCCL_MAX_CTAS"]))
     n_rot = 8
     tok_h, tgt_h = fast_synthetic_batch(B * n_rot, seed=1234 + rank)
     tok_h, tgt_h = tok_h.pin_memory(), tgt_h.pin_memory()

@@ -123,6 +123,11 @@ int afr_sync_shadow(afr_ctx* ctx, void* stream);
  * written copy by itself; a sharded sweep (own rows only) is completed by the caller's
  * all-gather and then activated with afr_shadow_commit. */
 int afr_bind_shadow(afr_ctx* ctx, void* copy0, void* copy1);
+/* The GEMMs and the front-end kernels are persistent (one CTA per SM, static tile order): a CTA
+ * that cannot become resident because a collective's CTAs hold its SM delays the whole kernel.
+ * A data-parallel caller therefore leaves the collective its SMs: the persistent kernels launch
+ * at most `sms` CTAs (values outside [1, #SMs] restore the default, all SMs). */
+int afr_set_sm_limit(afr_ctx* ctx, int sms);
 int afr_shadow_index(const afr_ctx* ctx);
 int afr_shadow_commit(afr_ctx* ctx);
 
@@ -139,6 +144,15 @@ int afr_forward_eval(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, 
 int afr_train_forward_loss(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
                            const void* targets, int target_kind, const afr_dropout* dropout,
                            double loss_count, float* loss_out, void* stream);
+/* The same in two calls, for callers that overlap something with the front-end: afr_train_frontend
+ * is everything before fc_output (model.py:167-193; reads only the ten small parameters), so a
+ * data-parallel caller lets it run while the all-gather of the fc_output weights updated in the
+ * previous step is still in flight, then joins and calls afr_train_loss (model.py:196-202,
+ * 304-306: the GEMM with the clamp / MSE / d(logits) epilogue). */
+int afr_train_frontend(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
+                       const afr_dropout* dropout, void* stream);
+int afr_train_loss(afr_ctx* ctx, const void* targets, int target_kind, double loss_count,
+                   float* loss_out, void* stream);
 /* Backward of fc_output w.r.t. its weight and bias (part of loss.backward(), model.py:309) for
  * pixel rows [row_begin, row_end) -- row ranges let a data-parallel caller all-reduce finished
  * buckets while later ones are still being computed. Overwrites the bound gradient rows. */
