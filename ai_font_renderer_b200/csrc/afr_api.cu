@@ -578,6 +578,38 @@ int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps
   return AFR_OK;
 }
 
+int afr_adamw_rows_gather(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, int64_t step, int row_begin, int row_end,
+                          const void* const* peer_grads, void* const* peer_shadows, int world,
+                          int ctas, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_state)
+    return fail(c, AFR_ERR_STATE, "params / adam state not bound");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
+    return fail(c, AFR_ERR_INVALID, "bad step or row range");
+  if (peer_grads == nullptr || peer_shadows == nullptr || world < 1 || world > 8 || ctas < 1)
+    return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_gather: need 1..8 peers and ctas >= 1");
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  const long long n = static_cast<long long>(row_end - row_begin) * c->K;
+  const float* g[8];
+  __nv_bfloat16* sh[8];
+  for (int q = 0; q < world; ++q) {
+    if (peer_grads[q] == nullptr || peer_shadows[q] == nullptr)
+      return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_gather: null peer pointer");
+    g[q] = static_cast<const float*>(peer_grads[q]) + off;
+    sh[q] = static_cast<__nv_bfloat16*>(peer_shadows[q]) + off;
+  }
+  DeviceGuard guard(c->cfg.device);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  AFR_CUDA(c, launch_adamw_gather(c->params.wout + off, c->m.wout + off, c->v.wout + off, n, h, g, sh,
+                                  world, ctas, static_cast<cudaStream_t>(stream)),
+           "adamw_gather(fc_output.weight rows)");
+  c->launches += 1;
+  c->shadow_rows_swept += row_end - row_begin;   // completed by the peers' stores; afr_shadow_commit
+  return AFR_OK;
+}
+
 int afr_adamw_small(afr_ctx* c, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream) {
   if (!c) return AFR_ERR_INVALID;

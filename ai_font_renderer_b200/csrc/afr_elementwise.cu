@@ -93,6 +93,65 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// Row-sharded data parallel AdamW with the two collectives folded in (training.py): this rank
+// owns `n4` float4 groups of fc_output.weight. The gradient of an owned element is the sum over
+// ranks of the local gradients, read straight out of every peer's dW buffer over NVLink (the
+// reduce-scatter); the updated weight goes, rounded to bf16, into the inactive shadow copy of
+// EVERY rank (the all-gather). All buffers are symmetric-memory allocations; `g` / `sh` hold the
+// peer-mapped pointers already offset to the owned rows, in rank order (own rank included). The
+// summation order is the rank order on every rank, and every element has exactly one owner, so
+// the result does not depend on timing. Launched on a handful of SMs (the rest keep running the
+// GEMMs / front-end backward) with 1024 threads each: remote loads are latency-bound, every
+// thread keeps world + 3 16-byte loads in flight.
+constexpr int kMaxPeers = 8;
+struct GatherPeers {
+  const float* g[kMaxPeers];
+  __nv_bfloat16* sh[kMaxPeers];
+  int world;
+};
+
+__device__ __forceinline__ float4 ld_peer(const float* base, long long i) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(reinterpret_cast<const float4*>(base) + i));
+  return r;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+adamw_gather_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                    long long n4, AdamHyper h, GatherPeers peers) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int W = peers.world;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 g[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < W) g[q] = ld_peer(peers.g[q], i);
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float4 s = g[0];
+#pragma unroll
+    for (int q = 1; q < kMaxPeers; ++q)
+      if (q < W) { s.x += g[q].x; s.y += g[q].y; s.z += g[q].z; s.w += g[q].w; }
+    adamw_elem(pv.x, s.x, mv.x, vv.x, h);
+    adamw_elem(pv.y, s.y, mv.y, vv.y, h);
+    adamw_elem(pv.z, s.z, mv.z, vv.z, h);
+    adamw_elem(pv.w, s.w, mv.w, vv.w, h);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+    uint2 packed;
+    packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+    packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < W) reinterpret_cast<uint2*>(peers.sh[q])[i] = packed;
+  }
+}
+
 constexpr int kMaxSmallJobs = 16;
 struct SmallJobs { SmallAdamJob j[kMaxSmallJobs]; int n; };
 
@@ -217,6 +276,20 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
   if (blocks > static_cast<long long>(num_sms) * ctas_per_sm) blocks = static_cast<long long>(num_sms) * ctas_per_sm;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, m, v, n4, n, h, shadow);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_gather(float* p, float* m, float* v, long long n, const AdamHyper& h,
+                                const float* const* peer_g, __nv_bfloat16* const* peer_shadow, int world,
+                                int ctas, cudaStream_t s) {
+  if (world < 1 || world > kMaxPeers || (n % 4) != 0 || ctas < 1) return cudaErrorInvalidValue;
+  GatherPeers peers{};
+  peers.world = world;
+  for (int q = 0; q < world; ++q) {
+    peers.g[q] = peer_g[q];
+    peers.sh[q] = peer_shadow[q];
+  }
+  adamw_gather_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 4, h, peers);
   return cudaGetLastError();
 }
 

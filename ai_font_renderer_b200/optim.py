@@ -79,6 +79,17 @@ class FusedAdamW(torch.optim.Optimizer):
                                          _stream_ptr(ctx.device)))
 
     @torch.no_grad()
+    def step_rows_gather(self, t: int, row_begin: int, row_end: int, peer_grads, peer_shadows,
+                         world: int, ctas: int):
+        """Row-sharded data parallel (training.PeerLink): AdamW on the owned rows with the
+        gradient summed straight out of the peers' dW buffers and the bf16 result stored into
+        every peer's inactive shadow copy, over NVLink, in one kernel on `ctas` SMs."""
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_adamw_rows_gather(ctx.handle, *self._hyper(), t, row_begin, row_end,
+                                                peer_grads, peer_shadows, world, ctas,
+                                                _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
     def step_small(self, t: int):
         ctx, _ = self._bucket
         ctx.check(ctx.lib.afr_adamw_small(ctx.handle, *self._hyper(), t, _stream_ptr(ctx.device)))

@@ -223,12 +223,14 @@ class AttentionFontRenderer(nn.Module):
             c.shadow_version = w._version
         return c
 
-    def own_shadow_copies(self, batch: int = 1):
+    def own_shadow_copies(self, batch: int = 1, copies=None):
         """Data parallel with a row-sharded optimizer: the two bf16 copies of fc_output.weight the
         GEMMs read become torch tensors (so NCCL can all-gather updated rows into the inactive
         one). Returns [copy0, copy1]; `shadow_index()` tells which one the next forward reads."""
         c = self._context(batch, training=True)
         w = self.fc_output.weight
+        if copies is not None:
+            self._shadow = list(copies)          # e.g. symmetric-memory allocations (PeerLink)
         if self._shadow is None or self._shadow[0].device != w.device:
             self._shadow = [torch.empty(w.shape, dtype=torch.bfloat16, device=w.device) for _ in range(2)]
         if getattr(c, "shadow_bound", None) != tuple(t.data_ptr() for t in self._shadow):

@@ -101,7 +101,57 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
     return out
 
 
+import ctypes as _C
+
 _SMALL_GROUP = None
+
+
+class PeerLink:
+    """NVLink peer memory for the data-parallel step (torch symmetric memory): fc_output's gradient
+    buffer and the two bf16 shadow copies of its weight are allocated symmetrically on every rank
+    and mapped into every other rank's address space. With them the row-sharded optimizer needs no
+    collective call for fc_output: one kernel per rank (afr_adamw_rows_gather) reads the owned rows
+    of every rank's dW over NVLink, applies AdamW and stores the bf16 result into every rank's
+    inactive shadow copy; the signal-pad barriers of the symmetric allocation order it against the
+    wgrad GEMMs before and the next forward after. Construct on all ranks at the same time."""
+
+    @staticmethod
+    def default_ctas(world: int) -> int:
+        """SMs given to the gather/AdamW/broadcast kernel (measured on 2/4/8 B200, bench.py
+        --comm-ctas sweeps): the owned shard -- and with it the kernel's local HBM work -- shrinks
+        with the number of ranks while its NVLink volume stays, so fewer SMs saturate it."""
+        return 48 if world <= 2 else (32 if world <= 4 else 24)
+
+    def __init__(self, model, ctas: int = 0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ctas = ctas or self.default_ctas(self.world)
+        w = model.fc_output.weight
+        dev = w.device
+        self.ctas = ctas
+        self.wgrad = symm_mem.empty(tuple(w.shape), dtype=torch.float32, device=dev)
+        self.wgrad.zero_()
+        self.h_grad = symm_mem.rendezvous(self.wgrad, group)
+        self.shadow = [symm_mem.empty(tuple(w.shape), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.h_shadow = [symm_mem.rendezvous(t, group) for t in self.shadow]
+        w.grad = self.wgrad                       # the wgrad GEMM writes the peer-visible buffer
+        model._param_grads()
+        model.own_shadow_copies(copies=self.shadow)
+        arr = _C.c_void_p * self.world
+        self.grad_ptrs = arr(*[int(p) for p in self.h_grad.buffer_ptrs])
+        self.shadow_ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self.h_shadow]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        model.set_sm_limit(sms - ctas)            # the gather kernel's SMs stay free of persistent CTAs
+        model._peer_link = self
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+            return True
+        except Exception:
+            return False
 
 
 def _small_group():
@@ -174,14 +224,28 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     side = model.side_stream()
     rank = dist.get_rank() if rank is None else rank
     lo, hi = owned_rows(P, rank, world)
+    link = getattr(model, "_peer_link", None)
     shadows = model.own_shadow_copies()
-    nxt = shadows[1 - model.shadow_index()]
+    nxt_index = 1 - model.shadow_index()
+    nxt = shadows[nxt_index]
 
     def after_wgrad(i, r0, r1):
         mark("wgrad")
-        # sum over ranks of dW[lo:hi] lands in place; ordered behind the wgrad GEMM on `main`
-        rs = dist.reduce_scatter_tensor(wgrad[lo:hi], wgrad, op=dist.ReduceOp.SUM, async_op=True)
         side.wait_stream(main)
+        if link is not None:
+            # NVLink peer memory, no collective call: barrier (every rank's dW complete) -> one
+            # kernel: gather-sum of the owned gradient rows, AdamW, bf16 rows to every rank ->
+            # barrier (rows delivered everywhere, nobody still reads this rank's dW)
+            with torch.cuda.stream(side):
+                link.h_grad.barrier(channel=0)
+                mark("adamw_begin")
+                optimizer.step_rows_gather(t_step, lo, hi, link.grad_ptrs, link.shadow_ptrs[nxt_index],
+                                           world, link.ctas)
+                mark("adamw_end")
+                link.h_grad.barrier(channel=1)
+            return
+        # NCCL: sum over ranks of dW[lo:hi] lands in place; ordered behind the wgrad GEMM on `main`
+        rs = dist.reduce_scatter_tensor(wgrad[lo:hi], wgrad, op=dist.ReduceOp.SUM, async_op=True)
         with torch.cuda.stream(side):
             rs.wait()                                   # stream-level wait on NCCL, no host sync
             mark("adamw_begin")

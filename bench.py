@@ -159,8 +159,8 @@ def workload_config(n_gpus):
                         "1024 glyphs per GPU per step (model.py:409)",
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
             "max_length": 100, "sheet": "80x240", "params": 122912896,
-            "parallelism": (f"dp{n_gpus}: batch sharded, dW reduce-scattered, AdamW of fc_output.weight "
-                            f"sharded by rows, bf16 weights all-gathered") if n_gpus > 1 else "single",
+            "parallelism": (f"dp{n_gpus}: batch sharded; AdamW of fc_output.weight sharded by rows, its "
+                            f"gradient rows summed from / bf16 weights stored to NVLink peer memory") if n_gpus > 1 else "single",
             "l2": "no flush: one step streams 3.9 GB (fp32 master, grads, Adam moments, bf16 shadow) "
                   "through the 126 MB L2 and rotates over 8 resident batches"}
 
@@ -174,8 +174,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--nccl-ctas", type=int, default=16,
-                    help="N > 1: SMs left to NCCL (NCCL_MAX_CTAS); the persistent kernels use the rest")
+    ap.add_argument("--dp-mode", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = row-sharded AdamW reading/writing NVLink peer memory in one "
+                         "kernel (no collective for fc_output); 'nccl' = reduce-scatter / all-gather")
+    ap.add_argument("--comm-ctas", type=int, default=0,
+                    help="N > 1: SMs left to the communication kernel (0 = PeerLink.default_ctas / 32 for "
+                         "NCCL); the persistent kernels use the rest")
     ap.add_argument("--adam-buckets", type=int, default=1,
                     help="single GPU: row buckets of the wgrad GEMM / AdamW sweep over fc_output.weight")
     args = ap.parse_args()
@@ -200,7 +204,8 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
+        if args.dp_mode == "nccl":
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_ctas or 32))
         dist.init_process_group("nccl", device_id=device)
     args.warmup = max(3, args.warmup)
     B = args.batch
@@ -211,8 +216,12 @@ def main():
     model = AttentionFontRenderer().to(device).train()
     opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
     if world > 1:
-        sms = torch.cuda.get_device_properties(device).multi_processor_count
-        model.set_sm_limit(sms - int(os.environ["NCCL_MAX_CTAS"]))
+        from ai_font_renderer_b200.training import PeerLink
+        if args.dp_mode == "peer":
+            PeerLink(model, ctas=args.comm_ctas)
+        else:
+            sms = torch.cuda.get_device_properties(device).multi_processor_count
+            model.set_sm_limit(sms - int(os.environ["NCCL_MAX_CTAS"]))
     n_rot = 8
     tok_h, tgt_h = fast_synthetic_batch(B * n_rot, seed=1234 + rank)
     tok_h, tgt_h = tok_h.pin_memory(), tgt_h.pin_memory()

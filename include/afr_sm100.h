@@ -179,6 +179,17 @@ int afr_adamw_step(afr_ctx* ctx, double lr, double beta1, double beta2, double e
                    double weight_decay, int64_t step, void* stream);
 int afr_adamw_rows(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int64_t step, int row_begin, int row_end, void* stream);
+/* Row-sharded data parallel step over NVLink peer memory (no NCCL call): AdamW on the owned rows
+ * [row_begin, row_end) whose gradient is the sum over `world` ranks, read directly from every
+ * rank's dW buffer (peer_grads[q] = base of rank q's fc_output.weight.grad, peer-mapped), and whose
+ * updated bf16 weights are stored into every rank's INACTIVE shadow copy (peer_shadows[q] = base
+ * of that copy on rank q, peer-mapped; see afr_bind_shadow / afr_shadow_commit). The caller
+ * provides the cross-rank barriers: all wgrad GEMMs done before, all stores delivered after.
+ * Runs on `ctas` CTAs so the remaining SMs keep the compute kernels. */
+int afr_adamw_rows_gather(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, int64_t step, int row_begin, int row_end,
+                          const void* const* peer_grads, void* const* peer_shadows, int world,
+                          int ctas, void* stream);
 int afr_adamw_small(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream);
 

@@ -24,11 +24,14 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_row_sharded_data_parallel_step_equals_single_gpu_step():
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_row_sharded_data_parallel_step_equals_single_gpu_step(mode):
+    """peer: gradient rows / bf16 weights move through NVLink peer memory inside the AdamW kernel;
+    nccl: reduce-scatter + all-gather."""
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(REPO, "tools", "dp_check.py")]
+           os.path.join(REPO, "tools", "dp_check.py"), mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=REPO)
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("dp_check")]
     assert res.returncode == 0 and lines and lines[-1].endswith("-> OK"), res.stdout[-2000:] + res.stderr[-2000:]

@@ -22,7 +22,8 @@ from ai_font_renderer_b200.renderer import AttentionFontRenderer  # noqa: E402
 from ai_font_renderer_b200.training import backward_and_step, owned_rows, shard_bounds  # noqa: E402
 
 
-def main(steps=3, per_rank=96):
+def main(steps=3, per_rank=96, mode=None):
+    mode = mode or (sys.argv[1] if len(sys.argv) > 1 else "peer")
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     torch.cuda.set_device(dev)
@@ -41,6 +42,9 @@ def main(steps=3, per_rank=96):
 
     solo, solo_opt = make()
     dp, dp_opt = make()
+    if mode == "peer":
+        from ai_font_renderer_b200.training import PeerLink
+        PeerLink(dp, ctas=16)
     lo, hi = shard_bounds(gB, rank, world)
     worst_loss = 0.0
     for _ in range(steps):
@@ -71,7 +75,7 @@ def main(steps=3, per_rank=96):
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     ok = res[0] < 1e-5 and res[1] < 1e-4 and res[3] < 1e-5 and res[4] < 1e-3
     if rank == 0:
-        print(f"dp_check world={world}: loss rel {res[0]:.2e}, bf16 weights rel {res[1]:.2e} "
+        print(f"dp_check world={world} mode={mode}: loss rel {res[0]:.2e}, bf16 weights rel {res[1]:.2e} "
               f"({100 * res[2]:.3f}% of elements differ by a bf16 ulp), owned fp32 rows rel {res[3]:.2e}, "
               f"small params rel {res[4]:.2e} -> {'OK' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
