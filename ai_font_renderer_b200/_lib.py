@@ -100,6 +100,10 @@ SIGNATURES = {
                                         C.c_int, C.c_int, _P]),
     "afr_adamw_small": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_int64, _P]),
+    "afr_train_wgrad_adamw": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                        C.c_int64, C.c_int, C.c_int, _P]),
+    "afr_train_bgrad": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "afr_debug_div_sqrt": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "afr_check_tokens": (C.c_int, [_P, _P]),
     "afr_workspace_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "afr_workspace_copy": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P]),

@@ -578,6 +578,62 @@ int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps
   return AFR_OK;
 }
 
+int afr_train_wgrad_adamw(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, int64_t step, int row_begin, int row_end,
+                          void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_wgrad_adamw before a training forward");
+  if (!c->has_params || !c->has_grads || !c->has_state)
+    return fail(c, AFR_ERR_STATE, "params / grads / adam state not bound");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end || (row_begin % 32) != 0 ||
+      ((row_end - row_begin) % 32) != 0)
+    return fail(c, AFR_ERR_INVALID, "bad step, or row range not 32-aligned inside [0, H*W]");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = row_end - row_begin;
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  GemmEpilogue ep{};
+  ep.kind = kEpiAdamW;
+  ep.out = c->wshadow_buf[1 - c->shadow_cur] + off;   // the copy the next forward will read
+  ep.ldo = c->K; ep.alpha = c->grad_scale;
+  ep.adam_p = c->params.wout + off; ep.adam_m = c->m.wout + off; ep.adam_v = c->v.wout + off;
+  ep.hyper = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  const char* msg = nullptr;
+  int bn = env_int("AFR_WA_BN");            // tuning knobs (tools/fused_sweep.py)
+  if (bn < 32 || bn > 256 || (bn % 32) != 0) bn = 256;
+  ep.adam_sets = env_int("AFR_WA_SETS");
+  ep.adam_sub = env_int("AFR_WA_SUB");
+  ep.adam_stages = env_int("AFR_WA_STAGES");
+  ep.adam_prefetch = env_int("AFR_WA_PREFETCH");
+  if (c->K < bn) bn = c->K;
+  cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
+                                   c->B, bn, ep, c->sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(wgrad+adamw)");
+  c->launches += 1;
+  c->shadow_rows_swept += rows;
+  if (c->shadow_rows_swept >= c->P) {   // every row rewritten: the next forward reads the new weights
+    c->shadow_cur ^= 1;
+    c->shadow_rows_swept = 0;
+    c->shadow_valid = true;
+  }
+  return AFR_OK;
+}
+
+int afr_train_bgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_bgrad before a training forward");
+  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  if (row_begin < 0 || row_end > c->P || row_begin >= row_end || (row_begin % 2) != 0)
+    return fail(c, AFR_ERR_INVALID, "bad row range");
+  DeviceGuard guard(c->cfg.device);
+  AFR_CUDA(c, launch_bias_grad(c->dz + row_begin, c->B, row_end - row_begin, c->grad_scale,
+                               c->bias_scratch, c->grads.bout + row_begin,
+                               static_cast<cudaStream_t>(stream), c->P),
+           "bias_grad");
+  c->launches += 2;
+  return AFR_OK;
+}
+
 int afr_adamw_rows_gather(afr_ctx* c, double lr, double beta1, double beta2, double eps,
                           double weight_decay, int64_t step, int row_begin, int row_end,
                           const void* const* peer_grads, void* const* peer_shadows, int world,
@@ -741,6 +797,15 @@ int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce(debug)");
   c->launches += 2;
+  return AFR_OK;
+}
+
+int afr_debug_div_sqrt(const float* a, const float* b, float* q, float* s, float* q_ieee,
+                       float* s_ieee, int64_t n, void* stream) {
+  if (!a || !b || !q || !s || !q_ieee || !s_ieee || n < 1)
+    return fail(nullptr, AFR_ERR_INVALID, "afr_debug_div_sqrt: null pointer or n < 1");
+  cudaError_t e = launch_div_sqrt_check(a, b, q, s, q_ieee, s_ieee, n, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail_cuda(nullptr, e, "afr_debug_div_sqrt");
   return AFR_OK;
 }
 

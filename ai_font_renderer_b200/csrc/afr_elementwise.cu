@@ -17,18 +17,6 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
   return r;
 }
 
-// torch.optim.AdamW (single-tensor path) element update, fp32, same operation order:
-//   p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = v*b2 + (1-b2)*g*g;
-//   p += -(lr/bc1) * (m / (sqrt(v)/sqrt(bc2) + eps))
-__device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v,
-                                           const AdamHyper& h) {
-  p = __fmul_rn(p, h.decay);
-  m = fmaf(h.beta1_w, __fsub_rn(g, m), m);
-  v = __fadd_rn(__fmul_rn(v, h.beta2), __fmul_rn(__fmul_rn(h.one_m_beta2, g), g));
-  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), h.bc2_sqrt), h.eps);
-  p = __fadd_rn(p, __fmul_rn(h.neg_step, __fdiv_rn(m, denom)));
-}
-
 // Grid-stride sweep, two independent 16-byte groups per thread and iteration (8 loads in flight
 // per thread before the first use).
 __device__ __forceinline__ void adamw_store(float* p, float* m, float* v, __nv_bfloat16* shadow,
@@ -254,6 +242,20 @@ clamp01_kernel(const float* __restrict__ z, float* __restrict__ y, long long n4,
       y[j] = fminf(fmaxf(z[j], 0.f), 1.f);
 }
 
+__global__ void __launch_bounds__(256)
+div_sqrt_check_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ q,
+                      float* __restrict__ s, float* __restrict__ q_ieee, float* __restrict__ s_ieee,
+                      long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = a[i], y = b[i];
+    q[i] = div_rn_nobranch(x, y);
+    q_ieee[i] = __fdiv_rn(x, y);
+    s[i] = sqrt_rn_nobranch(fabsf(x));
+    s_ieee[i] = __fsqrt_rn(fabsf(x));
+  }
+}
+
 int stream_grid(long long work_items, int threads, int num_sms) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms) * 8;  // 8 resident CTAs of 256 thr / SM
@@ -332,6 +334,12 @@ cudaError_t launch_bias_grad(const __nv_bfloat16* dz, int B, int P, float alpha,
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   bias_grad_stage2<<<(P + 255) / 256, 256, 0, s>>>(scratch, slices, P, alpha, dbias);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_div_sqrt_check(const float* a, const float* b, float* q, float* s, float* q_ieee,
+                                  float* s_ieee, long long n, cudaStream_t st) {
+  div_sqrt_check_kernel<<<stream_grid(n, 256, 148), 256, 0, st>>>(a, b, q, s, q_ieee, s_ieee, n);
   return cudaGetLastError();
 }
 

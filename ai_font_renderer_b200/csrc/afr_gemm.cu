@@ -45,14 +45,19 @@ bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const vo
 template <int EPI, bool A_MN, bool B_MN>
 cudaError_t launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_kernel<EPI, A_MN, B_MN>;
+  const int nsub = p.adam_sub;
+  const int smem_bytes = EPI == kEpiAdamW
+                             ? adam_smem_bytes(p.stages, p.b_stage_bytes, p.adam_sets, nsub)
+                             : kGemmSmemBytes;
+  const int threads = EPI == kEpiAdamW ? 64 + 128 * nsub : kGemmThreads;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         EPI == kEpiAdamW ? 232448 : kGemmSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, kGemmThreads, kGemmSmemBytes, stream>>>(p);
+  kern<<<grid, threads, smem_bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -91,6 +96,36 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
       ok &= encode_2d(&p.tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.out, M, N, epi.ldo, 32, 32);
     }
   }
+  if (epi.kind == kEpiAdamW) {
+    static const char* kBadAdam =
+        "gemm: fused AdamW epilogue needs MN-major operands, M % 32 == 0, 16-byte aligned p / m / v / "
+        "bf16 copy and ldo % 8 == 0";
+    if (!a_mn || !b_mn || (M % 32) != 0 || epi.adam_p == nullptr || epi.adam_m == nullptr ||
+        epi.adam_v == nullptr || epi.out == nullptr || (epi.ldo % 8) != 0 ||
+        ((reinterpret_cast<uintptr_t>(epi.adam_p) | reinterpret_cast<uintptr_t>(epi.adam_m) |
+          reinterpret_cast<uintptr_t>(epi.adam_v) | reinterpret_cast<uintptr_t>(epi.out)) & 15)) {
+      if (err_msg) *err_msg = kBadAdam;
+      return cudaErrorInvalidValue;
+    }
+    ok &= encode_2d(&p.tm_p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.adam_p, M, N, epi.ldo, 32, 32);
+    ok &= encode_2d(&p.tm_m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.adam_m, M, N, epi.ldo, 32, 32);
+    ok &= encode_2d(&p.tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.adam_v, M, N, epi.ldo, 32, 32);
+    p.hyper = epi.hyper;
+    p.adam_ptr[0] = epi.adam_p; p.adam_ptr[1] = epi.adam_m; p.adam_ptr[2] = epi.adam_v;
+    p.b_stage_bytes = ((BN + 63) / 64) * 8192;
+    p.adam_sub = epi.adam_sub >= 1 && epi.adam_sub <= kMaxAdamSub ? epi.adam_sub : kMaxAdamSub;
+    p.adam_sets = epi.adam_sets >= 1 && epi.adam_sets <= kMaxAdamSets ? epi.adam_sets : 1;
+    p.adam_prefetch = epi.adam_prefetch;
+    // deepest operand ring that still fits beside the slab sets
+    int stages = epi.adam_stages > 0 ? epi.adam_stages : kMaxStages;
+    if (stages > kMaxStages) stages = kMaxStages;
+    while (stages > 1 && adam_smem_bytes(stages, p.b_stage_bytes, p.adam_sets, p.adam_sub) > 232448) --stages;
+    if (stages < 2) {
+      if (err_msg) *err_msg = "gemm: fused AdamW epilogue: tile width / slab sets do not fit in shared memory";
+      return cudaErrorInvalidValue;
+    }
+    p.stages = stages;
+  }
   if (!ok) {
     if (err_msg) *err_msg = kBadMap;
     return cudaErrorInvalidValue;
@@ -116,6 +151,7 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     return launch_one<kEpiU8, false, false>(p, grid, stream);
   if (epi.kind == kEpiLoss && !a_mn && !b_mn && epi.bias != nullptr)
     return launch_one<kEpiLoss, false, false>(p, grid, stream);
+  if (epi.kind == kEpiAdamW) return launch_one<kEpiAdamW, true, true>(p, grid, stream);
   if (err_msg) *err_msg = kBadEpi;
   return cudaErrorInvalidValue;
 }

@@ -16,7 +16,16 @@
 //   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused epilogue -> global / TMA store)
 // Three mbarrier pipelines: smem full/empty, TMEM full/empty (two accumulator buffers so
 // the epilogue of tile i overlaps the MMAs of tile i+1), and a static persistent tile loop.
+//
+// kEpiAdamW is the wgrad GEMM with optimizer.step() of fc_output.weight (model.py:310) folded
+// into its epilogue: the accumulator IS the gradient, so instead of writing 491 MB of dW and
+// reading it back in a separate sweep, each epilogue warp streams the matching 32x32 tiles of
+// p / exp_avg / exp_avg_sq through shared memory with TMA (loads issued two chunks ahead, so
+// they run under the MMAs of the tile), applies torch's AdamW arithmetic in place and stores
+// p, m, v (TMA) and the bf16 weight copy. That kernel is HBM-bound (26 B/parameter); the operand
+// ring shrinks to two stages to make room for the staging slabs.
 #pragma once
+#include "afr_internal.h"
 #include "afr_ptx.cuh"
 
 namespace afr {
@@ -30,8 +39,20 @@ constexpr int kBStageBytes = kMaxBN * kBK * 2; // 32 KB
 constexpr int kStageBytes = kAStageBytes + kBStageBytes;
 constexpr int kEpiWarpBufBytes = 32 * 128;     // one 32-row x 128-byte staging slab
 constexpr int kEpiBytes = 4 * 2 * kEpiWarpBufBytes;  // 4 warps x 2 buffers = 32 KB
-constexpr int kBarrierBytes = 256;
+constexpr int kBarrierBytes = 512;
 constexpr int kGemmSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes + 1024;
+// kEpiAdamW: per epilogue warp `adam_sets` (2..4) slab sets of three 32x32 fp32 tiles (p, exp_avg,
+// exp_avg_sq); the operand ring has `stages` (2..8) stages of 16 KB + b_stage_bytes. Both are
+// chosen by the host so that the total fits the 227 KB of shared memory (adam_smem_bytes).
+constexpr int kAdamSlabBytes = 3 * kEpiWarpBufBytes;             // 12 KB
+constexpr int kMaxStages = 8;
+constexpr int kMaxAdamSets = 4;
+constexpr int kMaxAdamSub = 2;                                   // epilogue warps per lane quadrant
+constexpr int kAdamMaxThreads = 64 + 128 * kMaxAdamSub;
+__host__ __device__ constexpr int adam_smem_bytes(int stages, int b_stage_bytes, int sets, int nsub) {
+  return stages * (kAStageBytes + b_stage_bytes) + 4 * nsub * sets * kAdamSlabBytes + kBarrierBytes +
+         1024;
+}
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;                 // 2 accumulator buffers x 256 columns
 
@@ -39,6 +60,7 @@ enum EpiKind : int {
   kEpiF32 = 0,   // out_f32 = [clamp01](alpha*acc + bias[n])        (logits, dA, dW, eval sheet)
   kEpiU8 = 1,    // out_u8  = trunc(clamp01(acc + bias[n]) * 255)   (helpers.py:33 quantisation)
   kEpiLoss = 2,  // clamp + MSE partial sums + masked residual dZ   (model.py:202,270 + backward)
+  kEpiAdamW = 3, // g = alpha*acc never leaves the SM: AdamW on p/m/v tiles + bf16 copy (model.py:310)
 };
 
 struct GemmParams {
@@ -59,30 +81,49 @@ struct GemmParams {
   const void* target;    // kEpiLoss: [M, N] u8 (k/255) or f32
   int target_is_f32;
   float* loss_partials;  // kEpiLoss: [num_tiles * 4] per-warp sums of (y - t)^2
+  // kEpiAdamW: fp32 [M, N] maps (32x32 boxes, 128B swizzle) of the parameter and its moments,
+  // used for both the loads and the in-place stores; out = bf16 copy [M, ldo]
+  CUtensorMap tm_p, tm_m, tm_v;
+  AdamHyper hyper;
+  float* adam_ptr[3];    // p, exp_avg, exp_avg_sq base pointers (L2 prefetch of the next tile)
+  int stages;            // operand ring depth
+  int b_stage_bytes;     // bytes of one B-operand stage
+  int adam_sets;         // slab sets per epilogue warp (threads = 64 + 128 * warps per quadrant)
+  int adam_sub;          // epilogue warps per TMEM lane quadrant (1..kMaxAdamSub)
+  int adam_prefetch;     // 1: bulk-prefetch the next tile's p/m/v rows into L2 as contiguous runs
 };
 
 template <int EPI, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(EPI == kEpiAdamW ? kAdamMaxThreads : kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms are 1024-byte aligned.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int kStages = (EPI == kEpiAdamW) ? p.stages : afr::kStages;
+  const int kBStage = (EPI == kEpiAdamW) ? p.b_stage_bytes : kBStageBytes;
+  const int epi_region =
+      (EPI == kEpiAdamW) ? ((static_cast<int>(blockDim.x) - 64) >> 5) * p.adam_sets * kAdamSlabBytes : kEpiBytes;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kAStageBytes;
-  uint8_t* smem_epi = smem + kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiBytes);
-  uint64_t* full_bar = bars;                    // [kStages]
-  uint64_t* empty_bar = bars + kStages;         // [kStages]
-  uint64_t* tmem_full_bar = bars + 2 * kStages; // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* smem_epi = smem_b + kStages * kBStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + epi_region);
+  uint64_t* full_bar = bars;                          // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;    // [4]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 4;       // [4]
+  uint64_t* adam_ld_bar = tmem_empty_bar + 4;         // [kMaxAdamSub * 4 warps][kMaxAdamSets]   (kEpiAdamW)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(adam_ld_bar + 4 * kMaxAdamSub * kMaxAdamSets);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int BN = p.BN;
+  // TMEM accumulator buffers: 2 x 256 columns, or 4 x 128 when the tile is at most 128 wide (the
+  // MMA warp can then run three tiles ahead of the slowest epilogue warp instead of one)
+  const int n_acc = BN <= 128 ? 4 : 2;
+  const int acc_stride = kTmemCols / n_acc;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tm_a);
@@ -92,9 +133,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 128);
+      ptx::mbar_init(&tmem_empty_bar[a], blockDim.x - 64);   // every epilogue thread
+    }
+    if (EPI == kEpiAdamW) {
+      ptx::prefetch_tensormap(&p.tm_p);
+      ptx::prefetch_tensormap(&p.tm_m);
+      ptx::prefetch_tensormap(&p.tm_v);
+      for (int i = 0; i < 4 * kMaxAdamSub * kMaxAdamSets; ++i) ptx::mbar_init(&adam_ld_bar[i], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -122,19 +169,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
           uint8_t* sa = smem_a + stage * kAStageBytes;
-          uint8_t* sb = smem_b + stage * kBStageBytes;
+          uint8_t* sb = smem_b + stage * kBStage;
+          // the fused-AdamW kernel streams 3 GB through L2 next to its operands: keep them
+          constexpr uint64_t pol = EPI == kEpiAdamW ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
           if constexpr (!A_MN) {
-            ptx::tma_load_2d(&p.tm_a, &full_bar[stage], sa, kb * kBK, m0);
+            ptx::tma_load_2d_hint(&p.tm_a, &full_bar[stage], sa, kb * kBK, m0, pol);
           } else {
 #pragma unroll
             for (int i = 0; i < kBM / 64; ++i)
-              ptx::tma_load_2d(&p.tm_a, &full_bar[stage], sa + i * 8192, m0 + i * 64, kb * kBK);
+              ptx::tma_load_2d_hint(&p.tm_a, &full_bar[stage], sa + i * 8192, m0 + i * 64, kb * kBK, pol);
           }
           if constexpr (!B_MN) {
-            ptx::tma_load_2d(&p.tm_b, &full_bar[stage], sb, kb * kBK, n0);
+            ptx::tma_load_2d_hint(&p.tm_b, &full_bar[stage], sb, kb * kBK, n0, pol);
           } else {
             for (uint32_t i = 0; i < b_boxes; ++i)
-              ptx::tma_load_2d(&p.tm_b, &full_bar[stage], sb + i * 8192, n0 + i * 64, kb * kBK);
+              ptx::tma_load_2d_hint(&p.tm_b, &full_bar[stage], sb + i * 8192, n0 + i * 64, kb * kBK, pol);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -155,14 +204,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_stride);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint64_t da = ptx::make_smem_desc_sw128(
               ptx::smem_u32(smem_a + stage * kAStageBytes), a_lbo, 1024u);
           const uint64_t db = ptx::make_smem_desc_sw128(
-              ptx::smem_u32(smem_b + stage * kBStageBytes), b_lbo, 1024u);
+              ptx::smem_u32(smem_b + stage * kBStage), b_lbo, 1024u);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             ptx::umma_bf16(d_tmem, da + static_cast<uint64_t>(k * a_kstep),
@@ -173,9 +222,161 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
       }
+    }
+  } else if constexpr (EPI == kEpiAdamW) {
+    // ------------------------------------------------------------ epilogue warps, fused AdamW
+    // 4 * nsub warps: warp (q, sub) owns the 32 rows of TMEM lane quadrant q = warp % 4 and the
+    // 32-column chunks c = sub (mod nsub) of every tile. Per chunk the p / exp_avg / exp_avg_sq
+    // tiles arrive by TMA in one of the warp's slab sets (128B swizzle, row = lane); the warp
+    // moves them to registers and immediately refills the set with a later chunk, so the sets are
+    // load buffers that are in flight almost all the time. The update runs in registers and
+    // leaves through 32-byte streaming stores (every lane writes full sectors of its own row).
+    // Loads never depend on the MMAs, so they also run while the warp waits for an accumulator.
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int nsub = (static_cast<int>(blockDim.x) - 64) >> 7;
+    const int sets = p.adam_sets;
+    uint8_t* slabs = smem_epi + (sub * 4 + q) * (sets * kAdamSlabBytes);
+    uint64_t* ld_bar = adam_ld_bar + (sub * 4 + q) * kMaxAdamSets;
+    const AdamHyper h = p.hyper;
+    auto chunks_of = [&](int t) {
+      const int n0 = (t / p.num_m_tiles) * BN;
+      return (min(BN, p.N - n0)) >> 5;
+    };
+    // next tile >= t in which this warp has work: its 32 rows inside M, a chunk index == sub
+    auto next_active = [&](int t) {
+      while (t < num_tiles && ((t % p.num_m_tiles) * kBM + q * 32 >= p.M || chunks_of(t) <= sub))
+        t += gridDim.x;
+      return t;
+    };
+    // loader cursor (lane 0 issues; every lane tracks it)
+    int lt = next_active(blockIdx.x), lc = sub, s_issue = 0;
+    int l_chunks = 0, l_col0 = 0, l_row = 0;
+    auto load_tile_coords = [&]() {
+      if (lt >= num_tiles) return;
+      l_chunks = chunks_of(lt);
+      l_col0 = (lt / p.num_m_tiles) * BN;
+      l_row = (lt % p.num_m_tiles) * kBM + q * 32;
+    };
+    load_tile_coords();
+    auto issue_next = [&]() {
+      if (lt >= num_tiles) return;
+      if (lane == 0) {
+        const int col = l_col0 + lc * 32;
+        uint8_t* dst = slabs + s_issue * kAdamSlabBytes;
+        ptx::mbar_arrive_expect_tx(&ld_bar[s_issue], kAdamSlabBytes);
+        ptx::tma_load_2d_hint(&p.tm_p, &ld_bar[s_issue], dst, col, l_row, ptx::kL2EvictFirst);
+        ptx::tma_load_2d_hint(&p.tm_m, &ld_bar[s_issue], dst + kEpiWarpBufBytes, col, l_row,
+                              ptx::kL2EvictFirst);
+        ptx::tma_load_2d_hint(&p.tm_v, &ld_bar[s_issue], dst + 2 * kEpiWarpBufBytes, col, l_row,
+                              ptx::kL2EvictFirst);
+        // adam_prefetch >= 2: also pull this warp's next (adam_prefetch - 1) chunks of the same
+        // rows into L2 now, so DRAM sees several adjacent 128-byte pieces of a row at once
+        for (int k = 1; k < p.adam_prefetch; ++k) {
+          if (lc + k * nsub >= l_chunks) break;
+          const int pc = col + k * nsub * 32;
+          ptx::tma_prefetch_2d(&p.tm_p, pc, l_row);
+          ptx::tma_prefetch_2d(&p.tm_m, pc, l_row);
+          ptx::tma_prefetch_2d(&p.tm_v, pc, l_row);
+        }
+      }
+      if (++s_issue == sets) s_issue = 0;
+      lc += nsub;
+      if (lc >= l_chunks) { lc = sub; lt = next_active(lt + gridDim.x); load_tile_coords(); }
+    };
+    for (int i = 0; i < sets; ++i) issue_next();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int s = 0;                              // slab set of the chunk being consumed
+    uint32_t s_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.num_m_tiles) * kBM;
+      const int n0 = (tile / p.num_m_tiles) * BN;
+      const long long m = m0 + q * 32 + lane;
+      const int n_chunks = chunks_of(tile);
+      const bool active = m0 + q * 32 < p.M && n_chunks > sub;
+      if (active && p.adam_prefetch == 1 && sub == 0) {
+        // the next tile's rows as contiguous runs -> L2; one row per lane
+        const int nt = next_active(tile + gridDim.x);
+        if (nt < num_tiles) {
+          const long long row = (nt % p.num_m_tiles) * kBM + q * 32 + lane;
+          const long long e = row * p.ldo + (nt / p.num_m_tiles) * BN;
+          const uint32_t bytes = static_cast<uint32_t>(chunks_of(nt)) * 128u;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) ptx::prefetch_l2_bulk(p.adam_ptr[a] + e, bytes);
+        }
+      }
+      bool acc_ready = false;
+      for (int c = sub; active && c < n_chunks; c += nsub) {
+        const int n = n0 + c * 32;
+        // p, m, v of this chunk: shared memory -> registers, then refill the slab set at once
+        const uint32_t sp = ptx::smem_u32(slabs + s * kAdamSlabBytes + lane * 128);
+        ptx::mbar_wait(&ld_bar[s], s_phase);
+        float4 pv[8], mv[8], vv[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const int off = (ch ^ (lane & 7)) << 4;
+          pv[ch] = ptx::lds_f4(sp + off);
+          mv[ch] = ptx::lds_f4(sp + kEpiWarpBufBytes + off);
+          vv[ch] = ptx::lds_f4(sp + 2 * kEpiWarpBufBytes + off);
+        }
+        __syncwarp();                       // every lane's reads of the set are done
+        issue_next();
+        if (++s == sets) { s = 0; s_phase ^= 1u; }
+        if (!acc_ready) {
+          ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+          ptx::tc_fence_after();
+          acc_ready = true;
+        }
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * acc_stride + c * 32),
+                           r);
+        ptx::tmem_ld_wait();
+        if (c + nsub >= n_chunks) {         // this warp's last read of the accumulator buffer
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          adamw_elem(pv[ch].x, __fmul_rn(__uint_as_float(r[4 * ch]), p.alpha), mv[ch].x, vv[ch].x, h);
+          adamw_elem(pv[ch].y, __fmul_rn(__uint_as_float(r[4 * ch + 1]), p.alpha), mv[ch].y, vv[ch].y, h);
+          adamw_elem(pv[ch].z, __fmul_rn(__uint_as_float(r[4 * ch + 2]), p.alpha), mv[ch].z, vv[ch].z, h);
+          adamw_elem(pv[ch].w, __fmul_rn(__uint_as_float(r[4 * ch + 3]), p.alpha), mv[ch].w, vv[ch].w, h);
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(pv[ch].x, pv[ch].y);
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(pv[ch].z, pv[ch].w);
+          packed[2 * ch] = *reinterpret_cast<const uint32_t*>(&lo);
+          packed[2 * ch + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+        }
+        const long long e = m * p.ldo + n;
+        float* op = p.adam_ptr[0] + e;
+        float* om = p.adam_ptr[1] + e;
+        float* ov = p.adam_ptr[2] + e;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ptx::stg_256(op + 8 * k, pv[2 * k], pv[2 * k + 1]);
+          ptx::stg_256(om + 8 * k, mv[2 * k], mv[2 * k + 1]);
+          ptx::stg_256(ov + 8 * k, vv[2 * k], vv[2 * k + 1]);
+        }
+        // bf16 copy: 64 bytes per row as two full 32-byte sectors
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + e;
+        const uint32_t w0[8] = {packed[0], packed[1], packed[2], packed[3],
+                                packed[4], packed[5], packed[6], packed[7]};
+        const uint32_t w1[8] = {packed[8],  packed[9],  packed[10], packed[11],
+                                packed[12], packed[13], packed[14], packed[15]};
+        ptx::stg_256(o, w0);
+        ptx::stg_256(o + 16, w1);
+      }
+      if (!acc_ready) {                     // no chunk of this tile is ours: just release the buffer
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
@@ -199,7 +400,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (n >= p.N) break;  // warp-uniform
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(acc * kMaxBN + c * 32),
+                               static_cast<uint32_t>(acc * acc_stride + c * 32),
                            r);
         ptx::tmem_ld_wait();
         if (c == n_chunks - 1 || n + 32 >= p.N) {
@@ -317,8 +518,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
         if (lane == 0) p.loss_partials[tile * 4 + q] = loss_acc;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
     }
     if (EPI == kEpiF32 && p.use_tma_store && lane == 0) ptx::tma_store_wait_all<0>();
   }

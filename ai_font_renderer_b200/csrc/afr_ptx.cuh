@@ -70,6 +70,41 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority hints for TMA traffic (the 64-bit policy words createpolicy would produce):
+// data that is re-read by other CTAs (GEMM operands) vs. data that streams through once.
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* tm, uint64_t* bar, void* smem_dst,
+                                                 int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, const void* smem_src,
+                                                  int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+          reinterpret_cast<uint64_t>(tm)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// 32-byte streaming global stores (one full sector per thread; no L1 allocation, first to be
+// evicted from L2).
+__device__ __forceinline__ void stg_256(void* gdst, const uint32_t (&w)[8]) {
+  asm volatile(
+      "st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gdst),
+      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+      : "memory");
+}
+__device__ __forceinline__ void stg_256(float* gdst, const float4& a, const float4& b) {
+  asm volatile(
+      "st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gdst),
+      "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+      : "memory");
+}
 // 2-D tile store shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src,
                                              int32_t c0, int32_t c1) {
@@ -104,6 +139,38 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// Prefetch of one tensor-map box into L2 (no shared-memory destination).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// 128-bit shared-memory accesses by 32-bit shared address (the generic-pointer forms compile to
+// LD.E / ST.E, which take the slower generic path).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// Bulk prefetch of a contiguous global range into L2 (no shared-memory destination).
+// addr and bytes must be multiples of 16.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
+                   reinterpret_cast<uint64_t>(gsrc)),
+               "r"(bytes)
+               : "memory");
 }
 
 // ---------------------------------------------------------------- packed fp32 (FFMA2) / MUFU

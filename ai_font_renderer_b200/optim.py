@@ -16,12 +16,15 @@ from .renderer import AttentionFontRenderer, _stream_ptr
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model: AttentionFontRenderer, lr: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, weight_decay: float = 1e-2):
+                 eps: float = 1e-8, weight_decay: float = 1e-2, fuse_wgrad: bool = True):
         if not isinstance(model, AttentionFontRenderer):
             raise TypeError("FusedAdamW is bound to an ai_font_renderer_b200.AttentionFontRenderer")
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
             raise ValueError("invalid AdamW hyper-parameter")
         self.model = model
+        # single GPU: training.backward_and_step folds the step of fc_output.weight into the
+        # wgrad GEMM (wgrad_step_rows); False keeps the two-kernel form (gradient materialised)
+        self.fuse_wgrad = fuse_wgrad
         super().__init__(model._ordered_params(), dict(lr=lr, betas=betas, eps=eps,
                                                        weight_decay=weight_decay))
 
@@ -77,6 +80,21 @@ class FusedAdamW(torch.optim.Optimizer):
         ctx, _ = self._bucket
         ctx.check(ctx.lib.afr_adamw_rows(ctx.handle, *self._hyper(), t, row_begin, row_end,
                                          _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
+    def wgrad_step_rows(self, t: int, row_begin: int, row_end: int):
+        """Backward of fc_output w.r.t. weight / bias rows [row_begin, row_end) and the AdamW step
+        of those weight rows in ONE kernel (afr_train_wgrad_adamw): the gradient stays in tensor
+        memory, fc_output.weight.grad is not written. Needs a preceding fused_forward_loss."""
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_train_wgrad_adamw(ctx.handle, *self._hyper(), t, row_begin, row_end,
+                                                _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
+    def bias_grad_rows(self, row_begin: int, row_end: int):
+        """fc_output.bias.grad for the rows wgrad_step_rows handled (afr_train_bgrad)."""
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_train_bgrad(ctx.handle, row_begin, row_end, _stream_ptr(ctx.device)))
 
     @torch.no_grad()
     def step_rows_gather(self, t: int, row_begin: int, row_end: int, peer_grads, peer_shadows,

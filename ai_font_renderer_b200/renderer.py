@@ -412,16 +412,21 @@ class AttentionFontRenderer(nn.Module):
             self.dropout_step += 1
         return loss_out
 
-    def fused_backward(self, row_buckets=None, on_bucket=None):
+    def fused_backward(self, row_buckets=None, on_bucket=None, wgrad_fn=None):
         """loss.backward() (model.py:309): overwrites every p.grad. row_buckets: list of
         (row_begin, row_end) over fc_output's rows; on_bucket(i, begin, end) is called after the
-        launches of each bucket so a data-parallel caller can start its all-reduce."""
+        launches of each bucket so a data-parallel caller can start its all-reduce.
+        wgrad_fn(begin, end), if given, replaces the wgrad launch of a bucket (the optimizer's
+        wgrad_step_rows: gradient and AdamW step of those rows in one kernel)."""
         c = self._ctx
         st = _stream_ptr(self.fc_output.weight.device)
         P = self.sheet_height * self.sheet_width
         buckets = row_buckets or [(0, P)]
         for i, (lo, hi) in enumerate(buckets):
-            c.check(c.lib.afr_train_wgrad(c.handle, lo, hi, st))
+            if wgrad_fn is not None:
+                wgrad_fn(lo, hi)
+            else:
+                c.check(c.lib.afr_train_wgrad(c.handle, lo, hi, st))
             if on_bucket is not None:
                 on_bucket(i, lo, hi)
         c.check(c.lib.afr_train_dgrad(c.handle, st))

@@ -174,8 +174,11 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
                       rank: Optional[int] = None):
     """loss.backward(); optimizer.step() (model.py:309-310) for one rank of a data-parallel job.
 
-    world == 1: wgrad, the AdamW sweep over fc_output.weight (right behind the gradient that is
-    still partly in L2), dgrad, the front-end backward, the small-tensor AdamW -- one stream.
+    world == 1, optimizer.fuse_wgrad (default): the wgrad GEMM with the AdamW step of
+    fc_output.weight in its epilogue (afr_train_wgrad_adamw; fc_output.weight.grad is not
+    materialised), dgrad, the front-end backward, the small-tensor AdamW -- one stream.
+    world == 1, fuse_wgrad off: wgrad, the AdamW sweep over fc_output.weight (right behind the
+    gradient that is still partly in L2), dgrad, the front-end backward, the small-tensor AdamW.
     (Measured on B200, tools/overlap_probe.py: running the HBM-bound sweep on a second stream
     under the GEMMs / front-end backward buys nothing -- those kernels take the SM's whole
     shared-memory carveout, the sweep then runs with ~no L1 and both slow down by what the
@@ -202,6 +205,25 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     wgrad = model.fc_output.weight.grad
     t_step = optimizer.begin_step()
     P = wgrad.shape[0]
+
+    if world == 1 and getattr(optimizer, "fuse_wgrad", False):
+        # one kernel per bucket: wgrad GEMM whose epilogue applies AdamW to the fc_output.weight
+        # tiles (the gradient never reaches HBM); 'adamw_*' marks bracket that kernel
+        last = len(buckets) - 1
+
+        def fused_bucket(r0, r1):
+            mark("adamw_begin")
+            optimizer.wgrad_step_rows(t_step, r0, r1)
+            mark("adamw_end")
+            optimizer.bias_grad_rows(r0, r1)
+
+        model.fused_backward(buckets, lambda i, r0, r1: mark("wgrad") if i == last else None,
+                             wgrad_fn=fused_bucket)
+        mark("dgrad")
+        optimizer.step_small(t_step)
+        optimizer.end_step()
+        mark("tail")
+        return
 
     if world == 1:
         last = len(buckets) - 1

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- train glyphs/s of the B200 hot path (BASELINE.json metric) on synthetic sheets.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode train|render]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-fuse] [--no-render]
 
 N > 1 is launched by the driver as `python -m torch.distributed.run --nproc-per-node N bench.py
 --gpus N ...` (one rank per GPU, NCCL). Prints ONE JSON line on rank 0.
@@ -15,7 +15,9 @@ the per-GPU batch stays 1024, gradients are all-reduced over NCCL.
   value   whole-job glyphs/s with the batches already resident in HBM (CUDA events, max over ranks)
   e2e     the same step driven through the public API with HOST buffers: every step copies its
           tokens + uint8 sheets from pinned host memory and reads the loss back
-  roofline  the dominant kernel (the fused AdamW sweep, HBM-bound) timed live with CUDA events
+  roofline  the dominant kernel (single GPU: the wgrad GEMM with the AdamW step of fc_output.weight
+            in its epilogue, HBM-bound; N > 1: the row-sharded AdamW kernel) timed live with CUDA events
+  render    batched inference render glyphs/s (uint8 sheets), device-resident and end to end
   cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
 `--impl reference` times only that CPU path (the reference arm of the contract).
 """
@@ -43,6 +45,9 @@ K_FEAT, P_PIX, N_PARAMS_W = 6400, 19200, 19200 * 6400
 GEMM_FLOP_PER_GLYPH = 3 * 2 * K_FEAT * P_PIX          # fwd + dgrad + wgrad of fc_output
 ADAMW_BYTES_PER_PARAM = 30                            # p,g,m,v read; p,m,v write; bf16 shadow write
 ADAMW_TRAFFIC_NCU = 3629e6                            # dram read+write per full sweep, profiles/r01_ncu_summary.md
+FUSED_BYTES_PER_PARAM = 26                            # wgrad GEMM + AdamW epilogue: p,m,v read; p,m,v + bf16 copy write
+FUSED_TRAFFIC_NCU = None                              # filled from profiles/ once captured (see load_fused_traffic)
+RENDER_BATCH = 4096
 
 
 def load_peaks():
@@ -145,7 +150,7 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.gpus),
+        "data": "synthetic", "config": workload_config(args.gpus, args.gpus == 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -154,9 +159,84 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def load_fused_traffic():
+    """DRAM bytes (read + write) of one launch of the fused wgrad+AdamW kernel from the committed
+    `ncu --set full` capture (profiles/*_fused_traffic.json), or None before it exists."""
+    path = os.path.join(REPO, "profiles", "r01_fused_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_read_plus_write"])
+    except (OSError, KeyError, ValueError):
+        return FUSED_TRAFFIC_NCU
+
+
+def measure_render(model, device, rank, world, dist):
+    """Batched inference render (helpers.py:46-74 without the file writes): glyph strings sharded
+    over the ranks, no collective; one pass = RENDER_BATCH strings -> uint8 sheets. Reported
+    device-resident (tokens in HBM, sheets left in HBM) and end to end (int64 tokens from pinned
+    host memory, uint8 sheets copied back to pinned host memory)."""
+    n_pass, n_rot = 20, 4
+    g = torch.Generator().manual_seed(99 + rank)
+    n = RENDER_BATCH * n_rot
+    lengths = torch.randint(10, 101, (n, 1), generator=g)
+    letters = torch.randint(65, 91, (n, 100), generator=g)
+    letters[torch.rand((n, 100), generator=g) < 0.148] = 32
+    tok_h = torch.where(torch.arange(100).unsqueeze(0) < lengths, letters, torch.zeros_like(letters)).long()
+    tok_h = tok_h.pin_memory()
+    if world > 1:
+        model.join_pending()
+        model.set_sm_limit(0)          # rendering has no collective: all SMs
+    tok_d = tok_h.to(device)
+    out_h = torch.empty((RENDER_BATCH, 80, 240), dtype=torch.uint8).pin_memory()
+    was_training = model.training
+    model.eval()
+
+    def resident(i):
+        s = (i % n_rot) * RENDER_BATCH
+        return model.render_u8(tok_d[s:s + RENDER_BATCH])
+
+    def e2e(i):
+        s = (i % n_rot) * RENDER_BATCH
+        x = tok_h[s:s + RENDER_BATCH].to(device, non_blocking=True)
+        out_h.copy_(model.render_u8(x), non_blocking=True)
+
+    res = {}
+    for name, fn in (("resident", resident), ("e2e", e2e)):
+        for i in range(3):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_pass):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        res[name] = ms
+    model.train(was_training)
+    glyphs = RENDER_BATCH * n_pass * world
+    flop = 2.0 * K_FEAT * P_PIX
+    return {"metric": "render_glyphs_per_sec", "unit": UNIT, "batch_per_gpu": RENDER_BATCH,
+            "passes": n_pass, "value": glyphs / (res["resident"] / 1e3),
+            "ms_per_pass": res["resident"] / n_pass,
+            "tflops_per_gpu": glyphs / world * flop / (res["resident"] / 1e3) / 1e12,
+            "e2e": {"value": glyphs / (res["e2e"] / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_pass": RENDER_BATCH * 100 * 8, "d2h_bytes_per_pass": RENDER_BATCH * P_PIX,
+                    "ms_per_pass": res["e2e"] / n_pass},
+            "output": "uint8 sheets (helpers.py:33 quantisation fused in the GEMM epilogue)"}
+
+
+def workload_config(n_gpus, fused=False):
     return {"workload": "config[1] FiraCode model 100 chars -> 80x240, fused fwd/bwd/AdamW, "
                         "1024 glyphs per GPU per step (model.py:409)",
+            "optimizer": ("AdamW of fc_output.weight inside the wgrad GEMM epilogue (gradient not materialised)"
+                          if fused else "AdamW sweep kernel over fc_output.weight"),
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
             "max_length": 100, "sheet": "80x240", "params": 122912896,
             "parallelism": (f"dp{n_gpus}: batch sharded; AdamW of fc_output.weight sharded by rows, its "
@@ -180,6 +260,9 @@ def main():
     ap.add_argument("--comm-ctas", type=int, default=0,
                     help="N > 1: SMs left to the communication kernel (0 = PeerLink.default_ctas / 32 for "
                          "NCCL); the persistent kernels use the rest")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="single GPU: keep wgrad and the AdamW sweep as two kernels (gradient materialised)")
+    ap.add_argument("--no-render", action="store_true", help="skip the batched-render measurement")
     ap.add_argument("--adam-buckets", type=int, default=1,
                     help="single GPU: row buckets of the wgrad GEMM / AdamW sweep over fc_output.weight")
     args = ap.parse_args()
@@ -214,7 +297,8 @@ def main():
     # model: the reference's construction under its seed (model.py:87-90,402)
     torch.manual_seed(SEED)
     model = AttentionFontRenderer().to(device).train()
-    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
+    fused = world == 1 and not args.no_fuse
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fused)
     if world > 1:
         from ai_font_renderer_b200.training import PeerLink
         if args.dp_mode == "peer":
@@ -323,13 +407,18 @@ def main():
             t_step = opt.begin_step()
             torch.cuda.synchronize()
             e0.record()
-            opt.step_rows(t_step, 0, P_PIX)
+            if fused:
+                opt.wgrad_step_rows(t_step, 0, P_PIX)   # dZ / features of the last step are still there
+            else:
+                opt.step_rows(t_step, 0, P_PIX)
             e1.record()
             opt.step_small(t_step)
             opt.end_step()
             torch.cuda.synchronize()
             iso.append(e0.elapsed_time(e1))
     adamw_iso_ms = min(iso) if iso else None
+
+    render = None if args.no_render else measure_render(model, device, rank, world, dist)
 
     if rank != 0:
         if world > 1:
@@ -339,26 +428,36 @@ def main():
     peaks = load_peaks()
     value = gB * args.steps / (ms_res / 1e3)
     e2e_value = gB * args.steps / (ms_e2e / 1e3)
-    adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
+    if fused:
+        # wgrad GEMM with the AdamW epilogue: p, m, v read + written, bf16 copy written, plus the
+        # two bf16 operands (dZ [B,P], features [B,K]) read once
+        kernel_name = "gemm_bf16_tcgen05_kernel<kEpiAdamW> (wgrad GEMM, AdamW of fc_output.weight in its epilogue)"
+        adamw_bytes = FUSED_BYTES_PER_PARAM * N_PARAMS_W + 2 * B * (P_PIX + K_FEAT)
+        traffic = load_fused_traffic()
+    else:
+        kernel_name = "adamw_kernel (fc_output.weight sweep + bf16 shadow)"
+        adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
+        traffic = ADAMW_TRAFFIC_NCU
     adamw_gbs = adamw_bytes / (adamw_ms_per_step / 1e3) / 1e9
     gemm_tf = B * GEMM_FLOP_PER_GLYPH / ((phase_ms["forward"] + phase_ms["wgrad"] + phase_ms["dgrad"]) / 1e3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(world),
+        "config": workload_config(world, fused),
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(feeder.h2d_bytes_per_batch), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "adamw_kernel (fc_output.weight sweep + bf16 shadow)",
+        "roofline": {"kernel": kernel_name,
                      "bound": "hbm", "achieved": adamw_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": adamw_gbs / peaks["hbm"], "traffic": ADAMW_TRAFFIC_NCU,
+                     "frac": adamw_gbs / peaks["hbm"], "traffic": traffic,
                      "algorithmic_bytes_per_launch": adamw_bytes // len(buckets),
                      "launches_per_step": len(buckets), "ms_per_launch": adamw_ms_per_launch,
                      "alone_ms_per_sweep": adamw_iso_ms,
                      "alone_frac": (adamw_bytes / (adamw_iso_ms / 1e3) / 1e9 / peaks["hbm"]) if adamw_iso_ms else None,
+                     "tensor_flop_per_launch": (2 * B * K_FEAT * P_PIX // len(buckets)) if fused else 0,
                      "peak_source": peaks["source"]},
         "gemm": {"tflops_incl_frontend_and_epilogues": gemm_tf,
                  "frac_of_bf16_sustained_peak": gemm_tf / peaks["tf_sustained"],
@@ -368,6 +467,8 @@ def main():
         "train_tflops_whole_step": value * GEMM_FLOP_PER_GLYPH / 1e12 / world,
         "final_loss": final_loss,
     }
+    if render is not None:
+        line["render"] = render
     if world == 1 and not args.no_cpu_baseline:
         cpu_value, cpu_sec = cpu_train_glyphs_per_sec(steps=6, warmup=2)
         line["cpu_baseline"] = {

@@ -192,6 +192,22 @@ int afr_adamw_rows_gather(afr_ctx* ctx, double lr, double beta1, double beta2, d
                           int ctas, void* stream);
 int afr_adamw_small(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream);
+/* loss.backward() w.r.t. fc_output.weight / .bias (model.py:309) AND optimizer.step() of
+ * fc_output.weight (model.py:310) for pixel rows [row_begin, row_end) in ONE kernel: the wgrad
+ * GEMM's accumulator is the gradient, its epilogue streams the matching tiles of the parameter and
+ * the Adam moments through shared memory, applies afr_adamw_rows' arithmetic (bit-identical) and
+ * writes p, exp_avg, exp_avg_sq and the bf16 copy. The 491 MB gradient is never written or re-read
+ * (26 instead of 38 bytes of HBM traffic per parameter for the two reference statements), so the
+ * bound fc_output.weight.grad is left UNTOUCHED by this call. Single-GPU only (a data-parallel
+ * gradient must be summed over ranks first). Replaces afr_train_wgrad + afr_adamw_rows for the
+ * weight; the bias gradient of the same rows comes from afr_train_bgrad. Row ranges must be
+ * multiples of 32. */
+int afr_train_wgrad_adamw(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, int64_t step, int row_begin, int row_end,
+                          void* stream);
+/* fc_output.bias.grad[row_begin:row_end] alone (the part of afr_train_wgrad that
+ * afr_train_wgrad_adamw leaves out): column sums of d(loss)/d(logits), deterministic order. */
+int afr_train_bgrad(afr_ctx* ctx, int row_begin, int row_end, void* stream);
 
 /* Synchronises the stream and reports AFR_ERR_TOKEN_RANGE if any token id seen since the last
  * call was outside [0, vocab) (the reference fails with IndexError at model.py:167). */
@@ -221,6 +237,13 @@ int afr_debug_frontend_forward(afr_ctx* ctx, const int64_t* tokens, int64_t toke
                                int S, const afr_dropout* dropout, float* feats_f32, void* stream);
 int afr_debug_frontend_backward(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B,
                                 int S, const afr_dropout* dropout, const float* dfeat, void* stream);
+
+/* Test hook for the AdamW arithmetic: the kernels compute the optimizer's two divisions and its
+ * square root with branch-free round-to-nearest sequences (afr_internal.h). For n device floats
+ * a[i], b[i]: q[i] = that division a/b, s[i] = that square root of |a|, and q_ieee / s_ieee the
+ * results of the IEEE instructions (div.rn.f32 / sqrt.rn.f32) on the same inputs. */
+int afr_debug_div_sqrt(const float* a, const float* b, float* q, float* s, float* q_ieee,
+                       float* s_ieee, int64_t n, void* stream);
 
 /* Diagnostic: D[M,N] (fp32, ld = ldd) = alpha * A * B^T with bf16 operands on the tcgen05 path.
  * a_mn_major / b_mn_major: operand stored [K, M] resp. [K, N] row-major instead of [M, K] / [N, K].

@@ -324,6 +324,104 @@ def test_output_layer_chain_given_identical_features(default_state):
 
 
 # ------------------------------------------------------------------------------------ AdamW
+def _two_kernel_vs_fused(cfg, state, tokens, targets, steps, buckets_fused):
+    """Runs `steps` training steps twice -- wgrad + AdamW sweep as two kernels, and the wgrad GEMM
+    with the AdamW epilogue -- from the same state with the same built-in dropout stream."""
+    from ai_font_renderer_b200.optim import FusedAdamW
+    from ai_font_renderer_b200.training import backward_and_step, row_buckets
+    P = cfg.sheet_h * cfg.sheet_w
+    out = []
+    for fuse, nb in ((False, 1), (True, buckets_fused)):
+        model = make_model(cfg, state).train()
+        model.dropout_seed, model.dropout_step = 4242, 0
+        opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fuse)
+        losses = []
+        for _ in range(steps):
+            losses.append(model.fused_forward_loss(tokens, targets))
+            backward_and_step(model, opt, nb if isinstance(nb, list) else row_buckets(P, nb), 1)
+        torch.cuda.synchronize()
+        w = model.fc_output.weight
+        shadow = model._ctx.workspace_tensor(3, tuple(w.shape), torch.bfloat16)
+        out.append(dict(loss=[float(x) for x in losses],
+                        state={k: v.detach().clone() for k, v in model.state_dict().items()},
+                        m=opt.state[w]["exp_avg"].clone(), v=opt.state[w]["exp_avg_sq"].clone(),
+                        shadow=shadow, step=float(opt.state[w]["step"])))
+    return out
+
+
+def _assert_fused_identical(two, fused):
+    assert two["loss"] == fused["loss"]
+    assert two["step"] == fused["step"]
+    for k in orc.STATE_KEYS:
+        assert torch.equal(two["state"][k], fused["state"][k]), k
+    assert torch.equal(two["m"], fused["m"])
+    assert torch.equal(two["v"], fused["v"])
+    assert torch.equal(two["shadow"], fused["shadow"])
+    w = fused["state"]["fc_output.weight"]
+    assert torch.equal(fused["shadow"], w.to(torch.bfloat16))     # bf16 copy == rounded master
+
+
+@pytest.mark.parametrize("buckets", [1, 3, [(0, 96), (96, 256)]])
+def test_small_wgrad_adamw_epilogue_is_bit_identical_to_two_kernels(golden_small, buckets):
+    """afr_train_wgrad_adamw == afr_train_wgrad + afr_adamw_rows, bit for bit (parameters, both
+    Adam moments, the bf16 copy, the loss curve), over 3 steps, whole range, row buckets,
+    and ragged (32-aligned) row ranges whose last 128-row tile is partly outside."""
+    cfg = small_cfg(golden_small)
+    assert cfg.sheet_h * cfg.sheet_w == 256
+    tokens = torch.from_numpy(golden_small["tokens"]).to(dev())
+    targets = torch.from_numpy(golden_small["targets_u8"]).to(dev())
+    two, fused = _two_kernel_vs_fused(cfg, state_from_npz(golden_small, "state0"), tokens, targets,
+                                      3, buckets)
+    _assert_fused_identical(two, fused)
+
+
+@pytest.mark.parametrize("B", [192, 1024])
+def test_default_wgrad_adamw_epilogue_is_bit_identical_to_two_kernels(default_state, B):
+    """The same at the reference's shape (19200 x 6400 weight, 150 x 25 tiles of 128 x 256) for a
+    tail batch and the full batch."""
+    cfg = orc.OracleConfig()
+    strings = orc.dataset_strings(B)
+    tokens = orc.encode_strings(strings, cfg.max_length).to(dev())
+    targets = torch.from_numpy(orc.synthetic_targets_u8(strings, cfg)).to(dev())
+    two, fused = _two_kernel_vs_fused(cfg, default_state, tokens, targets, 2, 1)
+    _assert_fused_identical(two, fused)
+
+
+def test_adamw_branch_free_div_sqrt_are_ieee_round_to_nearest():
+    """The AdamW kernels' branch-free division / square root (afr_internal.h) against the IEEE
+    instructions, bit for bit, over the operand ranges AdamW produces: divisors sqrt(1-b2^t) in
+    [0.0999, 1] and sqrt(v)/.. + eps in [1e-8, 1e19]; numerators / radicands anything from 0 and
+    denormals up to 1e19 (quotients that would be denormal are excluded -- see the header)."""
+    from ai_font_renderer_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    n = 1 << 22
+    mag = lambda lo, hi: torch.exp2(torch.rand(n, generator=g) * (hi - lo) + lo)
+    sign = torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0)
+    cases = []
+    # m / denom : |m| in [2^-100, 2^60], denom in [1e-8, 2^63]
+    cases.append((sign * mag(-100, 60), mag(math.log2(1e-8), 63)))
+    # sqrt(v) / bc2_sqrt : numerator in [2^-75, 2^64], divisor in [0.0999, 1]
+    cases.append((mag(-75, 64), torch.rand(n, generator=g) * 0.9 + 0.0999))
+    # radicands down to the denormals and exact zeros / powers of two / perfect squares
+    edge = torch.cat([torch.zeros(64), torch.exp2(torch.arange(-149, 100).float()),
+                      (torch.arange(1, 4096).float()) ** 2,
+                      torch.tensor([1.1754944e-38, 1.4e-45, 5.4210109e-20, 5.421011e-20, 3.4e38])])
+    a_edge = torch.cat([edge, mag(-149, -60)[: n - edge.numel()]])
+    cases.append((a_edge, torch.ones(n)))
+    for a, b in cases:
+        a, b = a.float().to(dev()), b.float().to(dev())
+        out = [torch.empty_like(a) for _ in range(4)]
+        _lib.check(lib.afr_debug_div_sqrt(a.data_ptr(), b.data_ptr(), *[t.data_ptr() for t in out], n,
+                                          torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        q, s, q_ieee, s_ieee = out
+        normal_q = q_ieee.abs() >= 1.1754944e-38
+        assert torch.equal(q[normal_q].view(torch.int32), q_ieee[normal_q].view(torch.int32))
+        assert float((q - q_ieee).abs().max()) <= 1.5e-45 * 2        # denormal quotients: <= 1 ulp
+        assert torch.equal(s.view(torch.int32), s_ieee.view(torch.int32))
+
+
 def test_fused_adamw_matches_torch_adamw():
     from ai_font_renderer_b200.optim import FusedAdamW
     cfg = orc.OracleConfig(max_length=12, sheet_h=8, sheet_w=32)
