@@ -52,10 +52,87 @@ def render_batch_u8(model, strings: Sequence[str], device, batch_size: int = 409
     return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
 
 
-def render_strings(model, strings, output_dir, sheet_height, sheet_width, device):
+class RenderPipeline:
+    """Batched render into pinned HOST memory: batch i's uint8 sheets travel device -> host on a
+    copy stream while batch i+1 is rendered (two device buffers, CUDA events both ways), so the
+    19.2 KB/glyph of output crosses PCIe under the GEMM instead of after it. The reference
+    (helpers.py:62-68) does one forward, one `.cpu()` and one PIL call per string."""
+
+    def __init__(self, model, device, batch_size: int = 4096):
+        self.model, self.device, self.batch = model, torch.device(device), batch_size
+        shape = (batch_size, model.sheet_height, model.sheet_width)
+        self.dev = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.rendered = [torch.cuda.Event() for _ in range(2)]
+        self.copied = [None, None]
+
+    @torch.no_grad()
+    def render_to_host(self, tokens: torch.Tensor, out: torch.Tensor = None, on_batch=None) -> torch.Tensor:
+        """tokens: int64 [N, L] (host, ideally pinned, or device). Returns uint8 [N,H,W] in pinned
+        host memory (`out` if given). on_batch(lo, hi, done_event), if given, is called after the
+        D2H copy of sheets [lo, hi) has been enqueued; done_event fires when they are on the host."""
+        n = tokens.shape[0]
+        H, W = self.model.sheet_height, self.model.sheet_width
+        if out is None:
+            out = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
+        main = torch.cuda.current_stream(self.device)
+        for i, lo in enumerate(range(0, n, self.batch)):
+            hi, k = min(n, lo + self.batch), i % 2
+            x = tokens[lo:hi].to(self.device, non_blocking=True)
+            if self.copied[k] is not None:
+                main.wait_event(self.copied[k])            # buffer k has left for the host
+            y = self.dev[k][: hi - lo]
+            self.model.render_u8(x, out=y)
+            self.rendered[k].record(main)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.rendered[k])
+                out[lo:hi].copy_(y, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self.copy_stream)
+            self.copied[k] = done
+            if on_batch is not None:
+                on_batch(lo, hi, done)
+        main.wait_stream(self.copy_stream)
+        return out
+
+
+def bmp_file_block(sheets: np.ndarray) -> np.ndarray:
+    """[n, 1078 + H*stride] uint8: the complete file image of every sheet (same bytes as
+    grey_bmp_bytes), built with three array copies instead of n Python loops."""
+    assert sheets.dtype == np.uint8 and sheets.ndim == 3
+    n, h, w = sheets.shape
+    stride = (w + 3) & ~3
+    head = np.frombuffer(grey_bmp_bytes(np.zeros((h, w), dtype=np.uint8))[:_BMP_HEADER_BYTES], dtype=np.uint8)
+    block = np.zeros((n, _BMP_HEADER_BYTES + h * stride), dtype=np.uint8)
+    block[:, :_BMP_HEADER_BYTES] = head
+    block[:, _BMP_HEADER_BYTES:].reshape(n, h, stride)[:, :, :w] = sheets[:, ::-1, :]
+    return block
+
+
+def write_bmp_files(sheets: np.ndarray, output_dir: str, first_index: int = 0, threads: int = 8,
+                    name: str = "string_{}.bmp"):
+    """Writes sheets[i] as output_dir/string_{first_index+i}.bmp (helpers.py:66-68 naming) from a
+    small thread pool (file writes release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    block = bmp_file_block(sheets)
+
+    def one(i):
+        with open(os.path.join(output_dir, name.format(first_index + i)), "wb") as f:
+            f.write(memoryview(block[i]))
+
+    if len(block) <= 8 or threads <= 1:
+        for i in range(len(block)):
+            one(i)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(one, range(len(block))))
+
+
+def render_strings(model, strings, output_dir, sheet_height, sheet_width, device, batch_size: int = 4096):
     """Render a list of strings as BMP images -- same signature, file names, truncation warning and
-    summary line as helpers.py:46-74. Like the reference it does not switch the model to eval():
-    callers do (model.py:314, helpers.py:103)."""
+    summary line as helpers.py:46-74, for any number of strings: batches go through
+    RenderPipeline, and each batch's files are written while the next one renders. Like the
+    reference it does not switch the model to eval(): callers do (model.py:314, helpers.py:103)."""
     os.makedirs(output_dir, exist_ok=True)
     strings = list(strings)
     for i, s in enumerate(strings):
@@ -63,16 +140,20 @@ def render_strings(model, strings, output_dir, sheet_height, sheet_width, device
             strings[i] = s[:model.max_length]
             print(f"Warning: String truncated to {model.max_length} characters: {strings[i]}")
     if strings:
-        was_training = model.training
-        if was_training:
+        tokens = strings_to_tokens(strings, model.max_length)
+        if model.training:
             # helpers.py:64 would run a dropout forward here; that only happens if a caller
-            # forgot model.eval(). Keep the quirk observable but do not add RNG files to disk:
+            # forgot model.eval(). Keep the quirk observable:
             with torch.no_grad():
-                sheets = (model(strings_to_tokens(strings, model.max_length).to(device)) * 255).to(torch.uint8)
+                sheets = (model(tokens.to(device)) * 255).to(torch.uint8)
+            write_bmp_files(sheets.cpu().numpy(), output_dir)
         else:
-            sheets = render_batch_u8(model, strings, device)
-        host = sheets.cpu().numpy()
-        for idx in range(len(strings)):
-            with open(f"{output_dir}/string_{idx}.bmp", "wb") as f:
-                f.write(grey_bmp_bytes(host[idx]))
+            pipe = RenderPipeline(model, device, min(batch_size, len(strings)))
+            pending = []
+            host = pipe.render_to_host(tokens.pin_memory() if len(strings) > 64 else tokens,
+                                       on_batch=lambda lo, hi, ev: pending.append((lo, hi, ev)))
+            arr = host.numpy()
+            for lo, hi, ev in pending:       # batch k's files are written while later copies land
+                ev.synchronize()
+                write_bmp_files(arr[lo:hi], output_dir, first_index=lo)
     print(f"Saved {len(strings)} rendered strings to {output_dir}/")

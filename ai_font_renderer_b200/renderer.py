@@ -332,12 +332,18 @@ class AttentionFontRenderer(nn.Module):
         return d
 
     # ------------------------------------------------------------------ forward paths
-    def _eval_forward(self, x: torch.Tensor, kind: int) -> torch.Tensor:
+    def _eval_forward(self, x: torch.Tensor, kind: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.join_pending()
         x = self._check_tokens(x)
         B, S = x.shape[0], min(x.shape[1], self.max_length)
         c = self._context(B, training=False)
-        if kind == _lib.OUT_SHEET_U8:
+        if out is not None:
+            want = torch.uint8 if kind == _lib.OUT_SHEET_U8 else torch.float32
+            if (out.dtype != want or not out.is_contiguous() or out.device != x.device
+                    or out.numel() != B * self.sheet_height * self.sheet_width):
+                raise ValueError("out must be a contiguous tensor of B*H*W elements of the output dtype on the "
+                                 "tokens' device")
+        elif kind == _lib.OUT_SHEET_U8:
             out = torch.empty((B, self.sheet_height, self.sheet_width), dtype=torch.uint8, device=x.device)
         elif kind == _lib.OUT_SHEET_F32:
             out = torch.empty((B, self.sheet_height, self.sheet_width), dtype=torch.float32, device=x.device)
@@ -366,9 +372,10 @@ class AttentionFontRenderer(nn.Module):
         return self._eval_forward(x, _lib.OUT_SHEET_F32)
 
     @torch.no_grad()
-    def render_u8(self, x: torch.Tensor) -> torch.Tensor:
-        """Eval forward + helpers.py:33 quantisation fused in the GEMM epilogue -> uint8 [B,H,W]."""
-        return self._eval_forward(x, _lib.OUT_SHEET_U8)
+    def render_u8(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Eval forward + helpers.py:33 quantisation fused in the GEMM epilogue -> uint8 [B,H,W]
+        (written into `out` if given: render.RenderPipeline reuses two device buffers)."""
+        return self._eval_forward(x, _lib.OUT_SHEET_U8, out=out)
 
     @torch.no_grad()
     def logits(self, x: torch.Tensor) -> torch.Tensor:

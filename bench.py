@@ -50,6 +50,29 @@ FUSED_TRAFFIC_NCU = None                              # filled from profiles/ on
 RENDER_BATCH = 4096
 
 
+_STDOUT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner,
+    torchrun's OMP notice) are sent to stderr for the whole run; emit_line() writes the result to
+    the real stdout."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def load_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -156,7 +179,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def load_fused_traffic():
@@ -170,47 +193,63 @@ def load_fused_traffic():
         return FUSED_TRAFFIC_NCU
 
 
-def measure_render(model, device, rank, world, dist):
+def measure_render(model, device, rank, world, dist, bmp_set=False):
     """Batched inference render (helpers.py:46-74 without the file writes): glyph strings sharded
     over the ranks, no collective; one pass = RENDER_BATCH strings -> uint8 sheets. Reported
-    device-resident (tokens in HBM, sheets left in HBM) and end to end (int64 tokens from pinned
-    host memory, uint8 sheets copied back to pinned host memory)."""
-    n_pass, n_rot = 20, 4
-    g = torch.Generator().manual_seed(99 + rank)
-    n = RENDER_BATCH * n_rot
-    lengths = torch.randint(10, 101, (n, 1), generator=g)
-    letters = torch.randint(65, 91, (n, 100), generator=g)
-    letters[torch.rand((n, 100), generator=g) < 0.148] = 32
-    tok_h = torch.where(torch.arange(100).unsqueeze(0) < lengths, letters, torch.zeros_like(letters)).long()
+    device-resident (tokens in HBM, sheets left in HBM) and end to end through
+    render.RenderPipeline (int64 tokens from pinned host memory, uint8 sheets copied back to pinned
+    host memory on a copy stream under the next batch's render).
+    bmp_set: BASELINE config 5 -- a model whose embedding covers the 65,536 code points of the
+    Unicode BMP renders sample i = [code point i, 0, 0, ...]; the code points are sharded over the
+    ranks (65536 / world each)."""
+    from ai_font_renderer_b200.render import RenderPipeline
+    if bmp_set:
+        from ai_font_renderer_b200.renderer import AttentionFontRenderer
+        torch.manual_seed(SEED)
+        model = AttentionFontRenderer(vocab=65536).to(device)
+        per_rank = 65536 // world
+        codes = torch.arange(rank * per_rank, (rank + 1) * per_rank)
+        tok_h = torch.zeros((per_rank, 100), dtype=torch.int64)
+        tok_h[:, 0] = codes
+        n_pass, n_rot = max(1, per_rank // RENDER_BATCH), max(1, per_rank // RENDER_BATCH)
+        batch = min(RENDER_BATCH, per_rank)
+    else:
+        n_pass, n_rot, batch = 20, 4, RENDER_BATCH
+        g = torch.Generator().manual_seed(99 + rank)
+        n = batch * n_rot
+        lengths = torch.randint(10, 101, (n, 1), generator=g)
+        letters = torch.randint(65, 91, (n, 100), generator=g)
+        letters[torch.rand((n, 100), generator=g) < 0.148] = 32
+        tok_h = torch.where(torch.arange(100).unsqueeze(0) < lengths, letters, torch.zeros_like(letters)).long()
+        if world > 1:
+            model.join_pending()
+            model.set_sm_limit(0)          # rendering has no collective: all SMs
     tok_h = tok_h.pin_memory()
-    if world > 1:
-        model.join_pending()
-        model.set_sm_limit(0)          # rendering has no collective: all SMs
     tok_d = tok_h.to(device)
-    out_h = torch.empty((RENDER_BATCH, 80, 240), dtype=torch.uint8).pin_memory()
     was_training = model.training
     model.eval()
+    pipe = RenderPipeline(model, device, batch)
+    out_h = torch.empty((batch * n_pass, 80, 240), dtype=torch.uint8).pin_memory()
+    idx = torch.cat([torch.arange((i % n_rot) * batch, (i % n_rot + 1) * batch) for i in range(n_pass)])
+    tok_seq = tok_h[idx].pin_memory()      # the n_pass batches back to back
 
-    def resident(i):
-        s = (i % n_rot) * RENDER_BATCH
-        return model.render_u8(tok_d[s:s + RENDER_BATCH])
+    def resident():
+        for i in range(n_pass):
+            s = (i % n_rot) * batch
+            model.render_u8(tok_d[s:s + batch], out=pipe.dev[i % 2][:batch])
 
-    def e2e(i):
-        s = (i % n_rot) * RENDER_BATCH
-        x = tok_h[s:s + RENDER_BATCH].to(device, non_blocking=True)
-        out_h.copy_(model.render_u8(x), non_blocking=True)
+    def e2e():
+        pipe.render_to_host(tok_seq, out=out_h)
 
     res = {}
     for name, fn in (("resident", resident), ("e2e", e2e)):
-        for i in range(3):
-            fn(i)
+        fn()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(n_pass):
-            fn(i)
+        fn()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -219,16 +258,20 @@ def measure_render(model, device, rank, world, dist):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
         res[name] = ms
+    model.check_tokens_in_range()
     model.train(was_training)
-    glyphs = RENDER_BATCH * n_pass * world
+    glyphs = batch * n_pass * world
     flop = 2.0 * K_FEAT * P_PIX
-    return {"metric": "render_glyphs_per_sec", "unit": UNIT, "batch_per_gpu": RENDER_BATCH,
-            "passes": n_pass, "value": glyphs / (res["resident"] / 1e3),
+    return {"metric": "render_glyphs_per_sec", "unit": UNIT, "batch_per_gpu": batch,
+            "passes": n_pass, "glyphs": glyphs, "value": glyphs / (res["resident"] / 1e3),
             "ms_per_pass": res["resident"] / n_pass,
             "tflops_per_gpu": glyphs / world * flop / (res["resident"] / 1e3) / 1e12,
             "e2e": {"value": glyphs / (res["e2e"] / 1e3), "unit": UNIT,
-                    "h2d_bytes_per_pass": RENDER_BATCH * 100 * 8, "d2h_bytes_per_pass": RENDER_BATCH * P_PIX,
-                    "ms_per_pass": res["e2e"] / n_pass},
+                    "h2d_bytes_per_pass": batch * 100 * 8, "d2h_bytes_per_pass": batch * P_PIX,
+                    "ms_per_pass": res["e2e"] / n_pass,
+                    "how": "render.RenderPipeline: D2H of batch i on a copy stream under the render of batch i+1"},
+            "workload": ("config[4]: 65,536 BMP code points, embedding [65536,32], sharded over the ranks"
+                         if bmp_set else "config[1] model, synthetic strings of 10-100 chars"),
             "output": "uint8 sheets (helpers.py:33 quantisation fused in the GEMM epilogue)"}
 
 
@@ -266,6 +309,7 @@ def main():
     ap.add_argument("--adam-buckets", type=int, default=1,
                     help="single GPU: row buckets of the wgrad GEMM / AdamW sweep over fc_output.weight")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,7 +325,7 @@ def main():
     from ai_font_renderer_b200.training import backward_and_step, row_buckets
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"}))
+        emit_line({"error": "no CUDA device: the B200 path has no CPU fallback"})
         return 2
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
@@ -419,6 +463,7 @@ def main():
     adamw_iso_ms = min(iso) if iso else None
 
     render = None if args.no_render else measure_render(model, device, rank, world, dist)
+    render_bmp = None if args.no_render else measure_render(model, device, rank, world, dist, bmp_set=True)
 
     if rank != 0:
         if world > 1:
@@ -469,6 +514,7 @@ def main():
     }
     if render is not None:
         line["render"] = render
+        line["render_bmp_set"] = render_bmp
     if world == 1 and not args.no_cpu_baseline:
         cpu_value, cpu_sec = cpu_train_glyphs_per_sec(steps=6, warmup=2)
         line["cpu_baseline"] = {
@@ -476,7 +522,7 @@ def main():
             "host_cpus": os.cpu_count(),
             "sample": f"6 train steps of the oracle port at the reference CPU batch {CPU_BATCH} "
                       f"({cpu_sec:.2f} s/step, 2 warm-up steps)"}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

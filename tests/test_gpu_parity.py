@@ -588,6 +588,50 @@ def test_full_size_properties(default_state):
 
 
 # ------------------------------------------------------------------------------------ errors
+def test_bmp_vocabulary_render_matches_oracle():
+    """BASELINE config 5 (no reference implementation: restated-oracle parity): the embedding
+    widened to the 65,536 code points of the Unicode BMP, sample i = [code point, 0, 0, ...];
+    uint8 sheets equal to the oracle's on >= 99.9 % of pixels and at the 0.5 threshold."""
+    cfg = orc.OracleConfig(vocab=65536, max_length=100, sheet_h=16, sheet_w=64)
+    state = orc.init_state(cfg, seed=7)
+    model = make_model(cfg, state).eval()
+    codes = torch.cat([torch.arange(0, 256), torch.arange(0x4E00, 0x4E00 + 128),
+                       torch.tensor([0xFFFF, 0xFFFE, 0x8000, 0x0100])])
+    tokens = torch.zeros((codes.numel(), cfg.max_length), dtype=torch.int64)
+    tokens[:, 0] = codes
+    q = model.render_u8(tokens.to(dev())).cpu().numpy()
+    z = orc.logits(state, tokens, cfg)
+    q_ref = orc.quantise_u8(torch.clamp(z, 0, 1).view(-1, cfg.sheet_h, cfg.sheet_w))
+    assert float(((q >= 128) == (q_ref >= 128)).mean()) >= 0.999
+    assert float((np.abs(q.astype(np.int32) - q_ref.astype(np.int32)) <= 1).mean()) >= 0.999
+    bad = torch.full((1, cfg.max_length), 65536, dtype=torch.int64)
+    model.render_u8(bad.to(dev()))
+    with pytest.raises(IndexError):
+        model.check_tokens_in_range()
+
+
+def test_render_pipeline_equals_direct_render_and_writes_bmps(golden_small, tmp_path):
+    """RenderPipeline (two device buffers, D2H on a copy stream) returns the same sheets as one
+    direct render; render_strings writes them as the files PIL would."""
+    from PIL import Image
+    from ai_font_renderer_b200.render import RenderPipeline, render_strings, strings_to_tokens
+    cfg = small_cfg(golden_small)
+    model = make_model(cfg, state_from_npz(golden_small, "state0")).eval()
+    strings = orc.dataset_strings(37)
+    tokens = strings_to_tokens(strings, cfg.max_length)
+    direct = model.render_u8(tokens.to(dev())).cpu()
+    pipe = RenderPipeline(model, dev(), batch_size=8)          # 5 batches, ragged last one
+    seen = []
+    host = pipe.render_to_host(tokens.pin_memory(), on_batch=lambda lo, hi, ev: seen.append((lo, hi)))
+    torch.cuda.synchronize()
+    assert host.is_pinned() and torch.equal(host, direct)
+    assert seen == [(0, 8), (8, 16), (16, 24), (24, 32), (32, 37)]
+    render_strings(model, strings, str(tmp_path), cfg.sheet_h, cfg.sheet_w, dev(), batch_size=16)
+    for i in (0, 15, 16, 36):
+        img = np.array(Image.open(tmp_path / f"string_{i}.bmp"))
+        assert np.array_equal(img, direct[i].numpy()), i
+
+
 def test_errors_are_loud():
     from ai_font_renderer_b200 import _lib
     from ai_font_renderer_b200.renderer import AttentionFontRenderer

@@ -56,6 +56,25 @@ def test_bmp_writer_is_byte_identical_to_pil_and_reader_round_trips(tmp_path):
     assert len(grey_bmp_bytes(np.zeros((80, 240), np.uint8))) == 20278
 
 
+def test_batched_bmp_writer_writes_the_same_files(tmp_path):
+    """render.write_bmp_files (one vectorised block + a thread pool) == one PIL save per sheet
+    (helpers.py:36-42,66-68), file names string_{idx}.bmp."""
+    from PIL import Image
+    from ai_font_renderer_b200.render import bmp_file_block, grey_bmp_bytes, write_bmp_files
+    rng = np.random.default_rng(3)
+    for h, w, n in ((80, 240, 20), (9, 13, 3)):
+        sheets = rng.integers(0, 256, size=(n, h, w), dtype=np.uint8)
+        block = bmp_file_block(sheets)
+        assert block.shape == (n, len(grey_bmp_bytes(sheets[0])))
+        d = tmp_path / f"{h}x{w}"
+        d.mkdir()
+        write_bmp_files(sheets, str(d), first_index=5)
+        for i in range(n):
+            ref = d / "ref.bmp"
+            Image.fromarray(sheets[i], mode="L").save(ref)
+            assert (d / f"string_{5 + i}.bmp").read_bytes() == ref.read_bytes()
+
+
 def test_reader_decodes_generate_font_ts_layout(tmp_path):
     """24-bit, BGR, top-down (negative height), rows padded to 4 bytes (generate_font.ts:6-62)."""
     from PIL import Image
