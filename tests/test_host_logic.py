@@ -75,6 +75,37 @@ def test_batched_bmp_writer_writes_the_same_files(tmp_path):
             assert (d / f"string_{5 + i}.bmp").read_bytes() == ref.read_bytes()
 
 
+def test_offline_dataset_generator_follows_generate_font_ts_conventions(tmp_path):
+    """fontgen (Pillow stand-in for generate_font.ts): LCG strings in data.txt, 1-based 24-bit
+    top-down BMPs that helpers.load_string_dataset reads, black ink on white in the rows the
+    wrapped lines occupy, multi-font sets with fonts.txt."""
+    import helpers
+    from ai_font_renderer_b200 import fontgen
+    from ai_font_renderer_b200.data import dataset_texts, read_bmp_grey
+    d = tmp_path / "train_input"
+    texts = fontgen.generate_dataset(str(d), 6, [None, None], quiet=True)
+    assert texts == dataset_texts(6)
+    assert (d / "data.txt").read_text().split("\n") == texts
+    assert (d / "fonts.txt").read_text().split() == ["0", "1", "0", "1", "0", "1"]
+    raw = (d / "1.bmp").read_bytes()
+    assert raw[:2] == b"BM" and int.from_bytes(raw[10:14], "little") == 54
+    assert int.from_bytes(raw[18:22], "little", signed=True) == 240
+    assert int.from_bytes(raw[22:26], "little", signed=True) == -80          # top-down
+    assert int.from_bytes(raw[28:30], "little") == 24 and len(raw) == 54 + 720 * 80
+    grey = read_bmp_grey(str(d / "1.bmp"))
+    font = fontgen.load_font(None)
+    n_lines = len(fontgen.wrap_text(font, texts[0], 240))
+    ink_rows = np.where((grey < 128).any(axis=1))[0]
+    assert grey.max() == 255 and grey.min() < 64
+    assert ink_rows.min() >= 0 and ink_rows.max() <= int(n_lines * 14.4) + 4   # baseline k at (k+1)*14.4
+    assert 0.005 < float((grey < 255).mean()) < 0.25
+    for line in fontgen.wrap_text(font, texts[3], 240):
+        assert font.getlength(line) <= 240 or " " not in line
+    tokens, targets = helpers.load_string_dataset(str(d), 6).tensors
+    assert targets.shape == (6, 80, 240) and targets.dtype == torch.uint8
+    assert tokens.shape[0] == 6 and int(tokens[0, 0]) == ord(texts[0][0])
+
+
 def test_reader_decodes_generate_font_ts_layout(tmp_path):
     """24-bit, BGR, top-down (negative height), rows padded to 4 bytes (generate_font.ts:6-62)."""
     from PIL import Image
