@@ -86,6 +86,9 @@ SIGNATURES = {
                                          C.POINTER(AfrDropout), C.c_double, _P, _P]),
     "afr_train_wgrad": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "afr_train_dgrad": (C.c_int, [_P, _P]),
+    "afr_train_dgrad_gemm": (C.c_int, [_P, _P]),
+    "afr_train_frontend_backward": (C.c_int, [_P, _P]),
+    "afr_set_coresident": (C.c_int, [_P, C.c_int]),
     "afr_train_step": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_int,
                                  C.POINTER(AfrDropout), C.c_double, _P, _P]),
     "afr_forward_train": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(AfrDropout),

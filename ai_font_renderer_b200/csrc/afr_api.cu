@@ -49,6 +49,7 @@ struct afr_ctx {
   float grad_scale = 0.f;
   bool fwd_done = false;
   bool frontend_done = false;        // afr_train_frontend ran, afr_train_loss still to come
+  bool coresident = false;           // afr_set_coresident
   long long launches = 0;
   std::string err;
 };
@@ -332,6 +333,12 @@ int afr_set_sm_limit(afr_ctx* c, int sms) {
   return AFR_OK;
 }
 
+int afr_set_coresident(afr_ctx* c, int on) {
+  if (!c) return AFR_ERR_INVALID;
+  c->coresident = on != 0;
+  return AFR_OK;
+}
+
 int afr_shadow_index(const afr_ctx* c) { return c ? c->shadow_cur : AFR_ERR_INVALID; }
 
 int afr_shadow_commit(afr_ctx* c) {
@@ -463,23 +470,34 @@ int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
   return AFR_OK;
 }
 
-int afr_train_dgrad(afr_ctx* c, void* stream) {
+int afr_train_dgrad_gemm(afr_ctx* c, void* stream) {
   if (!c) return AFR_ERR_INVALID;
-  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_dgrad before a training forward");
-  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_dgrad_gemm before a training forward");
   DeviceGuard guard(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // dfeat[B, K] = scale * dZ[B, P] W[P, K] : A = dZ (K-major over pixels), B = W (MN-major)
   GemmEpilogue ep{};
   ep.kind = kEpiF32; ep.out = c->dfeat; ep.ldo = c->K; ep.alpha = c->grad_scale;
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
+  ep.compact = c->coresident ? 1 : 0;
   const char* msg = nullptr;
-  const int bn = choose_bn(c->B, c->K, c->sms, "AFR_BN_DGRAD");
+  int bn = choose_bn(c->B, c->K, c->sms, "AFR_BN_DGRAD");
+  if (c->coresident && bn > 128) bn = 128;
   cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow_buf[c->shadow_fwd], c->K, true, c->B, c->K, c->P, bn,
                                    ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(dgrad)");
+  c->launches += 1;
+  return AFR_OK;
+}
+
+int afr_train_frontend_backward(afr_ctx* c, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_frontend_backward before a training forward");
+  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
   if (!c->state_valid)
     return fail(c, AFR_ERR_STATE, "front-end records of this batch were overwritten by another forward");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
                                        c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
@@ -487,8 +505,16 @@ int afr_train_dgrad(afr_ctx* c, void* stream) {
            "frontend_backward");
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce");
-  c->launches += 3;
+  c->launches += 2;
   return AFR_OK;
+}
+
+int afr_train_dgrad(afr_ctx* c, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  int rc = afr_train_dgrad_gemm(c, stream);
+  if (rc) return rc;
+  return afr_train_frontend_backward(c, stream);
 }
 
 int afr_train_step(afr_ctx* c, const int64_t* tokens, int64_t token_stride, int B, int S,
@@ -601,6 +627,8 @@ int afr_train_wgrad_adamw(afr_ctx* c, double lr, double beta1, double beta2, dou
   const char* msg = nullptr;
   int bn = env_int("AFR_WA_BN");            // tuning knobs (tools/fused_sweep.py)
   if (bn < 32 || bn > 256 || (bn % 32) != 0) bn = 256;
+  ep.compact = c->coresident ? 1 : 0;
+  if (c->coresident && bn > 128) bn = 128;
   ep.adam_sets = env_int("AFR_WA_SETS");
   ep.adam_sub = env_int("AFR_WA_SUB");
   ep.adam_stages = env_int("AFR_WA_STAGES");

@@ -45,15 +45,12 @@ bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const vo
 template <int EPI, bool A_MN, bool B_MN>
 cudaError_t launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_kernel<EPI, A_MN, B_MN>;
-  const int nsub = p.adam_sub;
-  const int smem_bytes = EPI == kEpiAdamW
-                             ? adam_smem_bytes(p.stages, p.b_stage_bytes, p.adam_sets, nsub)
-                             : kGemmSmemBytes;
-  const int threads = EPI == kEpiAdamW ? 64 + 128 * nsub : kGemmThreads;
+  const int smem_bytes = gemm_smem_bytes(p.stages, p.b_stage_bytes, p.epi_bytes, p.compact != 0);
+  const int threads = EPI == kEpiAdamW ? 64 + 128 * p.adam_sub : kGemmThreads;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         EPI == kEpiAdamW ? 232448 : kGemmSmemBytes);
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -96,6 +93,25 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
       ok &= encode_2d(&p.tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.out, M, N, epi.ldo, 32, 32);
     }
   }
+  // ---- shared / tensor memory footprint
+  // default: 4 x (16 + 32) KB operand ring, 32 KB of TMA-store slabs, all 512 TMEM columns.
+  // compact (co-resident): tile at most 128 wide, 2 stages of 16 + 16 KB, direct stores, 256 TMEM
+  // columns -- two such CTAs (this GEMM under the HBM-bound AdamW GEMM) share one SM.
+  p.compact = epi.compact ? 1 : 0;
+  p.stages = kStages;
+  p.b_stage_bytes = kBStageBytes;
+  p.epi_bytes = kEpiBytes;
+  p.tmem_cols = kTmemCols;
+  if (epi.compact) {
+    if (BN > 128) {
+      if (err_msg) *err_msg = "gemm: the co-resident footprint needs a tile at most 128 wide";
+      return cudaErrorInvalidValue;
+    }
+    p.stages = 2;
+    p.b_stage_bytes = b_mn ? ((BN + 63) / 64) * 8192 : BN * kBK * 2;
+    p.tmem_cols = 256;
+    if (epi.kind == kEpiF32) { use_tma_store = 0; p.epi_bytes = 0; }
+  }
   if (epi.kind == kEpiAdamW) {
     static const char* kBadAdam =
         "gemm: fused AdamW epilogue needs MN-major operands, M % 32 == 0, 16-byte aligned p / m / v / "
@@ -116,10 +132,13 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     p.adam_sub = epi.adam_sub >= 1 && epi.adam_sub <= kMaxAdamSub ? epi.adam_sub : kMaxAdamSub;
     p.adam_sets = epi.adam_sets >= 1 && epi.adam_sets <= kMaxAdamSets ? epi.adam_sets : 1;
     p.adam_prefetch = epi.adam_prefetch;
+    p.epi_bytes = 4 * p.adam_sub * p.adam_sets * kAdamSlabBytes;
     // deepest operand ring that still fits beside the slab sets
-    int stages = epi.adam_stages > 0 ? epi.adam_stages : kMaxStages;
+    int stages = epi.adam_stages > 0 ? epi.adam_stages : (epi.compact ? 2 : kMaxStages);
     if (stages > kMaxStages) stages = kMaxStages;
-    while (stages > 1 && adam_smem_bytes(stages, p.b_stage_bytes, p.adam_sets, p.adam_sub) > 232448) --stages;
+    while (stages > 1 &&
+           gemm_smem_bytes(stages, p.b_stage_bytes, p.epi_bytes, p.compact != 0) > kSmemOptinMax)
+      --stages;
     if (stages < 2) {
       if (err_msg) *err_msg = "gemm: fused AdamW epilogue: tile width / slab sets do not fit in shared memory";
       return cudaErrorInvalidValue;

@@ -49,10 +49,13 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxAdamSets = 4;
 constexpr int kMaxAdamSub = 2;                                   // epilogue warps per lane quadrant
 constexpr int kAdamMaxThreads = 64 + 128 * kMaxAdamSub;
-__host__ __device__ constexpr int adam_smem_bytes(int stages, int b_stage_bytes, int sets, int nsub) {
-  return stages * (kAStageBytes + b_stage_bytes) + 4 * nsub * sets * kAdamSlabBytes + kBarrierBytes +
-         1024;
+// dynamic shared memory of a launch: operand ring + epilogue region + barriers (+ 1 KB alignment
+// slack unless the co-resident footprint is requested)
+__host__ __device__ constexpr int gemm_smem_bytes(int stages, int b_stage_bytes, int epi_bytes,
+                                                  bool compact) {
+  return stages * (kAStageBytes + b_stage_bytes) + epi_bytes + kBarrierBytes + (compact ? 0 : 1024);
 }
+constexpr int kSmemOptinMax = 232448;                            // 227 KB per CTA on sm_100
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 512;                 // 2 accumulator buffers x 256 columns
 
@@ -86,24 +89,33 @@ struct GemmParams {
   CUtensorMap tm_p, tm_m, tm_v;
   AdamHyper hyper;
   float* adam_ptr[3];    // p, exp_avg, exp_avg_sq base pointers (L2 prefetch of the next tile)
-  int stages;            // operand ring depth
+  // shared / tensor memory footprint (set by the host, launch_gemm_bf16)
+  int stages;            // operand ring depth (2..kMaxStages)
   int b_stage_bytes;     // bytes of one B-operand stage
+  int epi_bytes;         // epilogue staging region (TMA-store slabs / AdamW load slabs; may be 0)
+  int tmem_cols;         // TMEM columns to allocate: 512, or 256 in the co-resident footprint
+  int compact;           // 1: no alignment slack in the dynamic shared memory (base must be 1 KB aligned)
   int adam_sets;         // slab sets per epilogue warp (threads = 64 + 128 * warps per quadrant)
   int adam_sub;          // epilogue warps per TMEM lane quadrant (1..kMaxAdamSub)
   int adam_prefetch;     // 1: bulk-prefetch the next tile's p/m/v rows into L2 as contiguous runs
 };
 
 template <int EPI, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(EPI == kEpiAdamW ? kAdamMaxThreads : kGemmThreads, 1)
+// (the AdamW instantiation is bounded as if it had 512 threads: that caps it at 128 registers, so
+// that its 320 threads and a 192-thread GEMM CTA fit the register file of one SM together)
+__global__ void __launch_bounds__(EPI == kEpiAdamW ? 512 : kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle atoms are 1024-byte aligned.
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int kStages = (EPI == kEpiAdamW) ? p.stages : afr::kStages;
-  const int kBStage = (EPI == kEpiAdamW) ? p.b_stage_bytes : kBStageBytes;
-  const int epi_region =
-      (EPI == kEpiAdamW) ? ((static_cast<int>(blockDim.x) - 64) >> 5) * p.adam_sets * kAdamSlabBytes : kEpiBytes;
+  // 128B swizzle atoms are 1024-byte aligned. The co-resident footprint has no room for
+  // alignment slack: the dynamic window of a kernel without static shared memory starts 1 KB
+  // aligned, which is checked instead of assumed.
+  if (p.compact && (ptx::smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* smem = p.compact ? smem_raw
+                            : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                         ~static_cast<uintptr_t>(1023));
+  const int kStages = p.stages;
+  const int kBStage = p.b_stage_bytes;
+  const int epi_region = p.epi_bytes;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kAStageBytes;
   uint8_t* smem_epi = smem_b + kStages * kBStage;
@@ -120,10 +132,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int BN = p.BN;
-  // TMEM accumulator buffers: 2 x 256 columns, or 4 x 128 when the tile is at most 128 wide (the
-  // MMA warp can then run three tiles ahead of the slowest epilogue warp instead of one)
-  const int n_acc = BN <= 128 ? 4 : 2;
-  const int acc_stride = kTmemCols / n_acc;
+  // TMEM accumulator buffers of 256 columns, or 128 when the tile is at most 128 wide: 2 or 4 of
+  // them in the full 512-column allocation, 2 x 128 in the co-resident footprint (256 columns, so
+  // that two kernels can share an SM's tensor memory)
+  const int acc_stride = BN <= 128 ? 128 : 256;
+  const int n_acc = p.tmem_cols / acc_stride;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tm_a);
@@ -146,7 +159,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_base_slot, kTmemCols);
+    ptx::tmem_alloc(tmem_base_slot, static_cast<uint32_t>(p.tmem_cols));
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -310,65 +323,65 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       }
       bool acc_ready = false;
       for (int c = sub; active && c < n_chunks; c += nsub) {
-        const int n = n0 + c * 32;
-        // p, m, v of this chunk: shared memory -> registers, then refill the slab set at once
+        // p, m, v of this chunk wait in slab set s; they are moved to registers and updated in
+        // two halves of 16 columns (48 + 16 live values per thread instead of 96 + 32), and the
+        // set is refilled as soon as the second half has been read
         const uint32_t sp = ptx::smem_u32(slabs + s * kAdamSlabBytes + lane * 128);
         ptx::mbar_wait(&ld_bar[s], s_phase);
-        float4 pv[8], mv[8], vv[8];
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int off = (ch ^ (lane & 7)) << 4;
-          pv[ch] = ptx::lds_f4(sp + off);
-          mv[ch] = ptx::lds_f4(sp + kEpiWarpBufBytes + off);
-          vv[ch] = ptx::lds_f4(sp + 2 * kEpiWarpBufBytes + off);
-        }
-        __syncwarp();                       // every lane's reads of the set are done
-        issue_next();
-        if (++s == sets) { s = 0; s_phase ^= 1u; }
         if (!acc_ready) {
           ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
           ptx::tc_fence_after();
           acc_ready = true;
         }
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>(acc * acc_stride + c * 32),
-                           r);
-        ptx::tmem_ld_wait();
-        if (c + nsub >= n_chunks) {         // this warp's last read of the accumulator buffer
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        uint32_t packed[16];
+        const long long e = m * p.ldo + n0 + c * 32;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          adamw_elem(pv[ch].x, __fmul_rn(__uint_as_float(r[4 * ch]), p.alpha), mv[ch].x, vv[ch].x, h);
-          adamw_elem(pv[ch].y, __fmul_rn(__uint_as_float(r[4 * ch + 1]), p.alpha), mv[ch].y, vv[ch].y, h);
-          adamw_elem(pv[ch].z, __fmul_rn(__uint_as_float(r[4 * ch + 2]), p.alpha), mv[ch].z, vv[ch].z, h);
-          adamw_elem(pv[ch].w, __fmul_rn(__uint_as_float(r[4 * ch + 3]), p.alpha), mv[ch].w, vv[ch].w, h);
-          const __nv_bfloat162 lo = __floats2bfloat162_rn(pv[ch].x, pv[ch].y);
-          const __nv_bfloat162 hi = __floats2bfloat162_rn(pv[ch].z, pv[ch].w);
-          packed[2 * ch] = *reinterpret_cast<const uint32_t*>(&lo);
-          packed[2 * ch + 1] = *reinterpret_cast<const uint32_t*>(&hi);
-        }
-        const long long e = m * p.ldo + n;
-        float* op = p.adam_ptr[0] + e;
-        float* om = p.adam_ptr[1] + e;
-        float* ov = p.adam_ptr[2] + e;
+        for (int half = 0; half < 2; ++half) {
+          float4 pv[4], mv[4], vv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          ptx::stg_256(op + 8 * k, pv[2 * k], pv[2 * k + 1]);
-          ptx::stg_256(om + 8 * k, mv[2 * k], mv[2 * k + 1]);
-          ptx::stg_256(ov + 8 * k, vv[2 * k], vv[2 * k + 1]);
+          for (int ch = 0; ch < 4; ++ch) {
+            const int off = ((half * 4 + ch) ^ (lane & 7)) << 4;
+            pv[ch] = ptx::lds_f4(sp + off);
+            mv[ch] = ptx::lds_f4(sp + kEpiWarpBufBytes + off);
+            vv[ch] = ptx::lds_f4(sp + 2 * kEpiWarpBufBytes + off);
+          }
+          if (half == 1) {
+            __syncwarp();                   // every lane's reads of the set are done
+            issue_next();
+            if (++s == sets) { s = 0; s_phase ^= 1u; }
+          }
+          uint32_t r[16];
+          ptx::tmem_ld_16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                              static_cast<uint32_t>(acc * acc_stride + c * 32 + half * 16),
+                          r);
+          ptx::tmem_ld_wait();
+          if (half == 1 && c + nsub >= n_chunks) {   // this warp's last read of the accumulator buffer
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          uint32_t packed[8];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            adamw_elem(pv[ch].x, __fmul_rn(__uint_as_float(r[4 * ch]), p.alpha), mv[ch].x, vv[ch].x, h);
+            adamw_elem(pv[ch].y, __fmul_rn(__uint_as_float(r[4 * ch + 1]), p.alpha), mv[ch].y, vv[ch].y, h);
+            adamw_elem(pv[ch].z, __fmul_rn(__uint_as_float(r[4 * ch + 2]), p.alpha), mv[ch].z, vv[ch].z, h);
+            adamw_elem(pv[ch].w, __fmul_rn(__uint_as_float(r[4 * ch + 3]), p.alpha), mv[ch].w, vv[ch].w, h);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(pv[ch].x, pv[ch].y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(pv[ch].z, pv[ch].w);
+            packed[2 * ch] = *reinterpret_cast<const uint32_t*>(&lo);
+            packed[2 * ch + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+          }
+          float* op = p.adam_ptr[0] + e + half * 16;
+          float* om = p.adam_ptr[1] + e + half * 16;
+          float* ov = p.adam_ptr[2] + e + half * 16;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            ptx::stg_256(op + 8 * k, pv[2 * k], pv[2 * k + 1]);
+            ptx::stg_256(om + 8 * k, mv[2 * k], mv[2 * k + 1]);
+            ptx::stg_256(ov + 8 * k, vv[2 * k], vv[2 * k + 1]);
+          }
+          // bf16 copy: one full 32-byte sector per half
+          ptx::stg_256(reinterpret_cast<__nv_bfloat16*>(p.out) + e + half * 16, packed);
         }
-        // bf16 copy: 64 bytes per row as two full 32-byte sectors
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + e;
-        const uint32_t w0[8] = {packed[0], packed[1], packed[2], packed[3],
-                                packed[4], packed[5], packed[6], packed[7]};
-        const uint32_t w1[8] = {packed[8],  packed[9],  packed[10], packed[11],
-                                packed[12], packed[13], packed[14], packed[15]};
-        ptx::stg_256(o, w0);
-        ptx::stg_256(o + 16, w1);
       }
       if (!acc_ready) {                     // no chunk of this tile is ours: just release the buffer
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -527,7 +540,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 

@@ -16,7 +16,8 @@ from .renderer import AttentionFontRenderer, _stream_ptr
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model: AttentionFontRenderer, lr: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, weight_decay: float = 1e-2, fuse_wgrad: bool = True):
+                 eps: float = 1e-8, weight_decay: float = 1e-2, fuse_wgrad: bool = True,
+                 overlap_dgrad: bool = False):
         if not isinstance(model, AttentionFontRenderer):
             raise TypeError("FusedAdamW is bound to an ai_font_renderer_b200.AttentionFontRenderer")
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
@@ -25,6 +26,11 @@ class FusedAdamW(torch.optim.Optimizer):
         # single GPU: training.backward_and_step folds the step of fc_output.weight into the
         # wgrad GEMM (wgrad_step_rows); False keeps the two-kernel form (gradient materialised)
         self.fuse_wgrad = fuse_wgrad
+        # ... and, optionally, runs the dgrad GEMM on a second stream under it with half-an-SM
+        # footprints (afr_set_coresident). Measured on B200: not a win -- two operand stages and
+        # two 128-column accumulators per kernel cost the AdamW GEMM more (0.72 -> 0.90 ms) than the
+        # overlap can return (dgrad is 0.22 ms) -- so it is off by default.
+        self.overlap_dgrad = overlap_dgrad
         super().__init__(model._ordered_params(), dict(lr=lr, betas=betas, eps=eps,
                                                        weight_decay=weight_decay))
 

@@ -438,6 +438,22 @@ class AttentionFontRenderer(nn.Module):
                 on_bucket(i, lo, hi)
         c.check(c.lib.afr_train_dgrad(c.handle, st))
 
+    def set_coresident(self, on: bool):
+        """Single GPU: the next wgrad+AdamW GEMM and dgrad GEMM launch with half-an-SM footprints
+        (afr_set_coresident) so that, enqueued on two streams, they share every SM."""
+        c = self._ctx
+        c.check(c.lib.afr_set_coresident(c.handle, 1 if on else 0))
+
+    def dgrad_gemm(self):
+        """d(features) = d(logits) W on the current stream (first half of afr_train_dgrad)."""
+        c = self._ctx
+        c.check(c.lib.afr_train_dgrad_gemm(c.handle, _stream_ptr(self.fc_output.weight.device)))
+
+    def frontend_backward(self):
+        """fc1 / LayerNorm / attention / embedding backward into the ten small gradients."""
+        c = self._ctx
+        c.check(c.lib.afr_train_frontend_backward(c.handle, _stream_ptr(self.fc_output.weight.device)))
+
     def fused_train_step(self, tokens, targets, **kw) -> torch.Tensor:
         """optimizer.zero_grad(); loss = mse(model(x), t); loss.backward()  (model.py:292-309)."""
         loss = self.fused_forward_loss(tokens, targets, **kw)

@@ -176,7 +176,8 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
 
     world == 1, optimizer.fuse_wgrad (default): the wgrad GEMM with the AdamW step of
     fc_output.weight in its epilogue (afr_train_wgrad_adamw; fc_output.weight.grad is not
-    materialised), dgrad, the front-end backward, the small-tensor AdamW -- one stream.
+    materialised) with, if optimizer.overlap_dgrad, the dgrad GEMM co-resident on every SM from a
+    second stream; then the front-end backward and the small-tensor AdamW.
     world == 1, fuse_wgrad off: wgrad, the AdamW sweep over fc_output.weight (right behind the
     gradient that is still partly in L2), dgrad, the front-end backward, the small-tensor AdamW.
     (Measured on B200, tools/overlap_probe.py: running the HBM-bound sweep on a second stream
@@ -210,6 +211,30 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
         # one kernel per bucket: wgrad GEMM whose epilogue applies AdamW to the fc_output.weight
         # tiles (the gradient never reaches HBM); 'adamw_*' marks bracket that kernel
         last = len(buckets) - 1
+        overlap = getattr(optimizer, "overlap_dgrad", False) and len(buckets) == 1
+        model.set_coresident(overlap)
+        if overlap:
+            # two streams, one CTA of each kernel on every SM: the HBM-bound wgrad+AdamW GEMM
+            # (tensor pipe ~17 % busy) on the compute stream, the tensor-bound dgrad GEMM under it
+            # on the side stream; both only read d(logits) and disjoint weight copies. The
+            # front-end backward needs whole SMs and d(features): it joins both.
+            side = model.side_stream()
+            side.wait_stream(main)
+            r0, r1 = buckets[0]
+            mark("adamw_begin")
+            optimizer.wgrad_step_rows(t_step, r0, r1)
+            mark("adamw_end")
+            with torch.cuda.stream(side):
+                model.dgrad_gemm()
+            optimizer.bias_grad_rows(r0, r1)
+            mark("wgrad")
+            main.wait_stream(side)
+            model.frontend_backward()
+            mark("dgrad")
+            optimizer.step_small(t_step)
+            optimizer.end_step()
+            mark("tail")
+            return
 
         def fused_bucket(r0, r1):
             mark("adamw_begin")

@@ -305,6 +305,8 @@ def main():
                          "NCCL); the persistent kernels use the rest")
     ap.add_argument("--no-fuse", action="store_true",
                     help="single GPU: keep wgrad and the AdamW sweep as two kernels (gradient materialised)")
+    ap.add_argument("--overlap-dgrad", action="store_true",
+                    help="single GPU: run the dgrad GEMM co-resident under the wgrad+AdamW GEMM (measured slower)")
     ap.add_argument("--no-render", action="store_true", help="skip the batched-render measurement")
     ap.add_argument("--adam-buckets", type=int, default=1,
                     help="single GPU: row buckets of the wgrad GEMM / AdamW sweep over fc_output.weight")
@@ -342,7 +344,8 @@ def main():
     torch.manual_seed(SEED)
     model = AttentionFontRenderer().to(device).train()
     fused = world == 1 and not args.no_fuse
-    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fused)
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fused,
+                     overlap_dgrad=fused and args.overlap_dgrad)
     if world > 1:
         from ai_font_renderer_b200.training import PeerLink
         if args.dp_mode == "peer":
@@ -384,13 +387,22 @@ def main():
     # package's HostBatchFeeder (copy stream, one batch ahead) and the step's loss is read back.
     feeder = HostBatchFeeder(tok_h, tgt_h, B, device)
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_ready, loss_copied = torch.cuda.Event(), torch.cuda.Event()
 
     def step_e2e(i):
         x_dev, t_dev = feeder.get(i)                             # H2D of batch i (and i+1 started)
         loss = model.fused_forward_loss(x_dev, t_dev, loss_count=count, sample_offset=rank * B)
+        # D2H read of THIS step's loss, every step: copied on the feeder's copy stream as soon as
+        # the forward has produced it, waited for on the host after the rest of the step has been
+        # enqueued -- the host blocks on the value (model.py:311 `.item()`), the GPU never idles
+        loss_ready.record()
+        with torch.cuda.stream(feeder.copy_stream):
+            feeder.copy_stream.wait_event(loss_ready)
+            loss_host.copy_(loss.view(1), non_blocking=True)
+            loss_copied.record()
         backward_and_step(model, opt, buckets, world)
         feeder.done(i)
-        loss_host.copy_(loss.view(1), non_blocking=False)        # D2H read of the step's loss (syncs)
+        loss_copied.synchronize()
         return float(loss_host[0])
 
     def barrier():

@@ -160,6 +160,17 @@ int afr_train_wgrad(afr_ctx* ctx, int row_begin, int row_end, void* stream);
 /* Rest of loss.backward(): d(features) through fc_output, then fc1 / LayerNorm / attention /
  * embedding backward into the ten small bound gradients (overwritten). */
 int afr_train_dgrad(afr_ctx* ctx, void* stream);
+/* afr_train_dgrad in its two parts, for callers that put them on different streams:
+ * afr_train_dgrad_gemm writes d(features) [B, 64*max_length] (library workspace) from
+ * d(logits) and the bf16 weights the forward read; afr_train_frontend_backward consumes it. */
+int afr_train_dgrad_gemm(afr_ctx* ctx, void* stream);
+int afr_train_frontend_backward(afr_ctx* ctx, void* stream);
+/* Co-resident launches (single GPU): with `on` != 0, afr_train_wgrad_adamw and
+ * afr_train_dgrad_gemm use a footprint of half an SM each (128-wide tiles, two operand stages,
+ * 256 tensor-memory columns, <= 128 registers), so that a caller who enqueues them on two streams
+ * gets one CTA of each per SM: the dgrad GEMM (tensor-bound) runs under the HBM-bound AdamW GEMM.
+ * Results are bit-identical to the default footprint. */
+int afr_set_coresident(afr_ctx* ctx, int on);
 /* Convenience: afr_train_forward_loss + afr_train_wgrad(0, H*W) + afr_train_dgrad. */
 int afr_train_step(afr_ctx* ctx, const int64_t* tokens, int64_t token_stride, int B, int S,
                    const void* targets, int target_kind, const afr_dropout* dropout,
