@@ -50,6 +50,7 @@ struct afr_ctx {
   bool fwd_done = false;
   bool frontend_done = false;        // afr_train_frontend ran, afr_train_loss still to come
   bool coresident = false;           // afr_set_coresident
+  bool cta2 = true;                  // forward / dgrad / wgrad GEMMs run as CTA pairs (AFR_CTA2=0: single CTAs)
   long long launches = 0;
   std::string err;
 };
@@ -111,15 +112,16 @@ int env_int(const char* name) {
   const char* s = std::getenv(name);
   return s ? std::atoi(s) : 0;
 }
-int choose_bn(int M, int N, int num_sms, const char* env_name) {
+int choose_bn(int M, int N, int num_sms, const char* env_name, bool cta2 = false) {
   const int forced = env_int(env_name);
   if (forced >= 32 && forced <= 256 && forced % 32 == 0) return forced;
   int best = 256;
   long long best_cost = -1;
+  const int units = cta2 ? num_sms / 2 : num_sms;   // CTAs, or CTA pairs working on 256-row tiles
   for (int bn = 256; bn >= 128; bn -= 32) {
-    const long long tiles = gemm_num_tiles(M, N, bn);
-    const long long waves = (tiles + num_sms - 1) / num_sms;
-    const long long cost = waves * (128 + bn);
+    const long long tiles = gemm_num_tiles(M, N, bn, cta2);
+    const long long waves = (tiles + units - 1) / units;
+    const long long cost = waves * ((cta2 ? 64 : 128) + bn);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   if (N < best) best = ((N + 31) / 32) * 32;
@@ -220,6 +222,7 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
   c->sms = c->num_sms;
   c->K = cfg->max_length * cfg->hidden;
   c->P = static_cast<int>(P);
+  { const char* e2 = std::getenv("AFR_CTA2"); c->cta2 = !(e2 && std::atoi(e2) == 0); }
   c->lay.init(cfg->max_length, cfg->vocab);
   c->fsl.init(cfg->max_length);
   if (cfg->training &&
@@ -371,7 +374,8 @@ int afr_forward_eval(afr_ctx* c, const int64_t* tokens, int64_t token_stride, in
   else return fail(c, AFR_ERR_INVALID, "unknown out_kind");
   if (env_int("AFR_NO_TMA_STORE")) ep.use_tma_store = 0;
   const char* msg = nullptr;
-  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
+  ep.cta2 = c->cta2;
+  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD", c->cta2);
   cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
                                    ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
@@ -415,10 +419,11 @@ int afr_train_loss(afr_ctx* c, const void* targets, int target_kind, double loss
   c->shadow_fwd = c->shadow_cur;
   c->grad_scale = static_cast<float>(2.0 / loss_count);  // d/dy of mean((y-t)^2)
   const int B = c->B;
-  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
-  const int tiles = gemm_num_tiles(B, c->P, bn);
+  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD", c->cta2);
+  const int tiles = gemm_num_tiles(B, c->P, bn, c->cta2) * (c->cta2 ? 2 : 1);   // 128-row blocks
   if ((rc = ensure_loss_partials(c, tiles * 4))) return rc;
   GemmEpilogue ep{};
+  ep.cta2 = c->cta2;
   ep.kind = kEpiLoss; ep.out = c->dz; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
   ep.target = targets; ep.target_is_f32 = target_kind == AFR_TARGET_F32;
   ep.loss_partials = c->loss_partials;
@@ -458,7 +463,8 @@ int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
   ep.out = c->grads.wout + static_cast<long long>(row_begin) * c->K;
   ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  const int bn = choose_bn(rows, c->K, c->sms, "AFR_BN_WGRAD");
+  ep.cta2 = c->cta2;
+  const int bn = choose_bn(rows, c->K, c->sms, "AFR_BN_WGRAD", c->cta2);
   cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
                                    c->B, bn, ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(wgrad)");
@@ -481,7 +487,8 @@ int afr_train_dgrad_gemm(afr_ctx* c, void* stream) {
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   ep.compact = c->coresident ? 1 : 0;
   const char* msg = nullptr;
-  int bn = choose_bn(c->B, c->K, c->sms, "AFR_BN_DGRAD");
+  ep.cta2 = c->cta2;
+  int bn = choose_bn(c->B, c->K, c->sms, "AFR_BN_DGRAD", c->cta2 && !c->coresident);
   if (c->coresident && bn > 128) bn = 128;
   cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow_buf[c->shadow_fwd], c->K, true, c->B, c->K, c->P, bn,
                                    ep, c->sms, st, nullptr, &msg);
@@ -551,7 +558,8 @@ int afr_forward_train(afr_ctx* c, const int64_t* tokens, int64_t token_stride, i
   ep.kind = kEpiF32; ep.out = c->logits; ep.ldo = c->P; ep.bias = c->params.bout; ep.alpha = 1.f;
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
+  ep.cta2 = c->cta2;
+  const int bn = choose_bn(B, c->P, c->sms, "AFR_BN_FWD", c->cta2);
   cudaError_t e = launch_gemm_bf16(c->feats, c->K, false, c->wshadow_buf[c->shadow_cur], c->K, false, B, c->P, c->K, bn,
                                    ep, c->sms, st, nullptr, &msg);
   if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(forward)");
@@ -628,6 +636,9 @@ int afr_train_wgrad_adamw(afr_ctx* c, double lr, double beta1, double beta2, dou
   int bn = env_int("AFR_WA_BN");            // tuning knobs (tools/fused_sweep.py)
   if (bn < 32 || bn > 256 || (bn % 32) != 0) bn = 256;
   ep.compact = c->coresident ? 1 : 0;
+  // the AdamW GEMM is HBM-bound and keeps single CTAs (8 epilogue warps + 2 x 48 KB ring measured
+  // faster than pairs with a 4 x 32 KB ring: 0.73 vs 0.79 ms); AFR_WA_CTA2=1 to compare
+  ep.cta2 = c->cta2 && env_int("AFR_WA_CTA2") != 0;
   if (c->coresident && bn > 128) bn = 128;
   ep.adam_sets = env_int("AFR_WA_SETS");
   ep.adam_sub = env_int("AFR_WA_SUB");
@@ -770,9 +781,9 @@ int afr_workspace_copy(afr_ctx* c, int which, void* dst, size_t bytes, void* str
 
 int afr_gemm_tiles(afr_ctx* c, int B, int* out) {
   if (!c || !out || B < 1) return AFR_ERR_INVALID;
-  out[0] = choose_bn(B, c->P, c->sms, "AFR_BN_FWD");
-  out[1] = choose_bn(B, c->K, c->sms, "AFR_BN_DGRAD");
-  out[2] = choose_bn(c->P, c->K, c->sms, "AFR_BN_WGRAD");
+  out[0] = choose_bn(B, c->P, c->sms, "AFR_BN_FWD", c->cta2);
+  out[1] = choose_bn(B, c->K, c->sms, "AFR_BN_DGRAD", c->cta2);
+  out[2] = choose_bn(c->P, c->K, c->sms, "AFR_BN_WGRAD", c->cta2);
   return AFR_OK;
 }
 
@@ -848,7 +859,9 @@ int afr_gemm_bf16(int device, const void* A, int64_t lda, int a_mn, const void* 
   if (major != 10) return fail(nullptr, AFR_ERR_UNSUPPORTED, "needs an sm_100 device");
   DeviceGuard guard(device);
   GemmEpilogue ep{};
-  ep.kind = kEpiF32; ep.out = D; ep.ldo = ldd; ep.alpha = alpha; ep.use_tma_store = use_tma_store;
+  ep.kind = kEpiF32; ep.out = D; ep.ldo = ldd; ep.alpha = alpha;
+  ep.use_tma_store = use_tma_store & 1;
+  ep.cta2 = (use_tma_store & 2) ? 1 : 0;
   const char* msg = nullptr;
   cudaError_t e = launch_gemm_bf16(static_cast<const __nv_bfloat16*>(A), lda, a_mn != 0,
                                    static_cast<const __nv_bfloat16*>(B), ldb, b_mn != 0, M, N, K,

@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map encoding, tile-shape bookkeeping, launch.
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "afr_gemm.cuh"
@@ -42,9 +43,9 @@ bool encode_2d(CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, const vo
   return r == CUDA_SUCCESS;
 }
 
-template <int EPI, bool A_MN, bool B_MN>
-cudaError_t launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_kernel<EPI, A_MN, B_MN>;
+template <int EPI, bool A_MN, bool B_MN, bool CTA2>
+cudaError_t launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_kernel<EPI, A_MN, B_MN, CTA2>;
   const int smem_bytes = gemm_smem_bytes(p.stages, p.b_stage_bytes, p.epi_bytes, p.compact != 0);
   const int threads = EPI == kEpiAdamW ? 64 + 128 * p.adam_sub : kGemmThreads;
   static bool attr_set = false;  // per instantiation
@@ -54,13 +55,36 @@ cudaError_t launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, threads, smem_bytes, stream>>>(p);
-  return cudaGetLastError();
+  if constexpr (!CTA2) {
+    kern<<<grid, threads, smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+  }
+}
+
+template <int EPI, bool A_MN, bool B_MN>
+cudaError_t launch_one(const GemmParams& p, int grid, cudaStream_t stream) {
+  if (p.cta2) return launch_impl<EPI, A_MN, B_MN, true>(p, grid, stream);
+  return launch_impl<EPI, A_MN, B_MN, false>(p, grid, stream);
 }
 
 }  // namespace
 
-int gemm_num_tiles(int M, int N, int BN) { return ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN); }
+int gemm_num_tiles(int M, int N, int BN, bool cta2) {
+  const int tile_m = cta2 ? 2 * kBM : kBM;
+  return ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+}
 
 cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
                              const __nv_bfloat16* B, long long ldb, bool b_mn, int M, int N, int K,
@@ -81,9 +105,13 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
   }
   GemmParams p{};
   bool ok = true;
+  // CTA pairs: 256 x BN tiles, each CTA loads half of the B tile (box of BN / 2 rows)
+  const bool cta2 = epi.cta2 != 0 && !epi.compact && num_sms >= 2;
+  p.cta2 = cta2 ? 1 : 0;
+  const int kctas = cta2 ? 2 : 1;
   if (!a_mn) ok &= encode_2d(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kBK, kBM);
   else       ok &= encode_2d(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, 64, kBK);
-  if (!b_mn) ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, kBK, BN);
+  if (!b_mn) ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, kBK, BN / kctas);
   else       ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, 64, kBK);
   int use_tma_store = epi.use_tma_store;
   if (epi.kind == kEpiF32 && use_tma_store) {
@@ -102,6 +130,13 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
   p.b_stage_bytes = kBStageBytes;
   p.epi_bytes = kEpiBytes;
   p.tmem_cols = kTmemCols;
+  if (cta2) {
+    // half a B tile per CTA: the ring gets as deep as shared memory allows (6 stages of 32 KB at BN = 256)
+    p.b_stage_bytes = b_mn ? ((BN / 2 + 63) / 64) * 8192 : (BN / 2) * kBK * 2;
+    int stages = kMaxStages;
+    while (stages > 2 && gemm_smem_bytes(stages, p.b_stage_bytes, p.epi_bytes, false) > kSmemOptinMax) --stages;
+    p.stages = stages;
+  }
   if (epi.compact) {
     if (BN > 128) {
       if (err_msg) *err_msg = "gemm: the co-resident footprint needs a tile at most 128 wide";
@@ -128,7 +163,7 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     ok &= encode_2d(&p.tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.adam_v, M, N, epi.ldo, 32, 32);
     p.hyper = epi.hyper;
     p.adam_ptr[0] = epi.adam_p; p.adam_ptr[1] = epi.adam_m; p.adam_ptr[2] = epi.adam_v;
-    p.b_stage_bytes = ((BN + 63) / 64) * 8192;
+    p.b_stage_bytes = ((BN / kctas + 63) / 64) * 8192;
     p.adam_sub = epi.adam_sub >= 1 && epi.adam_sub <= kMaxAdamSub ? epi.adam_sub : kMaxAdamSub;
     p.adam_sets = epi.adam_sets >= 1 && epi.adam_sets <= kMaxAdamSets ? epi.adam_sets : 1;
     p.adam_prefetch = epi.adam_prefetch;
@@ -150,15 +185,16 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     return cudaErrorInvalidValue;
   }
   p.M = M; p.N = N; p.K = K; p.BN = BN;
-  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_m_tiles = (M + kBM * kctas - 1) / (kBM * kctas);
   p.num_n_tiles = (N + BN - 1) / BN;
-  p.idesc = ptx::make_idesc_bf16(kBM, BN, a_mn, b_mn);
+  p.idesc = ptx::make_idesc_bf16(kBM * kctas, BN, a_mn, b_mn);
   p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.alpha = epi.alpha;
   p.clamp01 = epi.clamp01; p.use_tma_store = use_tma_store;
   p.target = epi.target; p.target_is_f32 = epi.target_is_f32; p.loss_partials = epi.loss_partials;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   if (num_tiles_out) *num_tiles_out = num_tiles;
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  int grid = num_tiles * kctas < num_sms ? num_tiles * kctas : num_sms;
+  if (cta2) grid &= ~1;
 
   if (epi.kind == kEpiF32) {
     if (!a_mn && !b_mn) return launch_one<kEpiF32, false, false>(p, grid, stream);

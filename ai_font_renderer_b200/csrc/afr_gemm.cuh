@@ -94,13 +94,22 @@ struct GemmParams {
   int b_stage_bytes;     // bytes of one B-operand stage
   int epi_bytes;         // epilogue staging region (TMA-store slabs / AdamW load slabs; may be 0)
   int tmem_cols;         // TMEM columns to allocate: 512, or 256 in the co-resident footprint
+  int cta2;              // 1: launched as CTA pairs (template CTA2)
   int compact;           // 1: no alignment slack in the dynamic shared memory (base must be 1 KB aligned)
   int adam_sets;         // slab sets per epilogue warp (threads = 64 + 128 * warps per quadrant)
   int adam_sub;          // epilogue warps per TMEM lane quadrant (1..kMaxAdamSub)
   int adam_prefetch;     // 1: bulk-prefetch the next tile's p/m/v rows into L2 as contiguous runs
 };
 
-template <int EPI, bool A_MN, bool B_MN>
+// CTA2: the kernel runs as clusters of two CTAs (one TPC) that execute 256-row MMAs together
+// (tcgen05 cta_group::2). A tile is then 256 x BN per pair; CTA rank r loads rows [128 r, 128 r +
+// 128) of A and columns [r BN/2, (r+1) BN/2) of B, so a stage costs 16 KB + BN/2 x 128 B of shared
+// memory per CTA instead of 16 KB + BN x 128 B for the same tensor work per SM: a third less
+// L2 -> shared-memory traffic and room for a deeper ring. Only the leader (rank 0) issues MMAs; its
+// full barriers count the bytes of both CTAs' TMA loads, its commits arrive on the empty /
+// accumulator-full barriers of both CTAs, and both CTAs' epilogue threads arrive on the leader's
+// accumulator-empty barriers. Each CTA's epilogue drains its own 128 TMEM lanes.
+template <int EPI, bool A_MN, bool B_MN, bool CTA2>
 // (the AdamW instantiation is bounded as if it had 512 threads: that caps it at 128 registers, so
 // that its 320 threads and a 192-thread GEMM CTA fit the register file of one SM together)
 __global__ void __launch_bounds__(EPI == kEpiAdamW ? 512 : kGemmThreads, 1)
@@ -129,6 +138,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int kCtas = CTA2 ? 2 : 1;
+  const int cta_rank = CTA2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int first_tile = static_cast<int>(blockIdx.x) / kCtas;     // pairs walk the tile list
+  const int tile_step = static_cast<int>(gridDim.x) / kCtas;
+  const int row_base = cta_rank * kBM;                             // this CTA's rows inside a tile
+  constexpr int kTileM = kBM * kCtas;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = (p.K + kBK - 1) / kBK;
   const int BN = p.BN;
@@ -148,7 +163,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], blockDim.x - 64);   // every epilogue thread
+      ptx::mbar_init(&tmem_empty_bar[a], (blockDim.x - 64) * kCtas);   // every epilogue thread (of the pair)
     }
     if (EPI == kEpiAdamW) {
       ptx::prefetch_tensormap(&p.tm_p);
@@ -159,52 +174,72 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_base_slot, static_cast<uint32_t>(p.tmem_cols));
-    ptx::tmem_relinquish();
+    if constexpr (CTA2) {
+      ptx::tmem_alloc_pair(tmem_base_slot, static_cast<uint32_t>(p.tmem_cols));
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_base_slot, static_cast<uint32_t>(p.tmem_cols));
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync();   // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  // an epilogue thread is done with accumulator buffer `a`: tell the (leader's) MMA warp
+  auto release_acc = [&](int a) {
+    if constexpr (CTA2) ptx::mbar_arrive_cluster(ptx::map_to_cta(&tmem_empty_bar[a], 0));
+    else ptx::mbar_arrive(&tmem_empty_bar[a]);
+  };
+
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp, one lane issues)
+    {
+      const bool leader = ptx::elect_one();
+      const int bn_cta = BN / kCtas;        // B columns this CTA loads
       const uint32_t a_bytes = kAStageBytes;
-      const uint32_t b_boxes = B_MN ? static_cast<uint32_t>((BN + 63) / 64) : 0u;
-      const uint32_t b_bytes = B_MN ? b_boxes * 8192u : static_cast<uint32_t>(BN) * kBK * 2u;
+      const uint32_t b_boxes = B_MN ? static_cast<uint32_t>((bn_cta + 63) / 64) : 0u;
+      const uint32_t b_bytes = B_MN ? b_boxes * 8192u : static_cast<uint32_t>(bn_cta) * kBK * 2u;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.num_m_tiles) * kBM;
-        const int n0 = (tile / p.num_m_tiles) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile % p.num_m_tiles) * kTileM + row_base;
+        const int n0 = (tile / p.num_m_tiles) * BN + cta_rank * bn_cta;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
           uint8_t* sa = smem_a + stage * kAStageBytes;
           uint8_t* sb = smem_b + stage * kBStage;
           // the fused-AdamW kernel streams 3 GB through L2 next to its operands: keep them
           constexpr uint64_t pol = EPI == kEpiAdamW ? ptx::kL2EvictLast : ptx::kL2EvictNormal;
-          if constexpr (!A_MN) {
-            ptx::tma_load_2d_hint(&p.tm_a, &full_bar[stage], sa, kb * kBK, m0, pol);
-          } else {
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
+            if constexpr (CTA2) ptx::tma_load_2d_pair(tm, ptx::map_to_cta(&full_bar[stage], 0), dst, c0, c1, pol);
+            else ptx::tma_load_2d_hint(tm, &full_bar[stage], dst, c0, c1, pol);
+          };
+          if (leader) {
+            // the leader CTA's barrier counts the bytes of both CTAs
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (a_bytes + b_bytes) * kCtas);
+            if constexpr (!A_MN) {
+              load(&p.tm_a, sa, kb * kBK, m0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < kBM / 64; ++i)
-              ptx::tma_load_2d_hint(&p.tm_a, &full_bar[stage], sa + i * 8192, m0 + i * 64, kb * kBK, pol);
-          }
-          if constexpr (!B_MN) {
-            ptx::tma_load_2d_hint(&p.tm_b, &full_bar[stage], sb, kb * kBK, n0, pol);
-          } else {
-            for (uint32_t i = 0; i < b_boxes; ++i)
-              ptx::tma_load_2d_hint(&p.tm_b, &full_bar[stage], sb + i * 8192, n0 + i * 64, kb * kBK, pol);
+              for (int i = 0; i < kBM / 64; ++i) load(&p.tm_a, sa + i * 8192, m0 + i * 64, kb * kBK);
+            }
+            if constexpr (!B_MN) {
+              load(&p.tm_b, sb, kb * kBK, n0);
+            } else {
+              for (uint32_t i = 0; i < b_boxes; ++i) load(&p.tm_b, sb + i * 8192, n0 + i * 64, kb * kBK);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one lane issues)
+    if (cta_rank == 0) {
+      const bool leader = ptx::elect_one();
       // K-major  : 8-row groups 1024 B apart (SBO); 16 K-elements = 32 B inside the swizzle row.
       // MN-major : 64-element MN chunks 8192 B apart (LBO); 8-row K groups 1024 B apart (SBO);
       //            16 K-rows = 2048 B.
@@ -214,7 +249,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_stride);
@@ -225,14 +260,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               ptx::smem_u32(smem_a + stage * kAStageBytes), a_lbo, 1024u);
           const uint64_t db = ptx::make_smem_desc_sw128(
               ptx::smem_u32(smem_b + stage * kBStage), b_lbo, 1024u);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            ptx::umma_bf16(d_tmem, da + static_cast<uint64_t>(k * a_kstep),
-                           db + static_cast<uint64_t>(k * b_kstep), p.idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              if constexpr (CTA2)
+                ptx::umma_bf16_pair(d_tmem, da + static_cast<uint64_t>(k * a_kstep),
+                                    db + static_cast<uint64_t>(k * b_kstep), p.idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+              else
+                ptx::umma_bf16(d_tmem, da + static_cast<uint64_t>(k * a_kstep),
+                               db + static_cast<uint64_t>(k * b_kstep), p.idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+            }
+            // smem slot reusable (in both CTAs) once these MMAs retire
+            if constexpr (CTA2) {
+              ptx::umma_commit_pair(&empty_bar[stage]);
+              if (kb == num_kb - 1) ptx::umma_commit_pair(&tmem_full_bar[acc]);
+            } else {
+              ptx::umma_commit(&empty_bar[stage]);
+              if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
+            }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
@@ -260,18 +308,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     };
     // next tile >= t in which this warp has work: its 32 rows inside M, a chunk index == sub
     auto next_active = [&](int t) {
-      while (t < num_tiles && ((t % p.num_m_tiles) * kBM + q * 32 >= p.M || chunks_of(t) <= sub))
-        t += gridDim.x;
+      while (t < num_tiles &&
+             ((t % p.num_m_tiles) * kTileM + row_base + q * 32 >= p.M || chunks_of(t) <= sub))
+        t += tile_step;
       return t;
     };
     // loader cursor (lane 0 issues; every lane tracks it)
-    int lt = next_active(blockIdx.x), lc = sub, s_issue = 0;
+    int lt = next_active(first_tile), lc = sub, s_issue = 0;
     int l_chunks = 0, l_col0 = 0, l_row = 0;
     auto load_tile_coords = [&]() {
       if (lt >= num_tiles) return;
       l_chunks = chunks_of(lt);
       l_col0 = (lt / p.num_m_tiles) * BN;
-      l_row = (lt % p.num_m_tiles) * kBM + q * 32;
+      l_row = (lt % p.num_m_tiles) * kTileM + row_base + q * 32;
     };
     load_tile_coords();
     auto issue_next = [&]() {
@@ -297,24 +346,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       }
       if (++s_issue == sets) s_issue = 0;
       lc += nsub;
-      if (lc >= l_chunks) { lc = sub; lt = next_active(lt + gridDim.x); load_tile_coords(); }
+      if (lc >= l_chunks) { lc = sub; lt = next_active(lt + tile_step); load_tile_coords(); }
     };
     for (int i = 0; i < sets; ++i) issue_next();
     int acc = 0;
     uint32_t acc_phase = 0;
     int s = 0;                              // slab set of the chunk being consumed
     uint32_t s_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.num_m_tiles) * kBM;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile % p.num_m_tiles) * kTileM + row_base;
       const int n0 = (tile / p.num_m_tiles) * BN;
       const long long m = m0 + q * 32 + lane;
       const int n_chunks = chunks_of(tile);
       const bool active = m0 + q * 32 < p.M && n_chunks > sub;
       if (active && p.adam_prefetch == 1 && sub == 0) {
         // the next tile's rows as contiguous runs -> L2; one row per lane
-        const int nt = next_active(tile + gridDim.x);
+        const int nt = next_active(tile + tile_step);
         if (nt < num_tiles) {
-          const long long row = (nt % p.num_m_tiles) * kBM + q * 32 + lane;
+          const long long row = (nt % p.num_m_tiles) * kTileM + row_base + q * 32 + lane;
           const long long e = row * p.ldo + (nt / p.num_m_tiles) * BN;
           const uint32_t bytes = static_cast<uint32_t>(chunks_of(nt)) * 128u;
 #pragma unroll
@@ -345,7 +394,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             vv[ch] = ptx::lds_f4(sp + 2 * kEpiWarpBufBytes + off);
           }
           if (half == 1) {
-            __syncwarp();                   // every lane's reads of the set are done
+            // the refill is an async-proxy write into memory this warp has just read through the
+            // generic proxy: every lane's reads must have been performed (not merely issued)
+            // before the TMA load is launched -- proxy fence per lane, then the warp barrier
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
             issue_next();
             if (++s == sets) { s = 0; s_phase ^= 1u; }
           }
@@ -356,7 +409,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           ptx::tmem_ld_wait();
           if (half == 1 && c + nsub >= n_chunks) {   // this warp's last read of the accumulator buffer
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tmem_empty_bar[acc]);
+            release_acc(acc);
           }
           uint32_t packed[8];
 #pragma unroll
@@ -387,7 +440,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
         ptx::tc_fence_after();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        release_acc(acc);
       }
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
     }
@@ -399,8 +452,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     int store_buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.num_m_tiles) * kBM;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile % p.num_m_tiles) * kTileM + row_base;
       const int n0 = (tile / p.num_m_tiles) * BN;
       const int m = m0 + row_in_tile;
       const bool row_ok = m < p.M;
@@ -419,7 +472,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (c == n_chunks - 1 || n + 32 >= p.N) {
           // last read of this accumulator buffer: hand it back to the MMA warp early
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          release_acc(acc);
         }
         float v[32];
 #pragma unroll
@@ -529,7 +582,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
           loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
-        if (lane == 0) p.loss_partials[tile * 4 + q] = loss_acc;
+        if (lane == 0) p.loss_partials[(tile * kCtas + cta_rank) * 4 + q] = loss_acc;
       }
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
     }
@@ -537,10 +590,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) ptx::cluster_sync();   // nobody signals a CTA that has exited
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if constexpr (CTA2) ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 

@@ -258,6 +258,9 @@ int afr_debug_div_sqrt(const float* a, const float* b, float* q, float* s, float
 
 /* Diagnostic: D[M,N] (fp32, ld = ldd) = alpha * A * B^T with bf16 operands on the tcgen05 path.
  * a_mn_major / b_mn_major: operand stored [K, M] resp. [K, N] row-major instead of [M, K] / [N, K].
+ * use_tma_store is a flag word: bit 0 = fp32 output through TMA stores, bit 1 = run as CTA pairs
+ * (tcgen05 cta_group::2, 256-row tiles: what the forward / dgrad / wgrad / render GEMMs use unless
+ * AFR_CTA2=0).
  * Exists so the tensor-core kernel can be tested against a plain matmul in isolation. */
 int afr_gemm_bf16(int device, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                   int b_mn_major, float* D, int64_t ldd, int M, int N, int K, int tile_n, float alpha,

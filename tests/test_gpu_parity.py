@@ -68,8 +68,9 @@ def assert_grads_close(got, want, tol_big=BF16_TOL, tol_small=BF16_TOL, label=""
 # ------------------------------------------------------------------------------------ raw GEMM
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("shape,bn", [((256, 512, 256), 256), ((200, 320, 200), 128),
-                                      ((1, 256, 640), 224), ((304, 1280, 304), 224)])
-@pytest.mark.parametrize("tma_store", [0, 1])
+                                      ((1, 256, 640), 224), ((304, 1280, 304), 224),
+                                      ((1024, 2048, 1088), 192)])
+@pytest.mark.parametrize("tma_store", [0, 1, 2, 3])      # bit 0: TMA stores, bit 1: CTA pairs (cta_group::2)
 def test_tcgen05_gemm_matches_fp32_matmul(a_mn, b_mn, shape, bn, tma_store):
     from ai_font_renderer_b200 import _lib
     lib = _lib.load()
@@ -331,7 +332,7 @@ def _two_kernel_vs_fused(cfg, state, tokens, targets, steps, buckets_fused):
     from ai_font_renderer_b200.training import backward_and_step, row_buckets
     P = cfg.sheet_h * cfg.sheet_w
     out = []
-    for fuse, nb in ((False, 1), (True, buckets_fused)):
+    for fuse, nb in ((False, 1), (True, buckets_fused), (True, buckets_fused)):
         model = make_model(cfg, state).train()
         model.dropout_seed, model.dropout_step = 4242, 0
         opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fuse)
@@ -352,8 +353,9 @@ def _two_kernel_vs_fused(cfg, state, tokens, targets, steps, buckets_fused):
 def _assert_fused_identical(two, fused):
     assert two["loss"] == fused["loss"]
     assert two["step"] == fused["step"]
-    for k in orc.STATE_KEYS:
-        assert torch.equal(two["state"][k], fused["state"][k]), k
+    differ = {k: float((two["state"][k] - fused["state"][k]).abs().max()) for k in orc.STATE_KEYS
+              if not torch.equal(two["state"][k], fused["state"][k])}
+    assert not differ, f"parameters differ (max abs): {differ}"
     assert torch.equal(two["m"], fused["m"])
     assert torch.equal(two["v"], fused["v"])
     assert torch.equal(two["shadow"], fused["shadow"])
@@ -370,9 +372,10 @@ def test_small_wgrad_adamw_epilogue_is_bit_identical_to_two_kernels(golden_small
     assert cfg.sheet_h * cfg.sheet_w == 256
     tokens = torch.from_numpy(golden_small["tokens"]).to(dev())
     targets = torch.from_numpy(golden_small["targets_u8"]).to(dev())
-    two, fused = _two_kernel_vs_fused(cfg, state_from_npz(golden_small, "state0"), tokens, targets,
-                                      3, buckets)
+    two, fused, again = _two_kernel_vs_fused(cfg, state_from_npz(golden_small, "state0"), tokens, targets,
+                                             3, buckets)
     _assert_fused_identical(two, fused)
+    _assert_fused_identical(two, again)
 
 
 @pytest.mark.parametrize("B", [192, 1024])
@@ -383,8 +386,9 @@ def test_default_wgrad_adamw_epilogue_is_bit_identical_to_two_kernels(default_st
     strings = orc.dataset_strings(B)
     tokens = orc.encode_strings(strings, cfg.max_length).to(dev())
     targets = torch.from_numpy(orc.synthetic_targets_u8(strings, cfg)).to(dev())
-    two, fused = _two_kernel_vs_fused(cfg, default_state, tokens, targets, 2, 1)
+    two, fused, again = _two_kernel_vs_fused(cfg, default_state, tokens, targets, 3, 1)
     _assert_fused_identical(two, fused)
+    _assert_fused_identical(two, again)      # and run-to-run: the slab refill must not race the reads
 
 
 def test_adamw_branch_free_div_sqrt_are_ieee_round_to_nearest():
@@ -630,6 +634,36 @@ def test_render_pipeline_equals_direct_render_and_writes_bmps(golden_small, tmp_
     for i in (0, 15, 16, 36):
         img = np.array(Image.open(tmp_path / f"string_{i}.bmp"))
         assert np.array_equal(img, direct[i].numpy()), i
+
+
+def test_scaled_64x64_sheet_config_matches_oracle():
+    """BASELINE config 4 shape (64x64 sheets, 64-char strings; the reference-width net -- the
+    widened embedding / heads of that config are not built): eval logits, loss and all gradients
+    against the restated oracle, then one fused optimizer step."""
+    from ai_font_renderer_b200.optim import FusedAdamW
+    from ai_font_renderer_b200.training import backward_and_step, row_buckets
+    cfg = orc.OracleConfig(max_length=64, sheet_h=64, sheet_w=64)
+    state = orc.init_state(cfg, seed=11)
+    B = 320
+    strings = [s[:64] for s in orc.dataset_strings(B)]
+    tokens = orc.encode_strings(strings, cfg.max_length)
+    targets = torch.from_numpy(orc.synthetic_targets_u8(strings, cfg))
+    model = make_model(cfg, state).eval()
+    z = model.logits(tokens.to(dev())).cpu()
+    assert rel_fro(z, orc.logits(state, tokens, cfg)) < 5e-3
+    model.train()
+    model.dropout_seed, model.dropout_step = 31337, 0
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
+    masks = orc.builtin_masks(cfg, B, cfg.max_length, seed=31337, step=0)
+    loss = model.fused_train_step(tokens.to(dev()), targets.to(dev()))
+    l_ref, g_ref, _ = orc.loss_and_grads(state, tokens, orc.targets_to_f32(targets.numpy()), cfg, masks)
+    assert abs(float(loss) - float(l_ref)) < 2e-3 * float(l_ref)
+    assert_grads_close(grads_of(model), g_ref, label="64x64")
+    loss2 = model.fused_forward_loss(tokens.to(dev()), targets.to(dev()))
+    backward_and_step(model, opt, row_buckets(cfg.sheet_h * cfg.sheet_w, 1), 1)
+    loss3 = model.fused_forward_loss(tokens.to(dev()), targets.to(dev()), dropout=False)
+    torch.cuda.synchronize()
+    assert math.isfinite(float(loss3)) and float(loss3) < float(loss2)
 
 
 def test_errors_are_loud():
