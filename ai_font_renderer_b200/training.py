@@ -122,11 +122,17 @@ class PeerLink:
         with the number of ranks while its NVLink volume stays, so fewer SMs saturate it."""
         return 48 if world <= 2 else (32 if world <= 4 else 24)
 
-    def __init__(self, model, ctas: int = 0, group=None):
+    def __init__(self, model, ctas: int = 0, group=None, inline: bool = False):
+        """inline: run the gather/AdamW/broadcast kernel on the compute stream on ALL SMs right
+        after the wgrad GEMM instead of on a side stream on `ctas` SMs next to the rest of
+        backward: no SM is withheld from the GEMMs / front-end kernels, and the kernel itself is
+        several times faster with the whole GPU's memory-level parallelism."""
         import torch.distributed._symmetric_memory as symm_mem
         group = group or dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        ctas = ctas or self.default_ctas(self.world)
+        self.inline = inline
+        sms_all = torch.cuda.get_device_properties(model.fc_output.weight.device).multi_processor_count
+        ctas = sms_all if inline else (ctas or self.default_ctas(self.world))
         w = model.fc_output.weight
         dev = w.device
         self.ctas = ctas
@@ -142,7 +148,7 @@ class PeerLink:
         self.grad_ptrs = arr(*[int(p) for p in self.h_grad.buffer_ptrs])
         self.shadow_ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self.h_shadow]
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        model.set_sm_limit(sms - ctas)            # the gather kernel's SMs stay free of persistent CTAs
+        model.set_sm_limit(0 if inline else sms - ctas)   # side-stream mode: the gather kernel's SMs stay free
         model._peer_link = self
 
     @staticmethod
@@ -278,6 +284,15 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
 
     def after_wgrad(i, r0, r1):
         mark("wgrad")
+        if link is not None and link.inline:
+            # compute stream, all SMs: barrier -> gather-sum + AdamW + bf16 broadcast -> barrier
+            link.h_grad.barrier(channel=0)
+            mark("adamw_begin")
+            optimizer.step_rows_gather(t_step, lo, hi, link.grad_ptrs, link.shadow_ptrs[nxt_index],
+                                       world, link.ctas)
+            mark("adamw_end")
+            link.h_grad.barrier(channel=1)
+            return
         side.wait_stream(main)
         if link is not None:
             # NVLink peer memory, no collective call: barrier (every rank's dW complete) -> one
@@ -310,7 +325,10 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     # waits for the sharded AdamW sweep, which waits for the reduce-scatter
     dist.all_reduce(model.small_grad_flat, op=dist.ReduceOp.SUM, group=_small_group())
     optimizer.step_small(t_step)
-    model.defer_join(side)      # joined right before the next fc_output GEMM (renderer.join_pending)
+    if link is not None and link.inline:
+        model.shadow_commit()   # everything is on the compute stream: the next forward reads the new copy
+    else:
+        model.defer_join(side)  # joined right before the next fc_output GEMM (renderer.join_pending)
     optimizer.end_step()
     mark("tail")
 

@@ -297,9 +297,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--dp-mode", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "peer", "peer-side", "nccl"],
                     help="N > 1: 'peer' = row-sharded AdamW reading/writing NVLink peer memory in one "
-                         "kernel (no collective for fc_output); 'nccl' = reduce-scatter / all-gather")
+                         "kernel on all SMs of the compute stream, 'peer-side' = the same kernel on a side "
+                         "stream on --comm-ctas SMs under the rest of backward, 'nccl' = reduce-scatter / "
+                         "all-gather, 'auto' = peer at 2 GPUs, peer-side above")
     ap.add_argument("--comm-ctas", type=int, default=0,
                     help="N > 1: SMs left to the communication kernel (0 = PeerLink.default_ctas / 32 for "
                          "NCCL); the persistent kernels use the rest")
@@ -348,8 +350,13 @@ def main():
                      overlap_dgrad=fused and args.overlap_dgrad)
     if world > 1:
         from ai_font_renderer_b200.training import PeerLink
-        if args.dp_mode == "peer":
-            PeerLink(model, ctas=args.comm_ctas)
+        if args.dp_mode == "auto":
+            # measured on B200: at 2 GPUs the gather kernel is HBM-bound and
+            # fastest on all SMs on the compute stream; from 4 GPUs on it is NVLink-bound (0.65 GB
+            # in per rank and step at 8 GPUs) and has to hide on a side stream under backward
+            args.dp_mode = "peer" if world == 2 else "peer-side"
+        if args.dp_mode in ("peer", "peer-side"):
+            PeerLink(model, ctas=args.comm_ctas, inline=args.dp_mode == "peer")
         else:
             sms = torch.cuda.get_device_properties(device).multi_processor_count
             model.set_sm_limit(sms - int(os.environ["NCCL_MAX_CTAS"]))
