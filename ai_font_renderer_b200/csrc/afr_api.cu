@@ -705,6 +705,32 @@ int afr_adamw_rows_gather(afr_ctx* c, double lr, double beta1, double beta2, dou
   return AFR_OK;
 }
 
+int afr_adamw_rows_gather_nvls(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, int64_t step, int row_begin, int row_end,
+                               const void* grad_multicast, void* shadow_multicast, int ctas,
+                               void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_state)
+    return fail(c, AFR_ERR_STATE, "params / adam state not bound");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
+    return fail(c, AFR_ERR_INVALID, "bad step or row range");
+  if (grad_multicast == nullptr || shadow_multicast == nullptr || ctas < 1)
+    return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_gather_nvls: null multicast pointer or ctas < 1");
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  const long long n = static_cast<long long>(row_end - row_begin) * c->K;
+  DeviceGuard guard(c->cfg.device);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  AFR_CUDA(c, launch_adamw_gather_nvls(c->params.wout + off, c->m.wout + off, c->v.wout + off, n, h,
+                                       static_cast<const float*>(grad_multicast) + off,
+                                       static_cast<__nv_bfloat16*>(shadow_multicast) + off, ctas,
+                                       static_cast<cudaStream_t>(stream)),
+           "adamw_gather_nvls(fc_output.weight rows)");
+  c->launches += 1;
+  c->shadow_rows_swept += row_end - row_begin;   // completed by the multicast stores; afr_shadow_commit
+  return AFR_OK;
+}
+
 int afr_adamw_small(afr_ctx* c, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream) {
   if (!c) return AFR_ERR_INVALID;

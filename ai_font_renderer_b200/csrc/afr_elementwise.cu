@@ -140,6 +140,52 @@ adamw_gather_kernel(float* __restrict__ p, float* __restrict__ m, float* __restr
   }
 }
 
+// The same step through the NVSwitch (NVLS multicast objects of the symmetric allocations): ONE
+// multimem.ld_reduce returns the gradient already summed over all ranks inside the switch, ONE
+// multimem.st delivers the bf16 result to every rank -- the kernel's NVLink traffic drops from
+// (world - 1) x (16 + 8) bytes per float4 group to 16 + 8, so it is HBM-bound instead of link-bound.
+__device__ __forceinline__ float4 ld_reduce_mc(const float* g_mc, long long i) {
+  float4 s;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w)
+               : "l"(reinterpret_cast<const float4*>(g_mc) + i)
+               : "memory");
+  return s;
+}
+__device__ __forceinline__ void adamw_group_nvls(float* p, float* m, float* v, long long i, const float4& s,
+                                                 const AdamHyper& h, __nv_bfloat16* sh_mc) {
+  float4 pv = reinterpret_cast<float4*>(p)[i];
+  float4 mv = reinterpret_cast<float4*>(m)[i];
+  float4 vv = reinterpret_cast<float4*>(v)[i];
+  adamw_elem(pv.x, s.x, mv.x, vv.x, h);
+  adamw_elem(pv.y, s.y, mv.y, vv.y, h);
+  adamw_elem(pv.z, s.z, mv.z, vv.z, h);
+  adamw_elem(pv.w, s.w, mv.w, vv.w, h);
+  reinterpret_cast<float4*>(p)[i] = pv;
+  reinterpret_cast<float4*>(m)[i] = mv;
+  reinterpret_cast<float4*>(v)[i] = vv;
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+  asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(
+                   reinterpret_cast<uint2*>(sh_mc) + i),
+               "r"(*reinterpret_cast<const uint32_t*>(&lo)), "r"(*reinterpret_cast<const uint32_t*>(&hi))
+               : "memory");
+}
+// The in-switch reduction has a long round trip: every thread keeps four of them in flight.
+__global__ void __launch_bounds__(1024, 1)
+adamw_gather_nvls_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                         long long n4, AdamHyper h, const float* g_mc, __nv_bfloat16* sh_mc) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = ld_reduce_mc(g_mc, i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) adamw_group_nvls(p, m, v, i + u * stride, s[u], h, sh_mc);
+  }
+  for (; i < n4; i += stride) adamw_group_nvls(p, m, v, i, ld_reduce_mc(g_mc, i), h, sh_mc);
+}
+
 constexpr int kMaxSmallJobs = 16;
 struct SmallJobs { SmallAdamJob j[kMaxSmallJobs]; int n; };
 
@@ -292,6 +338,13 @@ cudaError_t launch_adamw_gather(float* p, float* m, float* v, long long n, const
     peers.sh[q] = peer_shadow[q];
   }
   adamw_gather_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 4, h, peers);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_gather_nvls(float* p, float* m, float* v, long long n, const AdamHyper& h,
+                                     const float* g_mc, __nv_bfloat16* sh_mc, int ctas, cudaStream_t s) {
+  if ((n % 4) != 0 || ctas < 1 || g_mc == nullptr || sh_mc == nullptr) return cudaErrorInvalidValue;
+  adamw_gather_nvls_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 4, h, g_mc, sh_mc);
   return cudaGetLastError();
 }
 

@@ -114,6 +114,15 @@ class FusedAdamW(torch.optim.Optimizer):
                                                 _stream_ptr(ctx.device)))
 
     @torch.no_grad()
+    def step_rows_gather_nvls(self, t: int, row_begin: int, row_end: int, grad_mc: int, shadow_mc: int,
+                              ctas: int):
+        """step_rows_gather through NVSwitch multicast addresses (in-switch gradient sum, one
+        multicast store of the bf16 rows)."""
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_adamw_rows_gather_nvls(ctx.handle, *self._hyper(), t, row_begin, row_end,
+                                                     grad_mc, shadow_mc, ctas, _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
     def step_small(self, t: int):
         ctx, _ = self._bucket
         ctx.check(ctx.lib.afr_adamw_small(ctx.handle, *self._hyper(), t, _stream_ptr(ctx.device)))

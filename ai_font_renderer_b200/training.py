@@ -54,6 +54,7 @@ class TrainConfig:
     render_every: int = 5
     grad_buckets: int = 8            # row buckets of fc_output.weight.grad (data parallel overlap)
     adam_buckets: int = 1            # single GPU: row buckets of the wgrad GEMM / AdamW sweep
+    peer_memory: bool = True         # data parallel: NVLink peer-memory / NVLS optimizer step (PeerLink); False = NCCL
     max_steps: Optional[int] = None  # stop after this many optimizer steps (tests / smoke)
     quiet: bool = False
 
@@ -122,7 +123,7 @@ class PeerLink:
         with the number of ranks while its NVLink volume stays, so fewer SMs saturate it."""
         return 48 if world <= 2 else (32 if world <= 4 else 24)
 
-    def __init__(self, model, ctas: int = 0, group=None, inline: bool = False):
+    def __init__(self, model, ctas: int = 0, group=None, inline: bool = False, nvls: bool = False):
         """inline: run the gather/AdamW/broadcast kernel on the compute stream on ALL SMs right
         after the wgrad GEMM instead of on a side stream on `ctas` SMs next to the rest of
         backward: no SM is withheld from the GEMMs / front-end kernels, and the kernel itself is
@@ -131,6 +132,7 @@ class PeerLink:
         group = group or dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.inline = inline
+        self.nvls = nvls
         sms_all = torch.cuda.get_device_properties(model.fc_output.weight.device).multi_processor_count
         ctas = sms_all if inline else (ctas or self.default_ctas(self.world))
         w = model.fc_output.weight
@@ -147,9 +149,29 @@ class PeerLink:
         arr = _C.c_void_p * self.world
         self.grad_ptrs = arr(*[int(p) for p in self.h_grad.buffer_ptrs])
         self.shadow_ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self.h_shadow]
+        if nvls:
+            # NVSwitch multicast objects over the same allocations (NVLS): in-switch reduction of
+            # the gradient rows, one multicast store for the bf16 rows
+            self.grad_mc = int(self.h_grad.multicast_ptr or 0)
+            self.shadow_mc = [int(h.multicast_ptr or 0) for h in self.h_shadow]
+            if not self.grad_mc or not all(self.shadow_mc):
+                raise RuntimeError("NVLS multicast is not available for the symmetric allocations on this system")
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         model.set_sm_limit(0 if inline else sms - ctas)   # side-stream mode: the gather kernel's SMs stay free
         model._peer_link = self
+
+    @staticmethod
+    def nvls_available() -> bool:
+        """True when symmetric allocations get an NVSwitch multicast mapping (collective: every rank
+        must call it at the same point)."""
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = torch.device("cuda", torch.cuda.current_device())
+            probe = symm_mem.empty((1024,), dtype=torch.float32, device=dev)
+            handle = symm_mem.rendezvous(probe, dist.group.WORLD)
+            return bool(getattr(handle, "multicast_ptr", 0))
+        except Exception:
+            return False
 
     @staticmethod
     def available() -> bool:
@@ -288,8 +310,11 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             # compute stream, all SMs: barrier -> gather-sum + AdamW + bf16 broadcast -> barrier
             link.h_grad.barrier(channel=0)
             mark("adamw_begin")
-            optimizer.step_rows_gather(t_step, lo, hi, link.grad_ptrs, link.shadow_ptrs[nxt_index],
-                                       world, link.ctas)
+            if link.nvls:
+                optimizer.step_rows_gather_nvls(t_step, lo, hi, link.grad_mc, link.shadow_mc[nxt_index], link.ctas)
+            else:
+                optimizer.step_rows_gather(t_step, lo, hi, link.grad_ptrs, link.shadow_ptrs[nxt_index],
+                                           world, link.ctas)
             mark("adamw_end")
             link.h_grad.barrier(channel=1)
             return
@@ -301,8 +326,12 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             with torch.cuda.stream(side):
                 link.h_grad.barrier(channel=0)
                 mark("adamw_begin")
-                optimizer.step_rows_gather(t_step, lo, hi, link.grad_ptrs, link.shadow_ptrs[nxt_index],
-                                           world, link.ctas)
+                if link.nvls:
+                    optimizer.step_rows_gather_nvls(t_step, lo, hi, link.grad_mc, link.shadow_mc[nxt_index],
+                                                    link.ctas)
+                else:
+                    optimizer.step_rows_gather(t_step, lo, hi, link.grad_ptrs, link.shadow_ptrs[nxt_index],
+                                               world, link.ctas)
                 mark("adamw_end")
                 link.h_grad.barrier(channel=1)
             return
@@ -362,6 +391,15 @@ class Trainer:
             self.optimizer, mode="min", factor=cfg.scheduler_factor,
             patience=cfg.scheduler_patience, min_lr=cfg.min_learning_rate)            # model.py:276-278
         self.P = cfg.sheet_height * cfg.sheet_width
+        if (self.world > 1 and cfg.peer_memory and device.type == "cuda" and self.P % self.world == 0
+                and getattr(model, "_peer_link", None) is None and PeerLink.available()):
+            # collective on every rank: symmetric allocations for dW and the bf16 weight copies; the
+            # NCCL reduce-scatter / all-gather form stays as the fallback
+            try:
+                PeerLink(model, nvls=PeerLink.nvls_available())
+            except Exception as exc:      # no peer access / symmetric memory on this system
+                if self.rank == 0 and not cfg.quiet:
+                    print(f"PeerLink unavailable ({exc}); using NCCL reduce-scatter / all-gather")
         self.buckets = row_buckets(self.P, cfg.grad_buckets if self.world > 1 else cfg.adam_buckets)
         self.steps_done = 0
 

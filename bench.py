@@ -297,7 +297,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--dp-mode", default="auto", choices=["auto", "peer", "peer-side", "nccl"],
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "peer", "peer-side", "nvls", "nvls-side", "nccl"],
                     help="N > 1: 'peer' = row-sharded AdamW reading/writing NVLink peer memory in one "
                          "kernel on all SMs of the compute stream, 'peer-side' = the same kernel on a side "
                          "stream on --comm-ctas SMs under the rest of backward, 'nccl' = reduce-scatter / "
@@ -351,12 +351,14 @@ def main():
     if world > 1:
         from ai_font_renderer_b200.training import PeerLink
         if args.dp_mode == "auto":
-            # measured on B200: at 2 GPUs the gather kernel is HBM-bound and
-            # fastest on all SMs on the compute stream; from 4 GPUs on it is NVLink-bound (0.65 GB
-            # in per rank and step at 8 GPUs) and has to hide on a side stream under backward
-            args.dp_mode = "peer" if world == 2 else "peer-side"
-        if args.dp_mode in ("peer", "peer-side"):
-            PeerLink(model, ctas=args.comm_ctas, inline=args.dp_mode == "peer")
+            # measured on B200: the gather / AdamW / broadcast kernel is bound by
+            # the NVLink egress of the gradient rows (0.43 GB per rank and step at 8 GPUs), so it hides
+            # on a side stream under the rest of backward; with NVSwitch multicast (NVLS) its inbound
+            # traffic and SM time shrink (2 GPUs 1.65 vs 1.82 ms, 8 GPUs 1.51 vs 1.55 ms)
+            args.dp_mode = "nvls-side" if PeerLink.nvls_available() else ("peer" if world == 2 else "peer-side")
+        if args.dp_mode in ("peer", "peer-side", "nvls", "nvls-side"):
+            PeerLink(model, ctas=args.comm_ctas, inline=args.dp_mode in ("peer", "nvls"),
+                     nvls=args.dp_mode.startswith("nvls"))
         else:
             sms = torch.cuda.get_device_properties(device).multi_processor_count
             model.set_sm_limit(sms - int(os.environ["NCCL_MAX_CTAS"]))

@@ -24,11 +24,12 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["peer", "peer-side", "nccl"])
+@pytest.mark.parametrize("mode", ["peer", "peer-side", "nvls", "nccl"])
 def test_row_sharded_data_parallel_step_equals_single_gpu_step(mode):
     """peer: gradient rows / bf16 weights move through NVLink peer memory inside the AdamW kernel, on
     the compute stream on all SMs; peer-side: the same kernel on a side stream on a few SMs;
-    nccl: reduce-scatter + all-gather."""
+    nvls: the same with the gradient summed inside the NVSwitch (multimem.ld_reduce) and the bf16
+    rows multicast (multimem.st); nccl: reduce-scatter + all-gather."""
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),

@@ -42,9 +42,9 @@ def main(steps=3, per_rank=96, mode=None):
 
     solo, solo_opt = make()
     dp, dp_opt = make()
-    if mode in ("peer", "peer-side"):
+    if mode in ("peer", "peer-side", "nvls", "nvls-side"):
         from ai_font_renderer_b200.training import PeerLink
-        PeerLink(dp, ctas=16, inline=mode == "peer")
+        PeerLink(dp, ctas=16, inline=mode in ("peer", "nvls"), nvls=mode.startswith("nvls"))
     lo, hi = shard_bounds(gB, rank, world)
     worst_loss = 0.0
     for _ in range(steps):
