@@ -103,6 +103,10 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     if (err_msg) *err_msg = kBadAlign;
     return cudaErrorInvalidValue;
   }
+  if ((epi.kind == kEpiU8 || epi.kind == kEpiLoss) && (reinterpret_cast<uintptr_t>(epi.bias) & 15)) {
+    if (err_msg) *err_msg = "gemm: the bias of the uint8 / loss epilogues must be 16-byte aligned";
+    return cudaErrorInvalidValue;
+  }
   GemmParams p{};
   bool ok = true;
   // CTA pairs: 256 x BN tiles, each CTA loads half of the B tile (box of BN / 2 rows)

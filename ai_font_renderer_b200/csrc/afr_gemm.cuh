@@ -511,6 +511,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           }
         } else if (EPI == kEpiU8) {
           if (row_ok) {
+            float bias[32];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {   // n is a multiple of 32: 16-byte aligned groups
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + ch);
+              bias[4 * ch] = b4.x; bias[4 * ch + 1] = b4.y; bias[4 * ch + 2] = b4.z; bias[4 * ch + 3] = b4.w;
+            }
             uint32_t packed[8];
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -518,7 +524,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int b = 0; b < 4; ++b) {
                 const int j = 4 * w + b;
-                float z = v[j] + __ldg(p.bias + n + j);
+                float z = v[j] + bias[j];
                 z = fminf(fmaxf(z, 0.f), 1.f);
                 const uint32_t u = static_cast<uint32_t>(__fmul_rn(z, 255.0f));  // truncation
                 word |= (u & 0xFFu) << (8 * b);
@@ -550,8 +556,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               for (int w = 0; w < 8; ++w)
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                  // exactly np.float32(u8) / 255.0 (helpers.py:121)
-                  t[4 * w + b] = __fdiv_rn(static_cast<float>((words[w] >> (8 * b)) & 0xFFu), 255.0f);
+                  // exactly np.float32(u8) / 255.0 (helpers.py:121): round-to-nearest division
+                  // without the range-check branch (operands are 0 or normal)
+                  t[4 * w + b] = div_rn_nobranch(static_cast<float>((words[w] >> (8 * b)) & 0xFFu), 255.0f);
+            }
+            float bias[32];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {   // n is a multiple of 32: 16-byte aligned groups
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + ch);
+              bias[4 * ch] = b4.x; bias[4 * ch + 1] = b4.y; bias[4 * ch + 2] = b4.z; bias[4 * ch + 3] = b4.w;
             }
             uint32_t packed[16];
 #pragma unroll
@@ -559,7 +572,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               float g2[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const float z = v[j + e] + __ldg(p.bias + n + j + e);
+                const float z = v[j + e] + bias[j + e];
                 const float y = fminf(fmaxf(z, 0.f), 1.f);
                 const float d = y - t[j + e];
                 loss_acc = fmaf(d, d, loss_acc);

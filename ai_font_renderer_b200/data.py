@@ -54,6 +54,25 @@ def encode(strings: Sequence[str], width: int) -> torch.Tensor:
     return torch.from_numpy(arr)
 
 
+def encode_with_font(strings: Sequence[str], font_ids: Sequence[int], width: int,
+                     n_chars: int = 128) -> torch.Tensor:
+    """Multi-font conditioning (BASELINE config 3; an extension -- the reference has one font and no
+    conditioning input): the font is a CONTROL TOKEN. Position 0 holds token n_chars + font_id, the
+    characters follow from position 1, zero padding as before; the model is built with
+    vocab = n_chars + n_fonts and max_length = longest string + 1. The token's embedding row plays
+    the role of a font embedding and reaches every position through the attention layer, and
+    because it is just a vocabulary row the forward / backward / optimizer kernels, the oracle and
+    the data-parallel path apply unchanged (SURVEY 8d proposed adding a font vector to every token
+    embedding instead; that needs a thirteenth parameter tensor in the checkpoint layout)."""
+    if len(strings) != len(font_ids):
+        raise ValueError("one font id per string")
+    body = encode(strings, width - 1)
+    tokens = torch.zeros((len(strings), width), dtype=torch.int64)
+    tokens[:, 1:] = body
+    tokens[:, 0] = torch.as_tensor(list(font_ids), dtype=torch.int64) + n_chars
+    return tokens
+
+
 def synthetic_sheets(strings: Sequence[str], height: int = 80, width: int = 240,
                      seed: int = 1234) -> np.ndarray:
     """uint8 [N,H,W] stand-ins for the FiraCode renders: white (255) with ~5 % ink at four grey
@@ -158,6 +177,22 @@ def load_string_dataset_u8(data_dir: str = "train_input", num_samples: int = 500
     strings = strings[:num_samples]
     max_len = max(len(s) for s in strings)
     return encode(strings, max_len), torch.from_numpy(targets)
+
+
+def load_multifont_dataset_u8(data_dir: str = "train_input", num_samples: int = 50000,
+                              sheet_height: int = 80, sheet_width: int = 240, n_chars: int = 128):
+    """A fontgen multi-font set (data.txt, <i>.bmp, fonts.txt with one font index per line) ->
+    (tokens int64 [N, Lmax + 1] with the font control token in column 0, uint8 sheets [N,H,W],
+    number of fonts)."""
+    tokens, targets = load_string_dataset_u8(data_dir, num_samples, sheet_height, sheet_width)
+    with open(os.path.join(data_dir, "fonts.txt")) as f:
+        fonts = [int(x) for x in f.read().split()][:num_samples]
+    if len(fonts) < num_samples:
+        raise ValueError(f"Not enough font ids in {data_dir}/fonts.txt. Expected {num_samples}, got {len(fonts)}")
+    out = torch.zeros((num_samples, tokens.shape[1] + 1), dtype=torch.int64)
+    out[:, 1:] = tokens
+    out[:, 0] = torch.tensor(fonts, dtype=torch.int64) + n_chars
+    return out, targets, max(fonts) + 1
 
 
 class HostBatchFeeder:

@@ -37,8 +37,12 @@ def grey_bmp_bytes(img: np.ndarray) -> bytes:
     return header + info + palette.tobytes() + rows.tobytes()
 
 
-def strings_to_tokens(strings: Sequence[str], max_length: int) -> torch.Tensor:
-    """helpers.py:52-59: truncate to max_length, ord(), pad with token 0."""
+def strings_to_tokens(strings: Sequence[str], max_length: int, font_ids=None) -> torch.Tensor:
+    """helpers.py:52-59: truncate to max_length, ord(), pad with token 0. With font_ids (multi-font
+    models, data.encode_with_font) position 0 carries the font control token."""
+    if font_ids is not None:
+        from .data import encode_with_font
+        return encode_with_font([s[:max_length - 1] for s in strings], font_ids, max_length)
     return encode([s[:max_length] for s in strings], max_length)
 
 
@@ -128,19 +132,21 @@ def write_bmp_files(sheets: np.ndarray, output_dir: str, first_index: int = 0, t
             list(pool.map(one, range(len(block))))
 
 
-def render_strings(model, strings, output_dir, sheet_height, sheet_width, device, batch_size: int = 4096):
+def render_strings(model, strings, output_dir, sheet_height, sheet_width, device, batch_size: int = 4096,
+                   font_ids=None):
     """Render a list of strings as BMP images -- same signature, file names, truncation warning and
     summary line as helpers.py:46-74, for any number of strings: batches go through
     RenderPipeline, and each batch's files are written while the next one renders. Like the
     reference it does not switch the model to eval(): callers do (model.py:314, helpers.py:103)."""
     os.makedirs(output_dir, exist_ok=True)
     strings = list(strings)
+    limit = model.max_length - (1 if font_ids is not None else 0)
     for i, s in enumerate(strings):
-        if len(s) > model.max_length:
-            strings[i] = s[:model.max_length]
-            print(f"Warning: String truncated to {model.max_length} characters: {strings[i]}")
+        if len(s) > limit:
+            strings[i] = s[:limit]
+            print(f"Warning: String truncated to {limit} characters: {strings[i]}")
     if strings:
-        tokens = strings_to_tokens(strings, model.max_length)
+        tokens = strings_to_tokens(strings, model.max_length, font_ids)
         if model.training:
             # helpers.py:64 would run a dropout forward here; that only happens if a caller
             # forgot model.eval(). Keep the quirk observable:

@@ -51,6 +51,7 @@ class TrainConfig:
     num_samples: int = 150000
     betas: Tuple[float, float] = (0.9, 0.99)
     test_strings: Sequence[str] = field(default_factory=list)
+    test_font_ids: Optional[Sequence[int]] = None   # multi-font models: font of every test string
     render_every: int = 5
     grad_buckets: int = 8            # row buckets of fc_output.weight.grad (data parallel overlap)
     adam_buckets: int = 1            # single GPU: row buckets of the wgrad GEMM / AdamW sweep
@@ -500,7 +501,7 @@ class Trainer:
                 if self.rank == 0 and cfg.output_dir and cfg.test_strings:
                     render_strings(model, cfg.test_strings, output_dir=f"{cfg.output_dir}/epoch_{epoch}",
                                    sheet_height=cfg.sheet_height, sheet_width=cfg.sheet_width,
-                                   device=self.device)
+                                   device=self.device, font_ids=cfg.test_font_ids)
             elif is_best:
                 say(f"Epoch {epoch}, New best validation loss: {avg_val_loss:.6f}")
             if patience_counter >= cfg.early_stopping_patience:         # model.py:362-366

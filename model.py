@@ -11,7 +11,10 @@ command line. Differences a user can see:
   * the reference pins CUDA_VISIBLE_DEVICES="3" (model.py:95); here the device is LOCAL_RANK
     (torchrun) or cuda:0;
   * optional extra flags after --train: --samples N, --epochs N, --batch N, --synthetic
-    (train on synthetic sheets when train_input/ is absent; real bitmaps need bun + node-canvas).
+    (train on synthetic sheets when train_input/ is absent; real bitmaps need bun + node-canvas;
+    `python -m ai_font_renderer_b200.fontgen` writes a FreeType-rasterised stand-in), --fonts N
+    (multi-font conditioning, BASELINE config 3: train_input/fonts.txt names the font of every
+    sample, the font is a control token in position 0, vocabulary 128 + N, 101 positions).
 Launched under torchrun it trains data-parallel (one process per GPU, NCCL).
 """
 import datetime
@@ -122,12 +125,33 @@ def train_string_renderer(argv=()):
     else:
         dataset = load_string_dataset(data_dir="train_input", num_samples=num_samples,
                                       sheet_height=SHEET_HEIGHT, sheet_width=SHEET_WIDTH)
+    n_fonts = _flag(argv, "--fonts", 0)
+    over_fonts = {}
+    if n_fonts > 0:
+        from ai_font_renderer_b200.data import (dataset_texts, encode_with_font, load_multifont_dataset_u8,
+                                                synthetic_sheets)
+        if "--synthetic" in argv:
+            texts = dataset_texts(num_samples)
+            fonts = [i % n_fonts for i in range(num_samples)]
+            sheets = synthetic_sheets(texts, SHEET_HEIGHT, SHEET_WIDTH)
+            for f in range(1, n_fonts):          # every synthetic "font" gets its own ink level
+                sheets[f::n_fonts] = 255 - (255 - sheets[f::n_fonts]) // (f + 1)
+            dataset = (encode_with_font(texts, fonts, MAX_CHARS_PER_SHEET + 1), torch.from_numpy(sheets))
+        else:
+            tokens, targets, found = load_multifont_dataset_u8("train_input", num_samples, SHEET_HEIGHT, SHEET_WIDTH)
+            if found > n_fonts:
+                raise SystemExit(f"train_input/fonts.txt names {found} fonts, --fonts {n_fonts} given")
+            dataset = (tokens, targets)
+        over_fonts = {"test_font_ids": [i % n_fonts for i in range(len(test_strings))]}
     print("Training attention-based sheet renderer with reduced embedding dimensions (32) and "
           "learned positional encoding...")
-    model = AttentionFontRenderer(max_length=MAX_CHARS_PER_SHEET).to(device)
+    if n_fonts > 0:
+        model = AttentionFontRenderer(max_length=dataset[0].shape[1], vocab=128 + n_fonts).to(device)
+    else:
+        model = AttentionFontRenderer(max_length=MAX_CHARS_PER_SHEET).to(device)
     batch_size = _flag(argv, "--batch", 1024)           # model.py:408-409 (GPU batch)
     print(f"Using batch size {batch_size}")
-    over = {"num_samples": num_samples}
+    over = {"num_samples": num_samples, **over_fonts}
     if "--epochs" in argv:
         over["num_epochs"] = _flag(argv, "--epochs", NUM_EPOCHS)
     return train_attention_model(model, dataset, batch_size, **over)

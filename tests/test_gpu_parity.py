@@ -666,6 +666,49 @@ def test_scaled_64x64_sheet_config_matches_oracle():
     assert math.isfinite(float(loss3)) and float(loss3) < float(loss2)
 
 
+def test_multifont_control_token_model_matches_oracle_and_separates_fonts():
+    """BASELINE config 3 (no reference implementation: restated-oracle parity): vocabulary 128 + 2
+    font control tokens, 101 positions. Loss / gradients against the oracle at that shape, then a
+    few fused steps on two synthetic 'fonts' whose sheets differ: the same string must render
+    differently under the two font tokens."""
+    from ai_font_renderer_b200.data import encode_with_font
+    from ai_font_renderer_b200.optim import FusedAdamW
+    from ai_font_renderer_b200.training import backward_and_step, row_buckets
+    cfg = orc.OracleConfig(vocab=130, max_length=101, sheet_h=16, sheet_w=64)
+    state = orc.init_state(cfg, seed=3)
+    B = 256
+    strings = orc.dataset_strings(B)
+    fonts = [i % 2 for i in range(B)]
+    tokens = encode_with_font(strings, fonts, cfg.max_length)
+    t8 = orc.synthetic_targets_u8(strings, cfg)
+    t8[1::2] = 255 - (255 - t8[1::2]) // 2           # font 1: half the ink
+    targets = torch.from_numpy(t8)
+    model = make_model(cfg, state).train()
+    model.dropout_seed, model.dropout_step = 77, 0
+    masks = orc.builtin_masks(cfg, B, cfg.max_length, seed=77, step=0)
+    loss = model.fused_train_step(tokens.to(dev()), targets.to(dev()))
+    l_ref, g_ref, _ = orc.loss_and_grads(state, tokens, orc.targets_to_f32(t8), cfg, masks)
+    assert abs(float(loss) - float(l_ref)) < 2e-3 * float(l_ref)
+    assert_grads_close(grads_of(model), g_ref, label="multifont")
+    assert float(grads_of(model)["embedding.weight"][128:130].abs().sum()) > 0     # font rows get gradient
+    # a learnable font signal: a dark band whose position depends only on the font (grey paper:
+    # logits that overshoot 1 have zero clamp gradient and would never come back)
+    band = np.full((B, cfg.sheet_h, cfg.sheet_w), 191, dtype=np.uint8)
+    band[0::2, 2:6] = 64
+    band[1::2, 10:14] = 64
+    band_t = torch.from_numpy(band).to(dev())
+    # (small steps: Adam's first updates move every logit by ~lr * sum|features| at once)
+    opt = FusedAdamW(model, lr=5e-5, weight_decay=5e-4, betas=(0.9, 0.99))
+    for _ in range(200):
+        model.fused_forward_loss(tokens.to(dev()), band_t)
+        backward_and_step(model, opt, row_buckets(cfg.sheet_h * cfg.sheet_w, 1), 1)
+    model.eval()
+    same = encode_with_font([strings[0]] * 2, [0, 1], cfg.max_length).to(dev())
+    y = model(same).cpu()
+    assert float(y[0, 2:6].mean()) < float(y[1, 2:6].mean()) - 0.05       # font 0 inks the upper band ...
+    assert float(y[1, 10:14].mean()) < float(y[0, 10:14].mean()) - 0.05   # ... font 1 the lower one
+
+
 def test_errors_are_loud():
     from ai_font_renderer_b200 import _lib
     from ai_font_renderer_b200.renderer import AttentionFontRenderer

@@ -106,6 +106,26 @@ def test_offline_dataset_generator_follows_generate_font_ts_conventions(tmp_path
     assert tokens.shape[0] == 6 and int(tokens[0, 0]) == ord(texts[0][0])
 
 
+def test_font_control_token_encoding_and_multifont_loader(tmp_path):
+    """BASELINE config 3 (extension): font id as a control token in position 0."""
+    from ai_font_renderer_b200 import fontgen
+    from ai_font_renderer_b200.data import encode, encode_with_font, load_multifont_dataset_u8
+    from ai_font_renderer_b200.render import strings_to_tokens
+    strings = ["AB C", "HELLO WORLD", ""]
+    tok = encode_with_font(strings, [0, 1, 1], 12)
+    assert tok.shape == (3, 12) and tok.dtype == torch.int64
+    assert tok[:, 0].tolist() == [128, 129, 129]
+    assert torch.equal(tok[:, 1:], encode(strings, 11))
+    assert torch.equal(strings_to_tokens(strings, 12, font_ids=[0, 1, 1]), tok)
+    with pytest.raises(ValueError):
+        encode_with_font(strings, [0], 12)
+    d = tmp_path / "mf"
+    texts = fontgen.generate_dataset(str(d), 5, [None, None], quiet=True)
+    tokens, targets, n_fonts = load_multifont_dataset_u8(str(d), 5)
+    assert n_fonts == 2 and tokens[:, 0].tolist() == [128, 129, 128, 129, 128]
+    assert int(tokens[0, 1]) == ord(texts[0][0]) and targets.shape == (5, 80, 240)
+
+
 def test_reader_decodes_generate_font_ts_layout(tmp_path):
     """24-bit, BGR, top-down (negative height), rows padded to 4 bytes (generate_font.ts:6-62)."""
     from PIL import Image
