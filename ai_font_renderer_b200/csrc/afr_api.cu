@@ -643,7 +643,6 @@ int afr_train_wgrad_adamw(afr_ctx* c, double lr, double beta1, double beta2, dou
   ep.adam_sets = env_int("AFR_WA_SETS");
   ep.adam_sub = env_int("AFR_WA_SUB");
   ep.adam_stages = env_int("AFR_WA_STAGES");
-  ep.adam_prefetch = env_int("AFR_WA_PREFETCH");
   if (c->K < bn) bn = c->K;
   cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
                                    c->B, bn, ep, c->sms, st, nullptr, &msg);

@@ -88,7 +88,7 @@ struct GemmParams {
   // used for both the loads and the in-place stores; out = bf16 copy [M, ldo]
   CUtensorMap tm_p, tm_m, tm_v;
   AdamHyper hyper;
-  float* adam_ptr[3];    // p, exp_avg, exp_avg_sq base pointers (L2 prefetch of the next tile)
+  float* adam_ptr[3];    // p, exp_avg, exp_avg_sq base pointers (the epilogue's direct stores)
   // shared / tensor memory footprint (set by the host, launch_gemm_bf16)
   int stages;            // operand ring depth (2..kMaxStages)
   int b_stage_bytes;     // bytes of one B-operand stage
@@ -98,7 +98,6 @@ struct GemmParams {
   int compact;           // 1: no alignment slack in the dynamic shared memory (base must be 1 KB aligned)
   int adam_sets;         // slab sets per epilogue warp (threads = 64 + 128 * warps per quadrant)
   int adam_sub;          // epilogue warps per TMEM lane quadrant (1..kMaxAdamSub)
-  int adam_prefetch;     // 1: bulk-prefetch the next tile's p/m/v rows into L2 as contiguous runs
 };
 
 // CTA2: the kernel runs as clusters of two CTAs (one TPC) that execute 256-row MMAs together
@@ -334,15 +333,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                               ptx::kL2EvictFirst);
         ptx::tma_load_2d_hint(&p.tm_v, &ld_bar[s_issue], dst + 2 * kEpiWarpBufBytes, col, l_row,
                               ptx::kL2EvictFirst);
-        // adam_prefetch >= 2: also pull this warp's next (adam_prefetch - 1) chunks of the same
-        // rows into L2 now, so DRAM sees several adjacent 128-byte pieces of a row at once
-        for (int k = 1; k < p.adam_prefetch; ++k) {
-          if (lc + k * nsub >= l_chunks) break;
-          const int pc = col + k * nsub * 32;
-          ptx::tma_prefetch_2d(&p.tm_p, pc, l_row);
-          ptx::tma_prefetch_2d(&p.tm_m, pc, l_row);
-          ptx::tma_prefetch_2d(&p.tm_v, pc, l_row);
-        }
       }
       if (++s_issue == sets) s_issue = 0;
       lc += nsub;
@@ -359,17 +349,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const long long m = m0 + q * 32 + lane;
       const int n_chunks = chunks_of(tile);
       const bool active = m0 + q * 32 < p.M && n_chunks > sub;
-      if (active && p.adam_prefetch == 1 && sub == 0) {
-        // the next tile's rows as contiguous runs -> L2; one row per lane
-        const int nt = next_active(tile + tile_step);
-        if (nt < num_tiles) {
-          const long long row = (nt % p.num_m_tiles) * kTileM + row_base + q * 32 + lane;
-          const long long e = row * p.ldo + (nt / p.num_m_tiles) * BN;
-          const uint32_t bytes = static_cast<uint32_t>(chunks_of(nt)) * 128u;
-#pragma unroll
-          for (int a = 0; a < 3; ++a) ptx::prefetch_l2_bulk(p.adam_ptr[a] + e, bytes);
-        }
-      }
       bool acc_ready = false;
       for (int c = sub; active && c < n_chunks; c += nsub) {
         // p, m, v of this chunk wait in slab set s; they are moved to registers and updated in

@@ -155,14 +155,6 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
-// Prefetch of one tensor-map box into L2 (no shared-memory destination).
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
-                   reinterpret_cast<uint64_t>(tm)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
-
 // 128-bit shared-memory accesses by 32-bit shared address (the generic-pointer forms compile to
 // LD.E / ST.E, which take the slower generic path).
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
@@ -175,15 +167,6 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 __device__ __forceinline__ void sts_f4(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
-               : "memory");
-}
-
-// Bulk prefetch of a contiguous global range into L2 (no shared-memory destination).
-// addr and bytes must be multiples of 16.
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(
-                   reinterpret_cast<uint64_t>(gsrc)),
-               "r"(bytes)
                : "memory");
 }
 

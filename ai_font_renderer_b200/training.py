@@ -265,15 +265,24 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             mark("tail")
             return
 
+        # the two small bias-gradient kernels (column sums of d(logits), 17 us) need no shared
+        # memory: on the side stream they slot in next to the AdamW GEMM's CTAs instead of
+        # running after it
+        side = model.side_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for r0, r1 in buckets:
+                optimizer.bias_grad_rows(r0, r1)
+
         def fused_bucket(r0, r1):
             mark("adamw_begin")
             optimizer.wgrad_step_rows(t_step, r0, r1)
             mark("adamw_end")
-            optimizer.bias_grad_rows(r0, r1)
 
         model.fused_backward(buckets, lambda i, r0, r1: mark("wgrad") if i == last else None,
                              wgrad_fn=fused_bucket)
         mark("dgrad")
+        main.wait_stream(side)
         optimizer.step_small(t_step)
         optimizer.end_step()
         mark("tail")

@@ -1,8 +1,8 @@
 """Times afr_train_wgrad_adamw (wgrad GEMM + AdamW epilogue) alone for a list of tile / pipeline
-configurations (env knobs AFR_WA_BN / _SETS / _STAGES / _PREFETCH / _SUB read at every call) and checks
+configurations (env knobs AFR_WA_BN / _SETS / _STAGES / _SUB read at every call) and checks
 that every configuration produces bit-identical p / exp_avg / exp_avg_sq / bf16 copy.
 
-    python tools/fused_sweep.py [--batch 1024] [--configs bn,sets,stages,prefetch,sub ...]
+    python tools/fused_sweep.py [--batch 1024] [--configs bn,sets,stages,sub ...]
 """
 import argparse
 import os
@@ -16,7 +16,7 @@ from ai_font_renderer_b200.data import fast_synthetic_batch      # noqa: E402
 from ai_font_renderer_b200.optim import FusedAdamW               # noqa: E402
 from ai_font_renderer_b200.renderer import AttentionFontRenderer, _stream_ptr  # noqa: E402
 
-DEFAULT = ["256,1,0,0,2", "256,2,0,0,1", "192,1,0,0,2", "128,1,0,0,2", "128,2,0,0,2", "256,1,0,1,2", "256,1,2,0,2", "192,2,0,0,2"]
+DEFAULT = ["256,1,0,2", "256,2,0,1", "192,1,0,2", "128,1,0,2", "256,1,2,2"]
 
 
 def main():
@@ -39,9 +39,9 @@ def main():
     nbytes = 26 * w.numel() + 2 * args.batch * (w.shape[0] + w.shape[1])
     first = None
     for cfg in args.configs:
-        bn, sets, stages, pf, sub = (int(x) for x in cfg.split(","))
+        bn, sets, stages, sub = (int(x) for x in cfg.split(","))
         os.environ.update(AFR_WA_BN=str(bn), AFR_WA_SETS=str(sets), AFR_WA_STAGES=str(stages),
-                          AFR_WA_PREFETCH=str(pf), AFR_WA_SUB=str(sub))
+                          AFR_WA_SUB=str(sub))
         times = []
         try:
             for rep in range(args.reps):
@@ -56,14 +56,14 @@ def main():
                 torch.cuda.synchronize()
                 times.append(e0.elapsed_time(e1))
         except Exception as exc:  # configuration does not fit / invalid
-            print(f"cfg bn={bn} sets={sets} stages={stages} prefetch={pf} sub={sub}: {exc}")
+            print(f"cfg bn={bn} sets={sets} stages={stages} sub={sub}: {exc}")
             continue
         shadow = ctx.workspace_tensor(3, tuple(w.shape), torch.bfloat16)
         sig = tuple(float(t.double().abs().sum()) for t in (w.data, st["exp_avg"], st["exp_avg_sq"], shadow.float()))
         if first is None:
             first = sig
         ms = min(times)
-        print(f"cfg bn={bn:3d} sets={sets} stages={stages} prefetch={pf} sub={sub}: {ms:.4f} ms "
+        print(f"cfg bn={bn:3d} sets={sets} stages={stages} sub={sub}: {ms:.4f} ms "
               f"(median {sorted(times)[len(times) // 2]:.4f})  {nbytes / ms / 1e6:.0f} GB/s  "
               f"{'same bits' if sig == first else 'DIFFERENT RESULT'}", flush=True)
 
