@@ -168,7 +168,7 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     p.hyper = epi.hyper;
     p.adam_ptr[0] = epi.adam_p; p.adam_ptr[1] = epi.adam_m; p.adam_ptr[2] = epi.adam_v;
     p.b_stage_bytes = ((BN / kctas + 63) / 64) * 8192;
-    p.adam_sub = epi.adam_sub >= 1 && epi.adam_sub <= kMaxAdamSub ? epi.adam_sub : kMaxAdamSub;
+    p.adam_sub = epi.adam_sub >= 1 && epi.adam_sub <= kMaxAdamSub ? epi.adam_sub : 2;
     p.adam_sets = epi.adam_sets >= 1 && epi.adam_sets <= kMaxAdamSets ? epi.adam_sets : 1;
     p.epi_bytes = 4 * p.adam_sub * p.adam_sets * kAdamSlabBytes;
     // deepest operand ring that still fits beside the slab sets

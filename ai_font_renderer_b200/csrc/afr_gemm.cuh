@@ -46,8 +46,8 @@ constexpr int kGemmSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes
 // chosen by the host so that the total fits the 227 KB of shared memory (adam_smem_bytes).
 constexpr int kAdamSlabBytes = 3 * kEpiWarpBufBytes;             // 12 KB
 constexpr int kMaxStages = 8;
-constexpr int kMaxAdamSets = 4;
-constexpr int kMaxAdamSub = 2;                                   // epilogue warps per lane quadrant
+constexpr int kMaxAdamSets = 2;
+constexpr int kMaxAdamSub = 3;                                   // epilogue warps per lane quadrant
 constexpr int kAdamMaxThreads = 64 + 128 * kMaxAdamSub;
 // dynamic shared memory of a launch: operand ring + epilogue region + barriers (+ 1 KB alignment
 // slack unless the co-resident footprint is requested)

@@ -275,15 +275,18 @@ def measure_render(model, device, rank, world, dist, bmp_set=False):
             "output": "uint8 sheets (helpers.py:33 quantisation fused in the GEMM epilogue)"}
 
 
-def workload_config(n_gpus, fused=False):
+def workload_config(n_gpus, fused=False, dp_mode=None):
     return {"workload": "config[1] FiraCode model 100 chars -> 80x240, fused fwd/bwd/AdamW, "
                         "1024 glyphs per GPU per step (model.py:409)",
             "optimizer": ("AdamW of fc_output.weight inside the wgrad GEMM epilogue (gradient not materialised)"
                           if fused else "AdamW sweep kernel over fc_output.weight"),
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
             "max_length": 100, "sheet": "80x240", "params": 122912896,
-            "parallelism": (f"dp{n_gpus}: batch sharded; AdamW of fc_output.weight sharded by rows, its "
-                            f"gradient rows summed from / bf16 weights stored to NVLink peer memory") if n_gpus > 1 else "single",
+            "parallelism": (f"dp{n_gpus} ({dp_mode}): batch sharded; AdamW of fc_output.weight sharded by rows, "
+                            + ("gradient rows summed inside the NVSwitch (multimem.ld_reduce), bf16 rows multicast"
+                               if (dp_mode or "").startswith("nvls") else
+                               "NCCL reduce-scatter / all-gather" if dp_mode == "nccl" else
+                               "gradient rows read from / bf16 rows stored to NVLink peer memory")) if n_gpus > 1 else "single",
             "l2": "no flush: one step streams 3.9 GB (fp32 master, grads, Adam moments, bf16 shadow) "
                   "through the 126 MB L2 and rotates over 8 resident batches"}
 
@@ -462,6 +465,7 @@ def main():
                       for x, y in zip(m.ev["adamw_begin"], m.ev["adamw_end"])]
     adamw_ms_per_launch = sum(adam_launch_ms) / len(adam_launch_ms)
     adamw_ms_per_step = sum(adam_launch_ms) / args.steps
+    launches_per_step = max(1, len(adam_launch_ms) // args.steps)
     phase_ms["adamw_side_stream"] = adamw_ms_per_step
 
     # the same sweep alone on the device (nothing else running), for reference
@@ -500,6 +504,16 @@ def main():
         kernel_name = "gemm_bf16_tcgen05_kernel<kEpiAdamW> (wgrad GEMM, AdamW of fc_output.weight in its epilogue)"
         adamw_bytes = FUSED_BYTES_PER_PARAM * N_PARAMS_W + 2 * B * (P_PIX + K_FEAT)
         traffic = load_fused_traffic()
+    elif world > 1 and args.dp_mode != "nccl":
+        # row-sharded optimizer step of this rank: HBM bytes of the owned rows (p, m, v read +
+        # written, local gradient read, local bf16 copy written); the kernel is bound by the
+        # NVLink egress of the other ranks' gradient rows, reported next to it
+        owned = N_PARAMS_W // world
+        kernel_name = ("adamw_gather_nvls_kernel (in-switch gradient sum + AdamW + multicast bf16 rows)"
+                       if args.dp_mode.startswith("nvls") else
+                       "adamw_gather_kernel (peer gradient rows + AdamW + bf16 rows to peers)")
+        adamw_bytes = (24 + 4 + 2) * owned
+        traffic = None
     else:
         kernel_name = "adamw_kernel (fc_output.weight sweep + bf16 shadow)"
         adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
@@ -510,7 +524,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(world, fused),
+        "config": workload_config(world, fused, args.dp_mode if world > 1 else None),
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(feeder.h2d_bytes_per_batch), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -519,11 +533,12 @@ def main():
         "roofline": {"kernel": kernel_name,
                      "bound": "hbm", "achieved": adamw_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": adamw_gbs / peaks["hbm"], "traffic": traffic,
-                     "algorithmic_bytes_per_launch": adamw_bytes // len(buckets),
-                     "launches_per_step": len(buckets), "ms_per_launch": adamw_ms_per_launch,
+                     "algorithmic_bytes_per_launch": adamw_bytes // launches_per_step,
+                     "launches_per_step": launches_per_step, "ms_per_launch": adamw_ms_per_launch,
                      "alone_ms_per_sweep": adamw_iso_ms,
                      "alone_frac": (adamw_bytes / (adamw_iso_ms / 1e3) / 1e9 / peaks["hbm"]) if adamw_iso_ms else None,
-                     "tensor_flop_per_launch": (2 * B * K_FEAT * P_PIX // len(buckets)) if fused else 0,
+                     "tensor_flop_per_launch": (2 * B * K_FEAT * P_PIX // launches_per_step) if fused else 0,
+                     "nvlink_egress_bytes_per_step": (4 * (N_PARAMS_W // world) * (world - 1)) if world > 1 else 0,
                      "peak_source": peaks["source"]},
         "gemm": {"tflops_incl_frontend_and_epilogues": gemm_tf,
                  "frac_of_bf16_sustained_peak": gemm_tf / peaks["tf_sustained"],
