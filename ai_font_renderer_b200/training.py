@@ -7,11 +7,12 @@ everything that decides WHAT is computed is kept: the 80/20 random_split with se
 loader generator (so batch composition and order equal the reference's), unweighted epoch means,
 ReduceLROnPlateau, early stopping with its shallow-copy "best state", the files written.
 
-Data parallel (one process per GPU, torch.distributed/NCCL): every rank walks the same global
-batch order and takes a contiguous slice of each batch; the loss is normalised by the GLOBAL
-batch so per-rank gradients just add; fc_output.weight.grad is all-reduced in row buckets that
-are launched as soon as the bucket's wgrad GEMM is enqueued and overlap the rest of backward;
-AdamW runs bucket by bucket as the reductions land.
+Data parallel (one process per GPU, torch.distributed): every rank walks the same global batch
+order and takes a contiguous slice of each batch; the loss is normalised by the GLOBAL batch so
+per-rank gradients just add. The optimizer over fc_output.weight is sharded by rows; its gradient
+rows are summed and its updated bf16 rows broadcast inside ONE kernel per rank over NVLink peer
+memory / NVSwitch multicast (PeerLink), overlapped with the rest of backward on a side stream; the
+33 k small parameters use one NCCL all-reduce. NCCL reduce-scatter / all-gather is the fallback.
 """
 from __future__ import annotations
 
