@@ -386,7 +386,7 @@ class AttentionFontRenderer(nn.Module):
     def fused_forward_loss(self, tokens: torch.Tensor, targets: torch.Tensor,
                            loss_count: Optional[float] = None,
                            masks: Optional[Dict[str, torch.Tensor]] = None, dropout: bool = True,
-                           sample_offset: int = 0, loss_out: Optional[torch.Tensor] = None):
+                           sample_offset: int = 0, loss_out: Optional[torch.Tensor] = None, marks=None):
         """model.py:299 + 304-306 in one pass; leaves d(loss)/d(logits) inside the library.
         targets: uint8 [B,H,W] (k/255 grey levels) or fp32 [B,H,W]. Returns the device loss scalar
         (sum of squared errors / loss_count; loss_count defaults to B*H*W = mse_loss's mean)."""
@@ -412,6 +412,8 @@ class AttentionFontRenderer(nn.Module):
         st = _stream_ptr(tokens.device)
         c.check(c.lib.afr_train_frontend(c.handle, tokens.data_ptr(), tokens.stride(0), B, S,
                                          C.byref(drop), st))
+        if marks is not None:
+            marks("frontend")        # bench.py: CUDA event between the front-end and the GEMM
         self.join_pending()          # fc_output weights of the previous data-parallel step
         c.check(c.lib.afr_train_loss(c.handle, targets.data_ptr(), kind, count, loss_out.data_ptr(), st))
         self._live = (tokens, targets, drop)   # the library reads tokens / masks again in backward
@@ -419,7 +421,7 @@ class AttentionFontRenderer(nn.Module):
             self.dropout_step += 1
         return loss_out
 
-    def fused_backward(self, row_buckets=None, on_bucket=None, wgrad_fn=None):
+    def fused_backward(self, row_buckets=None, on_bucket=None, wgrad_fn=None, marks=None):
         """loss.backward() (model.py:309): overwrites every p.grad. row_buckets: list of
         (row_begin, row_end) over fc_output's rows; on_bucket(i, begin, end) is called after the
         launches of each bucket so a data-parallel caller can start its all-reduce.
@@ -436,7 +438,13 @@ class AttentionFontRenderer(nn.Module):
                 c.check(c.lib.afr_train_wgrad(c.handle, lo, hi, st))
             if on_bucket is not None:
                 on_bucket(i, lo, hi)
-        c.check(c.lib.afr_train_dgrad(c.handle, st))
+        if marks is None:
+            c.check(c.lib.afr_train_dgrad(c.handle, st))
+        else:                        # bench.py: CUDA events around the dgrad GEMM
+            marks("dgrad_gemm_begin")
+            c.check(c.lib.afr_train_dgrad_gemm(c.handle, st))
+            marks("dgrad_gemm_end")
+            c.check(c.lib.afr_train_frontend_backward(c.handle, st))
 
     def set_coresident(self, on: bool):
         """Single GPU: the next wgrad+AdamW GEMM and dgrad GEMM launch with half-an-SM footprints

@@ -255,7 +255,9 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             optimizer.wgrad_step_rows(t_step, r0, r1)
             mark("adamw_end")
             with torch.cuda.stream(side):
+                mark("dgrad_gemm_begin")
                 model.dgrad_gemm()
+                mark("dgrad_gemm_end")
             optimizer.bias_grad_rows(r0, r1)
             mark("wgrad")
             main.wait_stream(side)
@@ -281,7 +283,7 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             mark("adamw_end")
 
         model.fused_backward(buckets, lambda i, r0, r1: mark("wgrad") if i == last else None,
-                             wgrad_fn=fused_bucket)
+                             wgrad_fn=fused_bucket, marks=marks)
         mark("dgrad")
         main.wait_stream(side)
         optimizer.step_small(t_step)
@@ -299,7 +301,7 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             optimizer.step_rows(t_step, r0, r1)
             mark("adamw_end")
 
-        model.fused_backward(buckets, after_bucket)
+        model.fused_backward(buckets, after_bucket, marks=marks)
         mark("dgrad")
         optimizer.step_small(t_step)
         optimizer.end_step()
@@ -357,7 +359,7 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             ag.wait()
 
     if has_samples:
-        model.fused_backward([(0, P)], after_wgrad)
+        model.fused_backward([(0, P)], after_wgrad, marks=marks)
     else:
         after_wgrad(0, 0, P)
     mark("dgrad")

@@ -165,6 +165,11 @@ def cpu_train_glyphs_per_sec(steps: int, warmup: int):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for every rank: the CPU arm uses all host cores anyway
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     steps = max(1, args.steps)
     value, sec = cpu_train_glyphs_per_sec(steps, max(1, args.warmup))
     cores = torch.get_num_threads()
@@ -360,11 +365,16 @@ def main():
             # traffic and SM time shrink (2 GPUs 1.65 vs 1.82 ms, 8 GPUs 1.51 vs 1.55 ms)
             args.dp_mode = "nvls-side" if PeerLink.nvls_available() else ("peer" if world == 2 else "peer-side")
         if args.dp_mode in ("peer", "peer-side", "nvls", "nvls-side"):
-            PeerLink(model, ctas=args.comm_ctas, inline=args.dp_mode in ("peer", "nvls"),
-                     nvls=args.dp_mode.startswith("nvls"))
-        else:
+            try:
+                PeerLink(model, ctas=args.comm_ctas, inline=args.dp_mode in ("peer", "nvls"),
+                         nvls=args.dp_mode.startswith("nvls"))
+            except Exception as exc:     # no symmetric memory / peer access on this system
+                sys.stderr.write(f"[bench] PeerLink unavailable ({exc}); falling back to --dp-mode nccl\n")
+                args.dp_mode = "nccl"
+                model.set_sm_limit(torch.cuda.get_device_properties(device).multi_processor_count - 32)
+        elif args.dp_mode == "nccl":
             sms = torch.cuda.get_device_properties(device).multi_processor_count
-            model.set_sm_limit(sms - int(os.environ["NCCL_MAX_CTAS"]))
+            model.set_sm_limit(sms - int(os.environ.get("NCCL_MAX_CTAS", "32")))
     n_rot = 8
     tok_h, tgt_h = fast_synthetic_batch(B * n_rot, seed=1234 + rank)
     tok_h, tgt_h = tok_h.pin_memory(), tgt_h.pin_memory()
@@ -390,7 +400,8 @@ def main():
         x, t = tok_d[s:s + B], tgt_d[s:s + B]
         if marks is not None:
             marks("start")
-        model.fused_forward_loss(x, t, loss_count=count, sample_offset=rank * B, loss_out=loss_buf[i])
+        model.fused_forward_loss(x, t, loss_count=count, sample_offset=rank * B, loss_out=loss_buf[i],
+                                 marks=marks)
         if marks is not None:
             marks("forward")
         backward_and_step(model, opt, buckets, world, marks=marks)
@@ -467,6 +478,13 @@ def main():
     adamw_ms_per_step = sum(adam_launch_ms) / args.steps
     launches_per_step = max(1, len(adam_launch_ms) // args.steps)
     phase_ms["adamw_side_stream"] = adamw_ms_per_step
+    # the two tensor-bound GEMMs by themselves (forward incl. its 5 us loss-finalize kernel)
+    fwd_gemm_ms = sum(m.ev["frontend"][0].elapsed_time(m.ev["forward"][0]) for m in step_marks) / args.steps
+    dgrad_gemm_ms = sum(m.ev["dgrad_gemm_begin"][0].elapsed_time(m.ev["dgrad_gemm_end"][0])
+                        for m in step_marks) / args.steps
+    phase_ms["frontend_forward"] = phase_ms["forward"] - fwd_gemm_ms
+    phase_ms["forward_gemm"] = fwd_gemm_ms
+    phase_ms["dgrad_gemm"] = dgrad_gemm_ms
 
     # the same sweep alone on the device (nothing else running), for reference
     iso = []
@@ -519,6 +537,7 @@ def main():
         adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
         traffic = ADAMW_TRAFFIC_NCU
     adamw_gbs = adamw_bytes / (adamw_ms_per_step / 1e3) / 1e9
+    one_gemm_tf = lambda ms: 2.0 * B * K_FEAT * P_PIX / (ms / 1e3) / 1e12
     gemm_tf = B * GEMM_FLOP_PER_GLYPH / ((phase_ms["forward"] + phase_ms["wgrad"] + phase_ms["dgrad"]) / 1e3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -543,7 +562,12 @@ def main():
         "gemm": {"tflops_incl_frontend_and_epilogues": gemm_tf,
                  "frac_of_bf16_sustained_peak": gemm_tf / peaks["tf_sustained"],
                  "frac_of_bf16_burst_peak": gemm_tf / peaks["tf_burst"],
-                 "flop_per_glyph": GEMM_FLOP_PER_GLYPH},
+                 "flop_per_glyph": GEMM_FLOP_PER_GLYPH,
+                 # the tensor-bound GEMM kernels alone (CUDA events around each launch): 2*B*K*P flop
+                 "forward_gemm": {"ms": fwd_gemm_ms, "tflops": one_gemm_tf(fwd_gemm_ms),
+                                  "frac_of_bf16_burst_peak": one_gemm_tf(fwd_gemm_ms) / peaks["tf_burst"]},
+                 "dgrad_gemm": {"ms": dgrad_gemm_ms, "tflops": one_gemm_tf(dgrad_gemm_ms),
+                                "frac_of_bf16_burst_peak": one_gemm_tf(dgrad_gemm_ms) / peaks["tf_burst"]}},
         "phase_ms": phase_ms,
         "train_tflops_whole_step": value * GEMM_FLOP_PER_GLYPH / 1e12 / world,
         "final_loss": final_loss,
