@@ -69,7 +69,8 @@ def assert_grads_close(got, want, tol_big=BF16_TOL, tol_small=BF16_TOL, label=""
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("shape,bn", [((256, 512, 256), 256), ((200, 320, 200), 128),
                                       ((1, 256, 640), 224), ((304, 1280, 304), 224),
-                                      ((1024, 2048, 1088), 192)])
+                                      ((1024, 2048, 1088), 192), ((129, 96, 72), 96),
+                                      ((257, 288, 8), 160), ((513, 32, 200), 32)])
 @pytest.mark.parametrize("tma_store", [0, 1, 2, 3])      # bit 0: TMA stores, bit 1: CTA pairs (cta_group::2)
 def test_tcgen05_gemm_matches_fp32_matmul(a_mn, b_mn, shape, bn, tma_store):
     from ai_font_renderer_b200 import _lib
