@@ -280,3 +280,23 @@ def test_cli_unknown_option_exits_1():
                          capture_output=True, text=True, cwd=REPO)
     assert res.returncode == 1
     assert "Unknown option: --bogus" in res.stdout and "Available options: --train" in res.stdout
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm of the contract): stdout is ONE JSON line with the
+    metric, config, cpu_baseline and e2e objects; everything else goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    from conftest import REPO
+    res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_glyphs_per_sec" and d["unit"] == "glyphs/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
