@@ -263,6 +263,20 @@ def measure_render(model, device, rank, world, dist, bmp_set=False):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
         res[name] = ms
+    # one string per call, the way the reference's render_strings drives the model (helpers.py:62-64)
+    single_ms = None
+    if not bmp_set:
+        one = tok_d[:1]
+        for _ in range(5):
+            model.render_u8(one)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            model.render_u8(one)
+        e1.record()
+        torch.cuda.synchronize()
+        single_ms = e0.elapsed_time(e1) / 50
     model.check_tokens_in_range()
     model.train(was_training)
     glyphs = batch * n_pass * world
@@ -270,6 +284,7 @@ def measure_render(model, device, rank, world, dist, bmp_set=False):
     return {"metric": "render_glyphs_per_sec", "unit": UNIT, "batch_per_gpu": batch,
             "passes": n_pass, "glyphs": glyphs, "value": glyphs / (res["resident"] / 1e3),
             "ms_per_pass": res["resident"] / n_pass,
+            "single_string_ms": single_ms,
             "tflops_per_gpu": glyphs / world * flop / (res["resident"] / 1e3) / 1e12,
             "e2e": {"value": glyphs / (res["e2e"] / 1e3), "unit": UNIT,
                     "h2d_bytes_per_pass": batch * 100 * 8, "d2h_bytes_per_pass": batch * P_PIX,
