@@ -77,6 +77,7 @@ SIGNATURES = {
     "afr_sync_shadow": (C.c_int, [_P, _P]),
     "afr_bind_shadow": (C.c_int, [_P, _P, _P]),
     "afr_set_sm_limit": (C.c_int, [_P, C.c_int]),
+    "afr_set_smem_reserve": (C.c_int, [_P, C.c_int]),
     "afr_shadow_index": (C.c_int, [_P]),
     "afr_shadow_commit": (C.c_int, [_P]),
     "afr_forward_eval": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_int, _P]),
@@ -103,6 +104,9 @@ SIGNATURES = {
                                         C.c_int, C.c_int, _P]),
     "afr_adamw_rows_gather_nvls": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                              C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "afr_adamw_rows_bg": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "afr_train_wgrad_to": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "afr_adamw_small": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_int64, _P]),
     "afr_train_wgrad_adamw": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -140,11 +144,17 @@ def load() -> C.CDLL:
     if not _build.is_current():
         try:
             _build.build(verbose=False)
-        except Exception as exc:  # stale-but-present library is still usable on a box without nvcc
+        except Exception as exc:
             if not os.path.exists(path):
                 raise AfrLibraryError(
                     f"{path} is missing and could not be built ({exc}). The B200 path has no "
                     "fallback: run `python -m ai_font_renderer_b200.build`.") from exc
+            # a library that does not match the sources is only used when the caller says so
+            # (AFR_ALLOW_STALE_LIB=1, e.g. a box without nvcc that received a prebuilt .so)
+            if os.environ.get("AFR_ALLOW_STALE_LIB", "0") != "1":
+                raise AfrLibraryError(
+                    f"{path} does not match the sources and could not be rebuilt ({exc}); set "
+                    "AFR_ALLOW_STALE_LIB=1 to load it anyway") from exc
     try:
         lib = C.CDLL(path)
     except OSError as exc:

@@ -49,18 +49,36 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
-    """Compile the library if sources changed. Returns the path of the .so."""
+    """Compile the library if sources changed. Returns the path of the .so.
+
+    Safe under `torchrun` (every rank may call it at once): the build runs under an exclusive file
+    lock, nvcc writes to a temporary file that is renamed over the library only when complete, and
+    a rank that waited for the lock re-checks the stamp instead of compiling again -- nobody can
+    dlopen a half-written library."""
     if not force and is_current():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print("[afr build]", " ".join(cmd), flush=True)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libafr_sm100.so")
-    with open(STAMP_PATH, "w") as f:
-        f.write(source_digest())
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():          # another process built it while we waited
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.tmp.{os.getpid()}"
+            cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            if verbose:
+                print("[afr build]", " ".join(cmd).replace(tmp, LIB_PATH), flush=True)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed building libafr_sm100.so")
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP_PATH + ".tmp", "w") as f:
+                f.write(source_digest())
+            os.replace(STAMP_PATH + ".tmp", STAMP_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -50,6 +50,7 @@ struct afr_ctx {
   bool fwd_done = false;
   bool frontend_done = false;        // afr_train_frontend ran, afr_train_loss still to come
   bool coresident = false;           // afr_set_coresident
+  int smem_reserve = 0;              // afr_set_smem_reserve: bytes per SM the GEMMs leave to a background kernel
   bool cta2 = true;                  // forward / dgrad / wgrad GEMMs run as CTA pairs (AFR_CTA2=0: single CTAs)
   long long launches = 0;
   std::string err;
@@ -342,6 +343,13 @@ int afr_set_coresident(afr_ctx* c, int on) {
   return AFR_OK;
 }
 
+int afr_set_smem_reserve(afr_ctx* c, int bytes) {
+  if (!c) return AFR_ERR_INVALID;
+  if (bytes < 0 || bytes > 96 * 1024) return fail(c, AFR_ERR_INVALID, "afr_set_smem_reserve: 0..96 KB");
+  c->smem_reserve = bytes;
+  return AFR_OK;
+}
+
 int afr_shadow_index(const afr_ctx* c) { return c ? c->shadow_cur : AFR_ERR_INVALID; }
 
 int afr_shadow_commit(afr_ctx* c) {
@@ -463,7 +471,7 @@ int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
   ep.out = c->grads.wout + static_cast<long long>(row_begin) * c->K;
   ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  ep.cta2 = c->cta2;
+  ep.cta2 = c->cta2; ep.smem_reserve = c->smem_reserve;
   const int bn = choose_bn(rows, c->K, c->sms, "AFR_BN_WGRAD", c->cta2);
   cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
                                    c->B, bn, ep, c->sms, st, nullptr, &msg);
@@ -487,7 +495,7 @@ int afr_train_dgrad_gemm(afr_ctx* c, void* stream) {
   ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   ep.compact = c->coresident ? 1 : 0;
   const char* msg = nullptr;
-  ep.cta2 = c->cta2;
+  ep.cta2 = c->cta2; ep.smem_reserve = c->smem_reserve;
   int bn = choose_bn(c->B, c->K, c->sms, "AFR_BN_DGRAD", c->cta2 && !c->coresident);
   if (c->coresident && bn > 128) bn = 128;
   cudaError_t e = launch_gemm_bf16(c->dz, c->P, false, c->wshadow_buf[c->shadow_fwd], c->K, true, c->B, c->K, c->P, bn,
@@ -508,7 +516,8 @@ int afr_train_frontend_backward(afr_ctx* c, void* stream) {
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
                                        c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
-                                       c->fstate, c->partials, c->sms, &grid, c->sms, st),
+                                       c->fstate, c->partials, c->sms, &grid, c->sms, st,
+                                       c->smem_reserve > 0),
            "frontend_backward");
   AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
            "small_grad_reduce");
@@ -612,6 +621,71 @@ int afr_adamw_rows(afr_ctx* c, double lr, double beta1, double beta2, double eps
   return AFR_OK;
 }
 
+int afr_adamw_rows_bg(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, int64_t step, int row_begin, int row_end,
+                      const float* grad_rows, int ctas, int stages, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_state || (grad_rows == nullptr && !c->has_grads))
+    return fail(c, AFR_ERR_STATE, "params / grads / adam state not bound");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
+    return fail(c, AFR_ERR_INVALID, "bad step or row range");
+  if ((static_cast<long long>(row_end - row_begin) * c->K) % 4 != 0 ||
+      (static_cast<long long>(row_begin) * c->K) % 4 != 0)
+    return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_bg: row range must cover whole 16-byte groups");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  const long long n = static_cast<long long>(row_end - row_begin) * c->K;
+  if (ctas < 1) ctas = c->num_sms;
+  if (stages < 1) stages = 4;
+  const float* g = grad_rows != nullptr ? grad_rows : c->grads.wout + off;
+  AFR_CUDA(c, launch_adamw_ring(c->params.wout + off, g, c->m.wout + off, c->v.wout + off, n, h,
+                                c->wshadow_buf[1 - c->shadow_cur] + off, ctas, stages, st),
+           "adamw_ring(fc_output.weight rows)");
+  c->launches += 1;
+  c->shadow_rows_swept += row_end - row_begin;
+  if (c->shadow_rows_swept >= c->P) {   // sweep complete: the next forward reads the new weights
+    c->shadow_cur ^= 1;
+    c->shadow_rows_swept = 0;
+    c->shadow_valid = true;
+  }
+  return AFR_OK;
+}
+
+int afr_train_wgrad_to(afr_ctx* c, int row_begin, int row_end, float* grad_rows, int with_bias,
+                       void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_wgrad_to before a training forward");
+  if (grad_rows == nullptr) return fail(c, AFR_ERR_INVALID, "afr_train_wgrad_to: grad_rows is NULL");
+  if (with_bias && !c->has_grads) return fail(c, AFR_ERR_STATE, "gradients not bound (afr_bind_grads)");
+  if (row_begin < 0 || row_end > c->P || row_begin >= row_end || (row_begin % 32) != 0 ||
+      ((row_end - row_begin) % 32) != 0)
+    return fail(c, AFR_ERR_INVALID, "row range must be 32-aligned inside [0, H*W]");
+  DeviceGuard guard(c->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = row_end - row_begin;
+  GemmEpilogue ep{};
+  ep.kind = kEpiF32;
+  ep.out = grad_rows;
+  ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
+  const char* msg = nullptr;
+  ep.cta2 = c->cta2; ep.smem_reserve = c->smem_reserve;
+  const int bn = choose_bn(rows, c->K, c->sms, "AFR_BN_WGRAD", c->cta2);
+  cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
+                                   c->B, bn, ep, c->sms, st, nullptr, &msg);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, msg) : fail_cuda(c, e, "gemm(wgrad chunk)");
+  c->launches += 1;
+  if (with_bias) {
+    AFR_CUDA(c, launch_bias_grad(c->dz + row_begin, c->B, rows, c->grad_scale, c->bias_scratch,
+                                 c->grads.bout + row_begin, st, c->P),
+             "bias_grad");
+    c->launches += 2;
+  }
+  return AFR_OK;
+}
+
 int afr_train_wgrad_adamw(afr_ctx* c, double lr, double beta1, double beta2, double eps,
                           double weight_decay, int64_t step, int row_begin, int row_end,
                           void* stream) {
@@ -638,7 +712,7 @@ int afr_train_wgrad_adamw(afr_ctx* c, double lr, double beta1, double beta2, dou
   ep.compact = c->coresident ? 1 : 0;
   // the AdamW GEMM is HBM-bound and keeps single CTAs (8 epilogue warps + 2 x 48 KB ring measured
   // faster than pairs with a 4 x 32 KB ring: 0.73 vs 0.79 ms); AFR_WA_CTA2=1 to compare
-  ep.cta2 = c->cta2 && env_int("AFR_WA_CTA2") != 0;
+  ep.cta2 = c->cta2 && env_int("AFR_WA_CTA2") != 0; ep.smem_reserve = c->smem_reserve;
   if (c->coresident && bn > 128) bn = 128;
   ep.adam_sets = env_int("AFR_WA_SETS");
   ep.adam_sub = env_int("AFR_WA_SUB");

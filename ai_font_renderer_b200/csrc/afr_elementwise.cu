@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "afr_internal.h"
+#include "afr_ptx.cuh"
 
 namespace afr {
 namespace {
@@ -41,6 +42,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
              __nv_bfloat16* __restrict__ shadow) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const AdamPairConst c(h);
   for (; i + stride < n4; i += 2 * stride) {
     const long long j = i + stride;
     float4 pa = reinterpret_cast<float4*>(p)[i], pb = reinterpret_cast<float4*>(p)[j];
@@ -48,15 +50,9 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     const float4 gb = ld_stream(reinterpret_cast<const float4*>(g) + j);
     float4 ma = reinterpret_cast<float4*>(m)[i], mb = reinterpret_cast<float4*>(m)[j];
     float4 va = reinterpret_cast<float4*>(v)[i], vb = reinterpret_cast<float4*>(v)[j];
-    adamw_elem(pa.x, ga.x, ma.x, va.x, h);
-    adamw_elem(pa.y, ga.y, ma.y, va.y, h);
-    adamw_elem(pa.z, ga.z, ma.z, va.z, h);
-    adamw_elem(pa.w, ga.w, ma.w, va.w, h);
+    adamw_quad(pa, ga, ma, va, c);
     adamw_store(p, m, v, shadow, i, pa, ma, va);
-    adamw_elem(pb.x, gb.x, mb.x, vb.x, h);
-    adamw_elem(pb.y, gb.y, mb.y, vb.y, h);
-    adamw_elem(pb.z, gb.z, mb.z, vb.z, h);
-    adamw_elem(pb.w, gb.w, mb.w, vb.w, h);
+    adamw_quad(pb, gb, mb, vb, c);
     adamw_store(p, m, v, shadow, j, pb, mb, vb);
   }
   if (i < n4) {
@@ -64,10 +60,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     const float4 gv = ld_stream(reinterpret_cast<const float4*>(g) + i);
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    adamw_elem(pv.x, gv.x, mv.x, vv.x, h);
-    adamw_elem(pv.y, gv.y, mv.y, vv.y, h);
-    adamw_elem(pv.z, gv.z, mv.z, vv.z, h);
-    adamw_elem(pv.w, gv.w, mv.w, vv.w, h);
+    adamw_quad(pv, gv, mv, vv, c);
     adamw_store(p, m, v, shadow, i, pv, mv, vv);
   }
   // scalar tail (n not a multiple of 4)
@@ -78,6 +71,129 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       p[j] = pj; m[j] = mj; v[j] = vj;
       if (shadow != nullptr) shadow[j] = __float2bfloat16_rn(pj);
     }
+  }
+}
+
+// Background form of the sweep (afr_adamw_rows_bg): a small-footprint persistent kernel meant to
+// share every SM with the compute kernels of the step (the wgrad / dgrad GEMMs, the front-end
+// backward, the next front-end forward), which leave few registers and little shared memory but
+// plenty of issue slots and all of the HBM bandwidth. The memory-level parallelism therefore
+// cannot live in registers (a thread of the plain sweep holds 8 x 16 B in flight): p, g, m, v
+// arrive through a shared-memory ring filled by 1-D bulk copies (cp.async.bulk, one elected
+// thread, mbarrier completion), kStages x 8 KB in flight per CTA whatever the thread count, and
+// the 128 threads only do LDS.128 -> adamw_elem -> streaming stores. <= 40 registers per thread
+// (5 K per CTA), 8 KB of shared memory per stage.
+constexpr int kRingThreads = 128;
+constexpr int kRingSegFloats = kRingThreads * 4;          // one float4 per thread and array
+constexpr int kRingStageBytes = 4 * kRingSegFloats * 4;   // p | g | m | v
+constexpr int kRingMaxStages = 12;
+
+__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                                  uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(ptx::smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void stg_stream_f4(float* dst, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void stg_stream_u2(void* dst, uint32_t a, uint32_t b) {
+  asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(a), "r"(b)
+               : "memory");
+}
+
+struct RingArgs {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  __nv_bfloat16* shadow;
+  long long n;        // floats, multiple of 4
+  long long nseg;     // ceil(n / kRingSegFloats)
+  AdamHyper h;
+  int stages;
+};
+
+__global__ void __launch_bounds__(kRingThreads, 12) adamw_ring_kernel(const RingArgs a) {
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stages = a.stages;
+  float* ring = reinterpret_cast<float*>(ring_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + static_cast<size_t>(stages) * kRingStageBytes);
+  uint64_t* empty = full + stages;
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full[s], kRingThreads / 32);
+      ptx::mbar_init(&empty[s], kRingThreads / 32);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  // Issuing a bulk copy costs the issuing thread a few hundred cycles (measured: one thread
+  // issuing all four copies of a stage capped a CTA at 8 KB per ~1300 cycles whatever the ring
+  // depth), so the four warps issue one array each: warp 0 = p, 1 = g, 2 = m, 3 = v.
+  const float* my_src = warp == 0 ? a.p : (warp == 1 ? a.g : (warp == 2 ? a.m : a.v));
+  const long long first = blockIdx.x, step = gridDim.x;
+  auto issue = [&](long long seg, int s) {     // lane 0 of every warp
+    const long long off = seg * kRingSegFloats;
+    const long long left = a.n - off;
+    const uint32_t bytes = static_cast<uint32_t>((left < kRingSegFloats ? left : kRingSegFloats) * 4);
+    float* dst = ring + static_cast<size_t>(s) * (kRingStageBytes / 4) + warp * kRingSegFloats;
+    ptx::mbar_arrive_expect_tx(&full[s], bytes);
+    bulk_load_1d_hint(dst, my_src + off, bytes, &full[s], ptx::kL2EvictFirst);
+  };
+  if (lane == 0) {
+    long long seg = first;
+    for (int s = 0; s < stages && seg < a.nseg; ++s, seg += step) issue(seg, s);
+  }
+
+  int s = 0;
+  uint32_t phase = 0;
+  long long it = 0;
+  for (long long seg = first; seg < a.nseg; seg += step, ++it) {
+    ptx::mbar_wait(&full[s], phase);
+    const float* src = ring + static_cast<size_t>(s) * (kRingStageBytes / 4) + 4 * tid;
+    const long long i = seg * kRingSegFloats + 4 * tid;
+    const bool live = i < a.n;
+    float4 pv = *reinterpret_cast<const float4*>(src);
+    const float4 gv = *reinterpret_cast<const float4*>(src + kRingSegFloats);
+    float4 mv = *reinterpret_cast<const float4*>(src + 2 * kRingSegFloats);
+    float4 vv = *reinterpret_cast<const float4*>(src + 3 * kRingSegFloats);
+    // the refill is an async-proxy write into memory this warp has just read: the stage is
+    // released only after every lane's four loads have returned (ptx::warp_reads_done)
+    const uint32_t z = ptx::warp_reads_done(__float_as_uint(pv.w) ^ __float_as_uint(gv.w) ^
+                                            __float_as_uint(mv.w) ^ __float_as_uint(vv.w));
+    if (lane == 0) {
+      ptx::mbar_arrive(&empty[s] + z);
+      // refill the stage released in the PREVIOUS iteration (all four warps have long arrived)
+      if (it > 0) {
+        const int ps = s == 0 ? stages - 1 : s - 1;
+        const uint32_t pphase = s == 0 ? phase ^ 1u : phase;
+        const long long nseg = seg + static_cast<long long>(stages - 1) * step;
+        if (nseg < a.nseg) {
+          ptx::mbar_wait(&empty[ps], pphase);
+          issue(nseg, ps);
+        }
+      }
+    }
+    if (live) {
+      adamw_quad(pv, gv, mv, vv, AdamPairConst(a.h));
+      stg_stream_f4(a.p + i, pv);
+      stg_stream_f4(a.m + i, mv);
+      stg_stream_f4(a.v + i, vv);
+      if (a.shadow != nullptr) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(pv.z, pv.w);
+        stg_stream_u2(a.shadow + i, *reinterpret_cast<const uint32_t*>(&lo),
+                      *reinterpret_cast<const uint32_t*>(&hi));
+      }
+    }
+    if (++s == stages) { s = 0; phase ^= 1u; }
   }
 }
 
@@ -123,10 +239,7 @@ adamw_gather_kernel(float* __restrict__ p, float* __restrict__ m, float* __restr
 #pragma unroll
     for (int q = 1; q < kMaxPeers; ++q)
       if (q < W) { s.x += g[q].x; s.y += g[q].y; s.z += g[q].z; s.w += g[q].w; }
-    adamw_elem(pv.x, s.x, mv.x, vv.x, h);
-    adamw_elem(pv.y, s.y, mv.y, vv.y, h);
-    adamw_elem(pv.z, s.z, mv.z, vv.z, h);
-    adamw_elem(pv.w, s.w, mv.w, vv.w, h);
+    adamw_quad(pv, s, mv, vv, AdamPairConst(h));
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -157,10 +270,7 @@ __device__ __forceinline__ void adamw_group_nvls(float* p, float* m, float* v, l
   float4 pv = reinterpret_cast<float4*>(p)[i];
   float4 mv = reinterpret_cast<float4*>(m)[i];
   float4 vv = reinterpret_cast<float4*>(v)[i];
-  adamw_elem(pv.x, s.x, mv.x, vv.x, h);
-  adamw_elem(pv.y, s.y, mv.y, vv.y, h);
-  adamw_elem(pv.z, s.z, mv.z, vv.z, h);
-  adamw_elem(pv.w, s.w, mv.w, vv.w, h);
+  adamw_quad(pv, s, mv, vv, AdamPairConst(h));
   reinterpret_cast<float4*>(p)[i] = pv;
   reinterpret_cast<float4*>(m)[i] = mv;
   reinterpret_cast<float4*>(v)[i] = vv;
@@ -324,6 +434,31 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
   if (blocks > static_cast<long long>(num_sms) * ctas_per_sm) blocks = static_cast<long long>(num_sms) * ctas_per_sm;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(p, g, m, v, n4, n, h, shadow);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_ring(float* p, const float* g, float* m, float* v, long long n,
+                              const AdamHyper& h, __nv_bfloat16* shadow, int ctas, int stages,
+                              cudaStream_t s) {
+  if ((n % 4) != 0 || n < 4 || ctas < 1) return cudaErrorInvalidValue;
+  if (stages < 2) stages = 2;
+  if (stages > kRingMaxStages) stages = kRingMaxStages;
+  RingArgs a{};
+  a.p = p; a.g = g; a.m = m; a.v = v; a.shadow = shadow; a.n = n;
+  a.nseg = (n + kRingSegFloats - 1) / kRingSegFloats;
+  a.h = h; a.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * kRingStageBytes + 2 * stages * sizeof(uint64_t);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(adamw_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(adamw_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  if (ctas > a.nseg) ctas = static_cast<int>(a.nseg);
+  adamw_ring_kernel<<<ctas, kRingThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 

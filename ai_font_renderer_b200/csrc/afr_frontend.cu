@@ -531,7 +531,7 @@ __host__ __device__ inline BwdSmem make_bwd_smem(int L, int vocab) {
   return s;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const FrontArgs a) {
+__device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
   extern __shared__ __align__(16) float sm[];
   const BwdSmem o = make_bwd_smem(a.L, a.vocab);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -981,6 +981,17 @@ __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const Fr
     for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = sm[o.hist + i];
 }
 
+__global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const FrontArgs a) {
+  frontend_backward_body(a);
+}
+// The same kernel capped at 112 registers (a few spills): with 13 warps of 128 registers one
+// scheduler partition of the SM holds 4 x 4096 = all 16 K of its registers and no warp of another
+// kernel fits beside it; at 112 the background AdamW sweep (afr_adamw_rows_bg, 40 registers) can
+// share the SM with the front-end backward.
+__global__ void __maxnreg__(112) frontend_backward_kernel_shared(const FrontArgs a) {
+  frontend_backward_body(a);
+}
+
 // grads[i] = sum over CTAs of partials[cta][i], fixed order.
 struct ReduceArgs {
   const float* partials;
@@ -1076,6 +1087,8 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
     e = cudaFuncSetAttribute(frontend_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(frontend_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
     configured = smem;
   }
   int grid = num_sms * 2;
@@ -1087,7 +1100,8 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
 cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, long long token_stride,
                                      int B, int S, int L, int vocab, const Dropout& drop,
                                      const float* dfeat, const float* state, float* partials,
-                                     int max_grid, int* grid_out, int num_sms, cudaStream_t stream) {
+                                     int max_grid, int* grid_out, int num_sms, cudaStream_t stream,
+                                     bool shared_sm) {
   if (S < 1 || S > L || L > kMaxL || state == nullptr) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
@@ -1101,16 +1115,20 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
   const size_t smem = frontend_backward_smem_bytes(L, vocab);
   static size_t configured = 0;
   if (smem > configured) {
-    e = cudaFuncSetAttribute(frontend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
+    for (auto kern : {frontend_backward_kernel, frontend_backward_kernel_shared}) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+    }
     configured = smem;
   }
   int grid = num_sms;
   if (grid > B) grid = B;
   if (grid > max_grid) grid = max_grid;
   *grid_out = grid;
-  frontend_backward_kernel<<<grid, kThreads, smem, stream>>>(a);
+  if (shared_sm) frontend_backward_kernel_shared<<<grid, kThreads, smem, stream>>>(a);
+  else frontend_backward_kernel<<<grid, kThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

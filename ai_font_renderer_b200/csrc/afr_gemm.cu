@@ -53,6 +53,10 @@ cudaError_t launch_impl(const GemmParams& p, int grid, cudaStream_t stream) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
     if (e != cudaSuccess) return e;
+    // every kernel of the step asks for the largest shared-memory carveout: an SM whose carveout
+    // had to change could not take a co-resident CTA of another kernel before it drained
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
   if constexpr (!CTA2) {
@@ -130,7 +134,10 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
   // compact (co-resident): tile at most 128 wide, 2 stages of 16 + 16 KB, direct stores, 256 TMEM
   // columns -- two such CTAs (this GEMM under the HBM-bound AdamW GEMM) share one SM.
   p.compact = epi.compact ? 1 : 0;
+  // shared memory left to a co-resident background kernel (afr_set_smem_reserve): shallower ring
+  const int smem_cap = kSmemOptinMax - (epi.smem_reserve > 0 ? epi.smem_reserve : 0);
   p.stages = kStages;
+  while (p.stages > 2 && gemm_smem_bytes(p.stages, kBStageBytes, kEpiBytes, false) > smem_cap) --p.stages;
   p.b_stage_bytes = kBStageBytes;
   p.epi_bytes = kEpiBytes;
   p.tmem_cols = kTmemCols;
@@ -138,7 +145,7 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     // half a B tile per CTA: the ring gets as deep as shared memory allows (6 stages of 32 KB at BN = 256)
     p.b_stage_bytes = b_mn ? ((BN / 2 + 63) / 64) * 8192 : (BN / 2) * kBK * 2;
     int stages = kMaxStages;
-    while (stages > 2 && gemm_smem_bytes(stages, p.b_stage_bytes, p.epi_bytes, false) > kSmemOptinMax) --stages;
+    while (stages > 2 && gemm_smem_bytes(stages, p.b_stage_bytes, p.epi_bytes, false) > smem_cap) --stages;
     p.stages = stages;
   }
   if (epi.compact) {
@@ -175,7 +182,7 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
     int stages = epi.adam_stages > 0 ? epi.adam_stages : (epi.compact ? 2 : kMaxStages);
     if (stages > kMaxStages) stages = kMaxStages;
     while (stages > 1 &&
-           gemm_smem_bytes(stages, p.b_stage_bytes, p.epi_bytes, p.compact != 0) > kSmemOptinMax)
+           gemm_smem_bytes(stages, p.b_stage_bytes, p.epi_bytes, p.compact != 0) > smem_cap)
       --stages;
     if (stages < 2) {
       if (err_msg) *err_msg = "gemm: fused AdamW epilogue: tile width / slab sets do not fit in shared memory";

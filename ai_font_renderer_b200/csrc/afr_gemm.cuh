@@ -300,7 +300,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     const int sets = p.adam_sets;
     uint8_t* slabs = smem_epi + (sub * 4 + q) * (sets * kAdamSlabBytes);
     uint64_t* ld_bar = adam_ld_bar + (sub * 4 + q) * kMaxAdamSets;
-    const AdamHyper h = p.hyper;
+    const AdamPairConst hc(p.hyper);
     auto chunks_of = [&](int t) {
       const int n0 = (t / p.num_m_tiles) * BN;
       return (min(BN, p.N - n0)) >> 5;
@@ -322,11 +322,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       l_row = (lt % p.num_m_tiles) * kTileM + row_base + q * 32;
     };
     load_tile_coords();
-    auto issue_next = [&]() {
+    auto issue_next = [&](uint32_t z) {     // z: 0, from ptx::warp_reads_done (orders the refill)
       if (lt >= num_tiles) return;
       if (lane == 0) {
         const int col = l_col0 + lc * 32;
-        uint8_t* dst = slabs + s_issue * kAdamSlabBytes;
+        uint8_t* dst = slabs + s_issue * kAdamSlabBytes + z;
         ptx::mbar_arrive_expect_tx(&ld_bar[s_issue], kAdamSlabBytes);
         ptx::tma_load_2d_hint(&p.tm_p, &ld_bar[s_issue], dst, col, l_row, ptx::kL2EvictFirst);
         ptx::tma_load_2d_hint(&p.tm_m, &ld_bar[s_issue], dst + kEpiWarpBufBytes, col, l_row,
@@ -338,7 +338,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       lc += nsub;
       if (lc >= l_chunks) { lc = sub; lt = next_active(lt + tile_step); load_tile_coords(); }
     };
-    for (int i = 0; i < sets; ++i) issue_next();
+    for (int i = 0; i < sets; ++i) issue_next(0u);
     int acc = 0;
     uint32_t acc_phase = 0;
     int s = 0;                              // slab set of the chunk being consumed
@@ -374,11 +374,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           }
           if (half == 1) {
             // the refill is an async-proxy write into memory this warp has just read through the
-            // generic proxy: every lane's reads must have been performed (not merely issued)
-            // before the TMA load is launched -- proxy fence per lane, then the warp barrier
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            issue_next();
+            // generic proxy: every lane's reads must have been PERFORMED (not merely issued)
+            // before the TMA load is launched. A vote over the loaded registers guarantees that
+            // (ptx::warp_reads_done); the proxy fence used here before also did, but its
+            // MEMBAR.ALL.CTA made every chunk wait for the previous chunk's streaming stores.
+            uint32_t dep = 0;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              dep ^= __float_as_uint(pv[ch].w) ^ __float_as_uint(mv[ch].w) ^ __float_as_uint(vv[ch].w);
+            issue_next(ptx::warp_reads_done(dep));
             if (++s == sets) { s = 0; s_phase ^= 1u; }
           }
           uint32_t r[16];
@@ -393,10 +397,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           uint32_t packed[8];
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            adamw_elem(pv[ch].x, __fmul_rn(__uint_as_float(r[4 * ch]), p.alpha), mv[ch].x, vv[ch].x, h);
-            adamw_elem(pv[ch].y, __fmul_rn(__uint_as_float(r[4 * ch + 1]), p.alpha), mv[ch].y, vv[ch].y, h);
-            adamw_elem(pv[ch].z, __fmul_rn(__uint_as_float(r[4 * ch + 2]), p.alpha), mv[ch].z, vv[ch].z, h);
-            adamw_elem(pv[ch].w, __fmul_rn(__uint_as_float(r[4 * ch + 3]), p.alpha), mv[ch].w, vv[ch].w, h);
+            const float4 g4 = make_float4(__fmul_rn(__uint_as_float(r[4 * ch]), p.alpha),
+                                          __fmul_rn(__uint_as_float(r[4 * ch + 1]), p.alpha),
+                                          __fmul_rn(__uint_as_float(r[4 * ch + 2]), p.alpha),
+                                          __fmul_rn(__uint_as_float(r[4 * ch + 3]), p.alpha));
+            adamw_quad(pv[ch], g4, mv[ch], vv[ch], hc);
             const __nv_bfloat162 lo = __floats2bfloat162_rn(pv[ch].x, pv[ch].y);
             const __nv_bfloat162 hi = __floats2bfloat162_rn(pv[ch].z, pv[ch].w);
             packed[2 * ch] = *reinterpret_cast<const uint32_t*>(&lo);

@@ -144,6 +144,20 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// "Every lane of this warp has RECEIVED the shared-memory values it loaded": a warp vote over a
+// word that depends on the loaded registers cannot execute before those loads have returned, so
+// whatever the elected lane does next (an async-proxy refill of the same buffer) cannot overtake a
+// read. This replaces fence.proxy.async in the read -> refill direction: that fence compiles to
+// MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the membar also waits for every global store the thread
+// still has in flight -- in a streaming kernel that serialises each iteration behind the previous
+// iteration's stores (measured: the background AdamW sweep ran at 1000 cycles per 8 KB stage).
+// Returns 0. The caller must ADD the result to the address of the barrier / buffer its next step
+// uses: ptxas deletes a vote whose result is unused, and the address dependency is what keeps the
+// refill behind the vote. (The vote is true only if all 32 lanes' words equal a magic constant.)
+__device__ __forceinline__ uint32_t warp_reads_done(uint32_t dep) {
+  return __all_sync(0xffffffffu, dep == 0x7fc5a3c1u) ? 1u : 0u;
+}
+
 // 1-D bulk copy global -> shared (no tensor map), completion on an mbarrier (complete_tx).
 // dst, src and bytes must be multiples of 16.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,

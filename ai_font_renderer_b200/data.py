@@ -49,7 +49,7 @@ def encode(strings: Sequence[str], width: int) -> torch.Tensor:
     """ord() per character, right-padded with 0 to `width` (helpers.py:57-59,163-177)."""
     arr = np.zeros((len(strings), width), dtype=np.int64)
     for i, s in enumerate(strings):
-        codes = np.frombuffer(s[:width].encode("latin-1", "replace"), dtype=np.uint8)
+        codes = [ord(c) for c in s[:width]]          # any code point, like the reference
         arr[i, : len(codes)] = codes
     return torch.from_numpy(arr)
 

@@ -17,7 +17,8 @@ from .renderer import AttentionFontRenderer, _stream_ptr
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model: AttentionFontRenderer, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, fuse_wgrad: bool = True,
-                 overlap_dgrad: bool = False):
+                 overlap_dgrad: bool = False, background: bool = False, bg_chunks: int = 4,
+                 bg_ctas: int = 0, bg_stages: int = 0):
         if not isinstance(model, AttentionFontRenderer):
             raise TypeError("FusedAdamW is bound to an ai_font_renderer_b200.AttentionFontRenderer")
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
@@ -31,6 +32,13 @@ class FusedAdamW(torch.optim.Optimizer):
         # two 128-column accumulators per kernel cost the AdamW GEMM more (0.72 -> 0.90 ms) than the
         # overlap can return (dgrad is 0.22 ms) -- so it is off by default.
         self.overlap_dgrad = overlap_dgrad
+        # single GPU: the step of fc_output.weight as a BACKGROUND sweep (afr_adamw_rows_bg) on a
+        # second stream, chunk k starting as soon as wgrad chunk k is done: the HBM-bound sweep
+        # then runs under the rest of backward (dgrad GEMM, front-end backward) and the next
+        # step's front-end forward instead of holding the GPU for itself. Takes precedence over
+        # fuse_wgrad.
+        self.background = background
+        self.bg_chunks, self.bg_ctas, self.bg_stages = bg_chunks, bg_ctas, bg_stages
         super().__init__(model._ordered_params(), dict(lr=lr, betas=betas, eps=eps,
                                                        weight_decay=weight_decay))
 
@@ -86,6 +94,15 @@ class FusedAdamW(torch.optim.Optimizer):
         ctx, _ = self._bucket
         ctx.check(ctx.lib.afr_adamw_rows(ctx.handle, *self._hyper(), t, row_begin, row_end,
                                          _stream_ptr(ctx.device)))
+
+    @torch.no_grad()
+    def step_rows_bg(self, t: int, row_begin: int, row_end: int, ctas: int = 0, stages: int = 0,
+                     grad_ptr: int = 0):
+        """step_rows as the small-footprint background kernel (afr_adamw_rows_bg) on the current
+        stream: meant for a side stream, where it shares the SMs with the compute kernels."""
+        ctx, _ = self._bucket
+        ctx.check(ctx.lib.afr_adamw_rows_bg(ctx.handle, *self._hyper(), t, row_begin, row_end,
+                                            grad_ptr or None, ctas, stages, _stream_ptr(ctx.device)))
 
     @torch.no_grad()
     def wgrad_step_rows(self, t: int, row_begin: int, row_end: int):

@@ -46,10 +46,21 @@ def strings_to_tokens(strings: Sequence[str], max_length: int, font_ids=None) ->
     return encode([s[:max_length] for s in strings], max_length)
 
 
+def check_token_range(model, tokens: torch.Tensor):
+    """nn.Embedding raises IndexError for an id outside the table (model.py:167, e.g. a character
+    >= 128 with the reference's 128-row vocabulary); so does the render path, on the host, before
+    anything is launched."""
+    vocab = model.embedding.num_embeddings
+    if tokens.numel() and (int(tokens.max()) >= vocab or int(tokens.min()) < 0):
+        raise IndexError("index out of range in self")
+
+
 @torch.no_grad()
 def render_batch_u8(model, strings: Sequence[str], device, batch_size: int = 4096) -> torch.Tensor:
     """uint8 [N,H,W] on the device, rendered in batches (no file I/O)."""
-    tokens = strings_to_tokens(strings, model.max_length).to(device)
+    tokens = strings_to_tokens(strings, model.max_length)
+    check_token_range(model, tokens)
+    tokens = tokens.to(device)
     outs = []
     for i in range(0, tokens.shape[0], batch_size):
         outs.append(model.render_u8(tokens[i:i + batch_size]))
@@ -147,6 +158,7 @@ def render_strings(model, strings, output_dir, sheet_height, sheet_width, device
             print(f"Warning: String truncated to {limit} characters: {strings[i]}")
     if strings:
         tokens = strings_to_tokens(strings, model.max_length, font_ids)
+        check_token_range(model, tokens)
         if model.training:
             # helpers.py:64 would run a dropout forward here; that only happens if a caller
             # forgot model.eval(). Keep the quirk observable:

@@ -213,6 +213,8 @@ class AttentionFontRenderer(nn.Module):
             self._ctx = c
             if getattr(self, "_sm_limit", 0):
                 c.check(c.lib.afr_set_sm_limit(c.handle, self._sm_limit))
+            if getattr(self, "_smem_reserve", 0):
+                c.check(c.lib.afr_set_smem_reserve(c.handle, self._smem_reserve))
             if self._shadow is not None and training and self._shadow[0].device == dev:
                 c.check(c.lib.afr_bind_shadow(c.handle, self._shadow[0].data_ptr(), self._shadow[1].data_ptr()))
                 c.shadow_bound = tuple(t.data_ptr() for t in self._shadow)
@@ -239,19 +241,29 @@ class AttentionFontRenderer(nn.Module):
             c.shadow_version = w._version       # rebuilt from the master at the next forward
         return self._shadow
 
-    def defer_join(self, side: torch.cuda.Stream):
-        """End of a data-parallel step: the all-gather of the updated bf16 rows is still running on
-        `side`. Nothing needs those weights before the next fc_output GEMM, so the join (stream
-        wait + activating the gathered copy) is postponed until then; the next step's front-end
-        kernel runs under the collective."""
-        self._pending = side
+    def defer_join(self, side: torch.cuda.Stream, commit: bool = True):
+        """End of a step whose fc_output.weight update is still running on `side` (data parallel:
+        the gather / AdamW / broadcast kernel; single GPU: the background AdamW sweep). Nothing
+        needs those weights before the next fc_output GEMM, so the join (stream wait + activating
+        the written copy when `commit`) is postponed until then; the next step's front-end kernel
+        runs under it."""
+        self._pending = (side, commit)
 
     def join_pending(self):
-        side = getattr(self, "_pending", None)
-        if side is not None:
+        pending = getattr(self, "_pending", None)
+        if pending is not None:
+            side, commit = pending
             torch.cuda.current_stream(side.device).wait_stream(side)
-            self.shadow_commit()
+            if commit:
+                self.shadow_commit()
             self._pending = None
+
+    def set_smem_reserve(self, nbytes: int):
+        """Shared memory per SM the wgrad / dgrad GEMMs and the front-end backward leave to the
+        background AdamW sweep (afr_set_smem_reserve); 0 = none."""
+        self._smem_reserve = nbytes
+        if self._ctx is not None:
+            self._ctx.check(self._ctx.lib.afr_set_smem_reserve(self._ctx.handle, nbytes))
 
     def set_sm_limit(self, sms: int):
         """Data parallel: leave `#SMs - sms` SMs to the collective's CTAs (0 = all SMs)."""
@@ -451,6 +463,11 @@ class AttentionFontRenderer(nn.Module):
         (afr_set_coresident) so that, enqueued on two streams, they share every SM."""
         c = self._ctx
         c.check(c.lib.afr_set_coresident(c.handle, 1 if on else 0))
+
+    def wgrad_rows(self, row_begin: int, row_end: int):
+        """d(loss)/d(fc_output.weight / .bias) for pixel rows [row_begin, row_end) (afr_train_wgrad)."""
+        c = self._ctx
+        c.check(c.lib.afr_train_wgrad(c.handle, row_begin, row_end, _stream_ptr(self.fc_output.weight.device)))
 
     def dgrad_gemm(self):
         """d(features) = d(logits) W on the current stream (first half of afr_train_dgrad)."""

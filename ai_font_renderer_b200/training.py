@@ -58,6 +58,11 @@ class TrainConfig:
     adam_buckets: int = 1            # single GPU: row buckets of the wgrad GEMM / AdamW sweep
     peer_memory: bool = True         # data parallel: NVLink peer-memory / NVLS optimizer step (PeerLink); False = NCCL
     max_steps: Optional[int] = None  # stop after this many optimizer steps (tests / smoke)
+    # The reference keeps `model.state_dict().copy()` as its "best state" (model.py:344): a shallow
+    # copy that aliases the live parameters, so both load_state_dict calls (model.py:365,370) are
+    # no-ops and the saved weights are the LAST epoch's. False reproduces that (default: drop-in);
+    # True keeps a real clone of the best epoch's weights and restores it.
+    restore_best_weights: bool = False
     quiet: bool = False
 
 
@@ -107,6 +112,9 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
 import ctypes as _C
 
 _SMALL_GROUP = None
+# shared memory per SM left to the background AdamW sweep (4 stages x 8 KB + barriers + the 1 KB the
+# hardware reserves per CTA); the wgrad / dgrad GEMM rings shrink from 6 to 5 stages for it
+BG_SMEM_RESERVE = 33 * 1024
 
 
 class PeerLink:
@@ -161,6 +169,19 @@ class PeerLink:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         model.set_sm_limit(0 if inline else sms - ctas)   # side-stream mode: the gather kernel's SMs stay free
         model._peer_link = self
+
+    @staticmethod
+    def detach(model):
+        """Undo a (partly) constructed link: plain gradient buffer and library-owned shadow copies
+        again, all SMs back to the compute kernels."""
+        model._peer_link = None
+        w = model.fc_output.weight
+        w.grad = torch.zeros_like(w)
+        model._param_grads()
+        model._rebind_param_grads()
+        model._shadow = None
+        model.own_shadow_copies()
+        model.set_sm_limit(0)
 
     @staticmethod
     def nvls_available() -> bool:
@@ -236,6 +257,44 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     wgrad = model.fc_output.weight.grad
     t_step = optimizer.begin_step()
     P = wgrad.shape[0]
+
+    if world == 1 and getattr(optimizer, "background", False):
+        # compute stream : wgrad chunk 0 | 1 | ... | dgrad GEMM | front-end backward | small AdamW
+        # side stream    :                 AdamW(chunk 0) | AdamW(chunk 1) | ...   (background
+        #                  kernel: one 128-thread CTA per SM beside whatever the compute stream runs)
+        # The join is deferred to the next fc_output GEMM, so the next front-end forward runs under
+        # the tail of the sweep too. The sweep writes the inactive bf16 copy: dgrad reads the old one.
+        model.join_pending()
+        model.set_smem_reserve(BG_SMEM_RESERVE)
+        side = model.side_stream()
+        chunks = row_buckets(P, max(1, optimizer.bg_chunks))
+        last = len(chunks) - 1
+        for i, (r0, r1) in enumerate(chunks):
+            model.wgrad_rows(r0, r1)
+            if i == last:
+                mark("wgrad")
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                if i == 0:
+                    mark("adamw_begin")
+                optimizer.step_rows_bg(t_step, r0, r1, optimizer.bg_ctas, optimizer.bg_stages)
+                if i == last:
+                    mark("adamw_end")
+        if marks is None:
+            model.dgrad_gemm()
+        else:
+            mark("dgrad_gemm_begin")
+            model.dgrad_gemm()
+            mark("dgrad_gemm_end")
+        model.frontend_backward()
+        mark("dgrad")
+        optimizer.step_small(t_step)
+        model.defer_join(side, commit=False)   # afr_adamw_rows_bg activates the copy it completed
+        optimizer.end_step()
+        mark("tail")
+        return
 
     if world == 1 and getattr(optimizer, "fuse_wgrad", False):
         # one kernel per bucket: wgrad GEMM whose epilogue applies AdamW to the fc_output.weight
@@ -404,17 +463,66 @@ class Trainer:
             self.optimizer, mode="min", factor=cfg.scheduler_factor,
             patience=cfg.scheduler_patience, min_lr=cfg.min_learning_rate)            # model.py:276-278
         self.P = cfg.sheet_height * cfg.sheet_width
-        if (self.world > 1 and cfg.peer_memory and device.type == "cuda" and self.P % self.world == 0
+        if self.world > 1:
+            if self.P % self.world != 0:
+                raise ValueError(f"data parallel: fc_output has {self.P} rows, not divisible by the world "
+                                 f"size {self.world} (the optimizer is sharded by rows)")
+            if device.type == "cuda":
+                self._check_replicas()
+        if (self.world > 1 and cfg.peer_memory and self.world <= 8 and device.type == "cuda" and self.P % self.world == 0
                 and getattr(model, "_peer_link", None) is None and PeerLink.available()):
             # collective on every rank: symmetric allocations for dW and the bf16 weight copies; the
             # NCCL reduce-scatter / all-gather form stays as the fallback
-            try:
-                PeerLink(model, nvls=PeerLink.nvls_available())
-            except Exception as exc:      # no peer access / symmetric memory on this system
-                if self.rank == 0 and not cfg.quiet:
-                    print(f"PeerLink unavailable ({exc}); using NCCL reduce-scatter / all-gather")
+            self._setup_peer_link()
         self.buckets = row_buckets(self.P, cfg.grad_buckets if self.world > 1 else cfg.adam_buckets)
         self.steps_done = 0
+
+    def _setup_peer_link(self):
+        """PeerLink construction is collective (symmetric-memory rendezvous): every rank must end
+        up on the same path. Ranks agree on NVLS availability and on success with all-reduces; if
+        any rank failed, all of them drop the link (NCCL reduce-scatter / all-gather path)."""
+        model, cfg = self.model, self.cfg
+        flag = torch.tensor([1 if PeerLink.nvls_available() else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        nvls = bool(flag.item())
+        err = None
+        try:
+            PeerLink(model, nvls=nvls)
+        except Exception as exc:      # no peer access / symmetric memory on this system
+            err = exc
+        ok = torch.tensor([0 if err is not None else 1], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            if getattr(model, "_peer_link", None) is not None:
+                PeerLink.detach(model)
+            if self.rank == 0 and not cfg.quiet:
+                print(f"PeerLink unavailable ({err or 'failed on another rank'}); "
+                      "using NCCL reduce-scatter / all-gather")
+
+    def _check_replicas(self):
+        """Data parallel needs identical replicas: same initial parameters and the same dropout
+        key on every rank (a caller that seeds ranks differently would silently diverge). Rank 0's
+        values are broadcast; a mismatch is reported once."""
+        model = self.model
+        flat = torch.cat([p.detach().reshape(-1)[:4096].float() for p in model._ordered_params()])
+        mine = torch.cat([flat, torch.tensor([float(model.dropout_seed % (1 << 24)),
+                                              float(model.dropout_step)], device=flat.device)])
+        ref = mine.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1 if torch.equal(ref, mine) else 0], device=self.device)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if not bool(same.item()):
+            if self.rank == 0 and not self.cfg.quiet:
+                print("data parallel: replicas differ at start-up; broadcasting rank 0's parameters "
+                      "and dropout key")
+            for p in model._ordered_params():
+                dist.broadcast(p.data, 0)
+            key = torch.tensor([model.dropout_seed & 0x7FFFFFFFFFFFFFFF, model.dropout_step],
+                               dtype=torch.int64, device=self.device)
+            dist.broadcast(key, 0)
+            model.dropout_seed, model.dropout_step = int(key[0].item()), int(key[1].item())
+            if model._ctx is not None:
+                model._ctx.shadow_version = None      # the bf16 copy is rebuilt from the new master
 
     # ------------------------------------------------------------------ one optimizer step
     def train_batch(self, idx: torch.Tensor, loss_slot: torch.Tensor):
@@ -429,10 +537,15 @@ class Trainer:
         if hi > lo:
             model.fused_forward_loss(x, t, loss_count=count, sample_offset=lo, loss_out=loss_slot)
         else:   # this rank has no sample of a ragged last batch: contribute zeros
+            # the previous step's gather kernel (side stream) may still be reading this rank's
+            # peer-mapped dW buffer: join it BEFORE the buffer is zeroed on the compute stream
+            model.join_pending()
             loss_slot.zero_()
             for p in model._ordered_params():
                 if p.grad is not None:
                     p.grad.zero_()
+            if model.training:
+                model.dropout_step += 1     # keep the dropout stream in step with the other ranks
         backward_and_step(model, self.optimizer, self.buckets, self.world, has_samples=hi > lo)
         self.steps_done += 1
 
@@ -500,7 +613,11 @@ class Trainer:
             if is_best:
                 best_val_loss = avg_val_loss
                 patience_counter = 0
-                best_model_state = model.state_dict().copy()   # shallow, as in the reference
+                if cfg.restore_best_weights:
+                    self.gather_master()          # row-sharded optimizer: complete fp32 master first
+                    best_model_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+                else:
+                    best_model_state = model.state_dict().copy()   # shallow, as in the reference
             else:
                 patience_counter += 1
             lr_now = self.optimizer.param_groups[0]["lr"]
@@ -518,12 +635,12 @@ class Trainer:
                 say(f"Epoch {epoch}, New best validation loss: {avg_val_loss:.6f}")
             if patience_counter >= cfg.early_stopping_patience:         # model.py:362-366
                 say(f"Early stopping at epoch {epoch}, Best Val Loss: {best_val_loss:.6f}")
-                model.load_state_dict(best_model_state)
+                self._load_best(best_model_state)
                 break
             if cfg.max_steps is not None and self.steps_done >= cfg.max_steps:
                 break
         if best_model_state is not None and patience_counter < cfg.early_stopping_patience:
-            model.load_state_dict(best_model_state)                     # model.py:369-371
+            self._load_best(best_model_state)                           # model.py:369-371
             say(f"Training completed, Best Val Loss: {best_val_loss:.6f}")
         self.gather_master()
         if self.rank == 0 and cfg.output_dir:
@@ -531,6 +648,13 @@ class Trainer:
             self._write_results(final_epoch, best_val_loss, patience_counter)
         self.history = history
         return model
+
+    def _load_best(self, best_model_state):
+        model = self.model
+        model.join_pending()
+        model.load_state_dict(best_model_state)
+        if self.cfg.restore_best_weights and model._ctx is not None:
+            model._ctx.shadow_version = None      # weights really changed: rebuild the bf16 copy
 
     @torch.no_grad()
     def gather_master(self):

@@ -55,10 +55,19 @@ def image_to_binary_array(image_path):
 
 
 def load_string_dataset(data_dir="train_input", num_samples=50000, sheet_height=80, sheet_width=240):
-    """helpers.py:125-181. Returns TensorDataset(int64 [N,Lmax], targets [N,H,W]); the sheets are
-    kept as the lossless uint8 grey levels (a quarter of the reference's fp32 footprint) -- the
-    trainer and the kernels compare against u8/255.0f, which is bit-identical to the fp32 array."""
+    """helpers.py:125-181, same contract: TensorDataset(int64 [N,Lmax], float32 [N,H,W] in [0,1]).
+    (train_attention_model converts the sheets back to the lossless uint8 grey levels they came
+    from -- `u8 / 255.0f` is bit-identical to this array -- before moving them to the device.)"""
     print(f"Loading {num_samples} samples from {data_dir}...")
     tokens, targets = load_string_dataset_u8(data_dir, num_samples, sheet_height, sheet_width)
     print(f"Dataset loading complete: {num_samples} samples with dimensions {sheet_height}x{sheet_width}")
-    return data.TensorDataset(tokens, targets)
+    return data.TensorDataset(tokens, targets.to(torch.float32) / 255.0)
+
+
+def load_string_dataset_compact(data_dir="train_input", num_samples=50000, sheet_height=80, sheet_width=240):
+    """The same files as (tokens int64 [N,Lmax], uint8 [N,H,W]): a quarter of the fp32 footprint
+    (2.9 GB instead of 11.5 GB for 150k samples). What `python model.py --train` itself uses."""
+    print(f"Loading {num_samples} samples from {data_dir}...")
+    tokens, targets = load_string_dataset_u8(data_dir, num_samples, sheet_height, sheet_width)
+    print(f"Dataset loading complete: {num_samples} samples with dimensions {sheet_height}x{sheet_width}")
+    return tokens, targets

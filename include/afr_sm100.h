@@ -128,6 +128,10 @@ int afr_bind_shadow(afr_ctx* ctx, void* copy0, void* copy1);
  * A data-parallel caller therefore leaves the collective its SMs: the persistent kernels launch
  * at most `sms` CTAs (values outside [1, #SMs] restore the default, all SMs). */
 int afr_set_sm_limit(afr_ctx* ctx, int sms);
+/* Shared memory (bytes per SM, 0..96 KB) the GEMM launches leave free -- their operand rings get
+ * shallower -- so that a background kernel (afr_adamw_rows_bg: stages x 8 KB + 1 KB) finds room
+ * beside them on every SM. 0 restores the full-depth rings. */
+int afr_set_smem_reserve(afr_ctx* ctx, int bytes);
 int afr_shadow_index(const afr_ctx* ctx);
 int afr_shadow_commit(afr_ctx* ctx);
 
@@ -211,6 +215,24 @@ int afr_adamw_rows_gather_nvls(afr_ctx* ctx, double lr, double beta1, double bet
                                double weight_decay, int64_t step, int row_begin, int row_end,
                                const void* grad_multicast, void* shadow_multicast, int ctas,
                                void* stream);
+/* afr_adamw_rows as a BACKGROUND kernel: a persistent launch of `ctas` small CTAs (128 threads,
+ * <= 40 registers, `stages` x 8 KB of shared memory; 0 = one CTA per SM / 4 stages) that streams
+ * p / g / m / v through a bulk-copy ring, so that -- enqueued on its own stream -- it shares every
+ * SM with the compute kernels of the step (GEMMs, front-end kernels: registers and shared memory
+ * are theirs, the HBM bandwidth is idle) instead of taking the GPU for itself. Bit-identical to
+ * afr_adamw_rows. grad_rows: the gradient of rows [row_begin,row_end) ([rows, 64*max_length] fp32,
+ * e.g. the L2-resident chunk afr_train_wgrad_to has just written), or NULL for the bound
+ * fc_output.weight.grad. Replaces optimizer.step() (model.py:310) for those rows. */
+int afr_adamw_rows_bg(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, int64_t step, int row_begin, int row_end,
+                      const float* grad_rows, int ctas, int stages, void* stream);
+/* afr_train_wgrad into caller memory: d(loss)/d(fc_output.weight[row_begin:row_end]) is written to
+ * grad_rows ([rows, 64*max_length] fp32) instead of the bound gradient tensor, so a caller can
+ * cycle a few chunk buffers that stay in the 126 MB L2 between this GEMM and the optimizer kernel
+ * that consumes them (the 491 MB gradient of model.py:309 is then never in HBM as a whole).
+ * with_bias != 0 also writes fc_output.bias.grad[row_begin:row_end] (bound gradients). */
+int afr_train_wgrad_to(afr_ctx* ctx, int row_begin, int row_end, float* grad_rows, int with_bias,
+                       void* stream);
 int afr_adamw_small(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream);
 /* loss.backward() w.r.t. fc_output.weight / .bias (model.py:309) AND optimizer.step() of

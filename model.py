@@ -29,7 +29,8 @@ from ai_font_renderer_b200.renderer import (AttentionFontRenderer, SHEET_HEIGHT,
                                             MAX_CHARS_PER_SHEET, EMBEDDING_DIM, DROPOUT_RATE,
                                             NUM_ATTENTION_HEADS)
 from ai_font_renderer_b200.training import TrainConfig, train_attention_model as _train
-from helpers import render_strings, save_model, load_model, load_string_dataset, MODEL_FILENAME
+from helpers import (render_strings, save_model, load_model, load_string_dataset,  # noqa: F401
+                     load_string_dataset_compact, MODEL_FILENAME)
 
 NUM_SAMPLES = 150000
 OUTPUT_DIR = "train_output_" + datetime.datetime.now().strftime("%m_%d_%H_%M_%S")
@@ -119,14 +120,16 @@ def train_string_renderer(argv=()):
     _require_gpu()
     num_samples = _flag(argv, "--samples", NUM_SAMPLES)
     print("Creating sheet dataset...")
-    if "--synthetic" in argv:
+    n_fonts = _flag(argv, "--fonts", 0)
+    over_fonts = {}
+    if n_fonts > 0:
+        pass        # the multi-font loaders below build the dataset (tokens carry the font)
+    elif "--synthetic" in argv:
         from ai_font_renderer_b200.data import fast_synthetic_batch
         dataset = fast_synthetic_batch(num_samples, MAX_CHARS_PER_SHEET, SHEET_HEIGHT, SHEET_WIDTH)
     else:
-        dataset = load_string_dataset(data_dir="train_input", num_samples=num_samples,
-                                      sheet_height=SHEET_HEIGHT, sheet_width=SHEET_WIDTH)
-    n_fonts = _flag(argv, "--fonts", 0)
-    over_fonts = {}
+        dataset = load_string_dataset_compact(data_dir="train_input", num_samples=num_samples,
+                                              sheet_height=SHEET_HEIGHT, sheet_width=SHEET_WIDTH)
     if n_fonts > 0:
         from ai_font_renderer_b200.data import (dataset_texts, encode_with_font, load_multifont_dataset_u8,
                                                 synthetic_sheets)
@@ -173,9 +176,18 @@ if __name__ == "__main__":
                 os.makedirs(OUTPUT_DIR, exist_ok=True)
             model = train_string_renderer(sys.argv[2:])
             if int(os.environ.get("RANK", "0")) == 0:
-                save_model(model)
-                render_strings(model, test_strings, output_dir=OUTPUT_DIR, sheet_height=SHEET_HEIGHT,
-                               sheet_width=SHEET_WIDTH, device=device)
+                n_fonts = _flag(sys.argv[2:], "--fonts", 0)
+                if n_fonts > 0:
+                    # a multi-font model (vocabulary 128 + N, one more position) is not loadable by
+                    # plain `python model.py`: it gets its own file name and is rendered with font ids
+                    save_model(model, f"font_renderer_{n_fonts}fonts.pth")
+                    render_strings(model, test_strings, output_dir=OUTPUT_DIR, sheet_height=SHEET_HEIGHT,
+                                   sheet_width=SHEET_WIDTH, device=device,
+                                   font_ids=[i % n_fonts for i in range(len(test_strings))])
+                else:
+                    save_model(model)
+                    render_strings(model, test_strings, output_dir=OUTPUT_DIR, sheet_height=SHEET_HEIGHT,
+                                   sheet_width=SHEET_WIDTH, device=device)
         else:
             print(f"Unknown option: {sys.argv[1]}")
             print("Available options: --train")

@@ -101,9 +101,17 @@ def test_offline_dataset_generator_follows_generate_font_ts_conventions(tmp_path
     assert 0.005 < float((grey < 255).mean()) < 0.25
     for line in fontgen.wrap_text(font, texts[3], 240):
         assert font.getlength(line) <= 240 or " " not in line
+    # the reference's contract (helpers.py:177-181): int64 tokens, float32 sheets in [0, 1]
     tokens, targets = helpers.load_string_dataset(str(d), 6).tensors
-    assert targets.shape == (6, 80, 240) and targets.dtype == torch.uint8
+    assert targets.shape == (6, 80, 240) and targets.dtype == torch.float32
+    assert float(targets.min()) >= 0.0 and float(targets.max()) == 1.0
     assert tokens.shape[0] == 6 and int(tokens[0, 0]) == ord(texts[0][0])
+    # the compact form the CLI uses, and the lossless way back the trainer takes
+    from ai_font_renderer_b200.data import targets_as_u8
+    tok2, u8 = helpers.load_string_dataset_compact(str(d), 6)
+    assert u8.dtype == torch.uint8 and torch.equal(tok2, tokens)
+    assert torch.equal(targets_as_u8(targets), u8)
+    assert torch.equal(u8.float() / 255.0, targets)
 
 
 def test_font_control_token_encoding_and_multifont_loader(tmp_path):
@@ -161,7 +169,7 @@ def test_load_string_dataset_conventions_and_errors(tmp_path):
     ds = helpers.load_string_dataset(str(d), 3, 8, 32)
     tok, tgt = ds.tensors
     assert tok.shape == (3, 11) and tok.dtype == torch.int64 and tok[0].tolist() == [65, 66] + [0] * 9
-    assert np.array_equal(tgt.numpy(), imgs)
+    assert tgt.dtype == torch.float32 and np.array_equal(tgt.numpy(), imgs.astype(np.float32) / 255.0)   # helpers.py:121
     with pytest.raises(ValueError):
         helpers.load_string_dataset(str(d), 4, 8, 32)
     os.remove(d / "2.bmp")
