@@ -165,7 +165,8 @@ int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, i
                  const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32 = nullptr) {
   float* state = save_state ? c->fstate : nullptr;
   AFR_CUDA(c, launch_frontend_forward(c->params, tokens, stride, B, S, c->cfg.max_length,
-                                      c->cfg.vocab, drop, c->feats, state, c->sms, st, feats_f32),
+                                      c->cfg.vocab, drop, c->feats, state, c->sms, st, feats_f32,
+                                      save_state && c->smem_reserve > 0),
            "frontend_forward");
   c->launches += 1;
   c->state_valid = state != nullptr;
@@ -471,7 +472,7 @@ int afr_train_wgrad(afr_ctx* c, int row_begin, int row_end, void* stream) {
   ep.out = c->grads.wout + static_cast<long long>(row_begin) * c->K;
   ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
-  ep.cta2 = c->cta2; ep.smem_reserve = c->smem_reserve;
+  ep.cta2 = c->cta2;
   const int bn = choose_bn(rows, c->K, c->sms, "AFR_BN_WGRAD", c->cta2);
   cudaError_t e = launch_gemm_bf16(c->dz + row_begin, c->P, true, c->feats, c->K, true, rows, c->K,
                                    c->B, bn, ep, c->sms, st, nullptr, &msg);

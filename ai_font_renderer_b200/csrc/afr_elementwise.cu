@@ -76,25 +76,28 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 
 // Background form of the sweep (afr_adamw_rows_bg): a small-footprint persistent kernel meant to
 // share every SM with the compute kernels of the step (the wgrad / dgrad GEMMs, the front-end
-// backward, the next front-end forward), which leave few registers and little shared memory but
-// plenty of issue slots and all of the HBM bandwidth. The memory-level parallelism therefore
-// cannot live in registers (a thread of the plain sweep holds 8 x 16 B in flight): p, g, m, v
-// arrive through a shared-memory ring filled by 1-D bulk copies (cp.async.bulk, one elected
-// thread, mbarrier completion), kStages x 8 KB in flight per CTA whatever the thread count, and
-// the 128 threads only do LDS.128 -> adamw_elem -> streaming stores. <= 40 registers per thread
-// (5 K per CTA), 8 KB of shared memory per stage.
+// backward), which leave few registers and little shared memory but plenty of issue slots and
+// all of the HBM bandwidth. The memory-level parallelism therefore cannot live in registers (a
+// thread of the plain sweep holds 8 x 16 B in flight): every thread streams its own 16-byte
+// groups of p, g, m, v through a private slot of a shared-memory ring with cp.async (LDGSTS,
+// L2 only), kStages - 1 groups of 4 x 16 B in flight per thread, and only does LDS.128 ->
+// adamw_quad -> streaming stores. No barrier of any kind: a thread reads only what it copied
+// itself (cp.async.wait_group). 128 threads, <= 40 registers (5 K per CTA), 8 KB per stage.
+// (A first version filled the ring with 2 KB cp.async.bulk copies + mbarriers: a CTA then
+// sustained only ~8 B/clk whatever the ring depth -- see profiles/r02_notes.md.)
 constexpr int kRingThreads = 128;
 constexpr int kRingSegFloats = kRingThreads * 4;          // one float4 per thread and array
 constexpr int kRingStageBytes = 4 * kRingSegFloats * 4;   // p | g | m | v
-constexpr int kRingMaxStages = 12;
 
-__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
-                                                  uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-      "[%0], [%1], %2, [%3], %4;" ::"r"(ptx::smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(ptx::smem_u32(bar)), "l"(policy)
-      : "memory");
+// (no L2::cache_hint: LDGSTS faulted with "illegal instruction" on the hand-encoded policy words
+// the TMA loads accept)
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void stg_stream_f4(float* dst, const float4& v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
@@ -115,74 +118,45 @@ struct RingArgs {
   long long n;        // floats, multiple of 4
   long long nseg;     // ceil(n / kRingSegFloats)
   AdamHyper h;
-  int stages;
 };
 
+template <int kStages>
 __global__ void __launch_bounds__(kRingThreads, 12) adamw_ring_kernel(const RingArgs a) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int stages = a.stages;
-  float* ring = reinterpret_cast<float*>(ring_smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + static_cast<size_t>(stages) * kRingStageBytes);
-  uint64_t* empty = full + stages;
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) {
-      ptx::mbar_init(&full[s], kRingThreads / 32);
-      ptx::mbar_init(&empty[s], kRingThreads / 32);
-    }
-    ptx::fence_mbar_init();
-  }
-  __syncthreads();
-
-  // Issuing a bulk copy costs the issuing thread a few hundred cycles (measured: one thread
-  // issuing all four copies of a stage capped a CTA at 8 KB per ~1300 cycles whatever the ring
-  // depth), so the four warps issue one array each: warp 0 = p, 1 = g, 2 = m, 3 = v.
-  const float* my_src = warp == 0 ? a.p : (warp == 1 ? a.g : (warp == 2 ? a.m : a.v));
+  const int tid = threadIdx.x;
+  const uint32_t slot = ptx::smem_u32(ring_smem) + 16u * tid;
   const long long first = blockIdx.x, step = gridDim.x;
-  auto issue = [&](long long seg, int s) {     // lane 0 of every warp
-    const long long off = seg * kRingSegFloats;
-    const long long left = a.n - off;
-    const uint32_t bytes = static_cast<uint32_t>((left < kRingSegFloats ? left : kRingSegFloats) * 4);
-    float* dst = ring + static_cast<size_t>(s) * (kRingStageBytes / 4) + warp * kRingSegFloats;
-    ptx::mbar_arrive_expect_tx(&full[s], bytes);
-    bulk_load_1d_hint(dst, my_src + off, bytes, &full[s], ptx::kL2EvictFirst);
-  };
-  if (lane == 0) {
-    long long seg = first;
-    for (int s = 0; s < stages && seg < a.nseg; ++s, seg += step) issue(seg, s);
-  }
-
-  int s = 0;
-  uint32_t phase = 0;
-  long long it = 0;
-  for (long long seg = first; seg < a.nseg; seg += step, ++it) {
-    ptx::mbar_wait(&full[s], phase);
-    const float* src = ring + static_cast<size_t>(s) * (kRingStageBytes / 4) + 4 * tid;
+  // one commit group per segment of this CTA's sequence (empty past the end: uniform counting)
+  auto issue = [&](long long seg, int s) {
     const long long i = seg * kRingSegFloats + 4 * tid;
-    const bool live = i < a.n;
-    float4 pv = *reinterpret_cast<const float4*>(src);
-    const float4 gv = *reinterpret_cast<const float4*>(src + kRingSegFloats);
-    float4 mv = *reinterpret_cast<const float4*>(src + 2 * kRingSegFloats);
-    float4 vv = *reinterpret_cast<const float4*>(src + 3 * kRingSegFloats);
-    // the refill is an async-proxy write into memory this warp has just read: the stage is
-    // released only after every lane's four loads have returned (ptx::warp_reads_done)
-    const uint32_t z = ptx::warp_reads_done(__float_as_uint(pv.w) ^ __float_as_uint(gv.w) ^
-                                            __float_as_uint(mv.w) ^ __float_as_uint(vv.w));
-    if (lane == 0) {
-      ptx::mbar_arrive(&empty[s] + z);
-      // refill the stage released in the PREVIOUS iteration (all four warps have long arrived)
-      if (it > 0) {
-        const int ps = s == 0 ? stages - 1 : s - 1;
-        const uint32_t pphase = s == 0 ? phase ^ 1u : phase;
-        const long long nseg = seg + static_cast<long long>(stages - 1) * step;
-        if (nseg < a.nseg) {
-          ptx::mbar_wait(&empty[ps], pphase);
-          issue(nseg, ps);
-        }
-      }
+    if (seg < a.nseg && i < a.n) {
+      const uint32_t dst = slot + static_cast<uint32_t>(s) * kRingStageBytes;
+      cp_async_16(dst, a.p + i);
+      cp_async_16(dst + 4 * kRingSegFloats, a.g + i);
+      cp_async_16(dst + 8 * kRingSegFloats, a.m + i);
+      cp_async_16(dst + 12 * kRingSegFloats, a.v + i);
     }
-    if (live) {
-      adamw_quad(pv, gv, mv, vv, AdamPairConst(a.h));
+    cp_async_commit();
+  };
+  {
+    long long seg = first;
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s, seg += step) issue(seg, s);
+  }
+  int s = 0;
+  for (long long seg = first; seg < a.nseg; seg += step) {
+    // refill the slot this thread read in the previous iteration (its values were consumed by
+    // that iteration's arithmetic, so the loads have long returned)
+    issue(seg + static_cast<long long>(kStages - 1) * step, s == 0 ? kStages - 1 : s - 1);
+    cp_async_wait<kStages - 1>();
+    const long long i = seg * kRingSegFloats + 4 * tid;
+    if (i < a.n) {
+      const uint32_t src = slot + static_cast<uint32_t>(s) * kRingStageBytes;
+      float4 pv = ptx::lds_f4(src);
+      const float4 gv = ptx::lds_f4(src + 4 * kRingSegFloats);
+      float4 mv = ptx::lds_f4(src + 8 * kRingSegFloats);
+      float4 vv = ptx::lds_f4(src + 12 * kRingSegFloats);
+      adamw_quad(pv, gv, mv, vv, AdamPairConst(a.h));   // constants straight from the constant bank
       stg_stream_f4(a.p + i, pv);
       stg_stream_f4(a.m + i, mv);
       stg_stream_f4(a.v + i, vv);
@@ -193,8 +167,9 @@ __global__ void __launch_bounds__(kRingThreads, 12) adamw_ring_kernel(const Ring
                       *reinterpret_cast<const uint32_t*>(&hi));
       }
     }
-    if (++s == stages) { s = 0; phase ^= 1u; }
+    if (++s == kStages) s = 0;
   }
+  cp_async_wait<0>();
 }
 
 // Row-sharded data parallel AdamW with the two collectives folded in (training.py): this rank
@@ -437,29 +412,38 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
   return cudaGetLastError();
 }
 
+template <int kStages>
+cudaError_t launch_ring_impl(const RingArgs& a, int ctas, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(kStages) * kRingStageBytes;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(adamw_ring_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(adamw_ring_kernel<kStages>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  adamw_ring_kernel<kStages><<<ctas, kRingThreads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_adamw_ring(float* p, const float* g, float* m, float* v, long long n,
                               const AdamHyper& h, __nv_bfloat16* shadow, int ctas, int stages,
                               cudaStream_t s) {
   if ((n % 4) != 0 || n < 4 || ctas < 1) return cudaErrorInvalidValue;
-  if (stages < 2) stages = 2;
-  if (stages > kRingMaxStages) stages = kRingMaxStages;
   RingArgs a{};
   a.p = p; a.g = g; a.m = m; a.v = v; a.shadow = shadow; a.n = n;
   a.nseg = (n + kRingSegFloats - 1) / kRingSegFloats;
-  a.h = h; a.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * kRingStageBytes + 2 * stages * sizeof(uint64_t);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(adamw_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(adamw_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  a.h = h;
   if (ctas > a.nseg) ctas = static_cast<int>(a.nseg);
-  adamw_ring_kernel<<<ctas, kRingThreads, smem, s>>>(a);
-  return cudaGetLastError();
+  // ring depth: 2, 3, 4, 6, 8 or 12 stages of 8 KB (rounded down to the next one built)
+  if (stages >= 12) return launch_ring_impl<12>(a, ctas, s);
+  if (stages >= 8) return launch_ring_impl<8>(a, ctas, s);
+  if (stages >= 6) return launch_ring_impl<6>(a, ctas, s);
+  if (stages >= 4) return launch_ring_impl<4>(a, ctas, s);
+  if (stages == 3) return launch_ring_impl<3>(a, ctas, s);
+  return launch_ring_impl<2>(a, ctas, s);
 }
 
 cudaError_t launch_adamw_gather(float* p, float* m, float* v, long long n, const AdamHyper& h,

@@ -195,7 +195,7 @@ __host__ __device__ inline FwdSmem make_fwd_smem(int L) {
   return s;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const FrontArgs a) {
+__device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
   extern __shared__ __align__(16) float sm[];
   const FwdSmem o = make_fwd_smem(a.L);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -491,6 +491,16 @@ __global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const Fro
     AFR_TICK(9);
   }
   AFR_TICK_FLUSH(0);
+}
+
+__global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const FrontArgs a) {
+  frontend_forward_body(a);
+}
+// Capped at 64 registers (72 otherwise; a few spills): two CTAs of 13 warps put 7 warps on two
+// of the SM's four scheduler partitions, 7 x 72 x 32 registers leave no room there for a warp of
+// another kernel; at 64 the background AdamW sweep's CTA (4 warps x 40 registers) fits beside both.
+__global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a) {
+  frontend_forward_body(a);
 }
 
 // =========================================================================== backward kernel
@@ -1070,7 +1080,7 @@ size_t frontend_backward_smem_bytes(int L, int vocab) {
 cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, long long token_stride,
                                     int B, int S, int L, int vocab, const Dropout& drop,
                                     __nv_bfloat16* feats, float* state, int num_sms,
-                                    cudaStream_t stream, float* feats_f32) {
+                                    cudaStream_t stream, float* feats_f32, bool shared_sm) {
   if (S < 1 || S > L || L > kMaxL) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
@@ -1084,16 +1094,18 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
   const size_t smem = static_cast<size_t>(make_fwd_smem(L).total) * 4;
   static size_t configured = 0;
   if (smem > configured) {
-    e = cudaFuncSetAttribute(frontend_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(frontend_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) return e;
+    for (auto kern : {frontend_forward_kernel, frontend_forward_kernel_shared}) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+    }
     configured = smem;
   }
   int grid = num_sms * 2;
   if (grid > B) grid = B;
-  frontend_forward_kernel<<<grid, kThreads, smem, stream>>>(a);
+  if (shared_sm) frontend_forward_kernel_shared<<<grid, kThreads, smem, stream>>>(a);
+  else frontend_forward_kernel<<<grid, kThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

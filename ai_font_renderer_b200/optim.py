@@ -17,7 +17,7 @@ from .renderer import AttentionFontRenderer, _stream_ptr
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model: AttentionFontRenderer, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, fuse_wgrad: bool = True,
-                 overlap_dgrad: bool = False, background: bool = False, bg_chunks: int = 4,
+                 overlap_dgrad: bool = False, background: bool = False, bg_chunks: int = 1,
                  bg_ctas: int = 0, bg_stages: int = 0):
         if not isinstance(model, AttentionFontRenderer):
             raise TypeError("FusedAdamW is bound to an ai_font_renderer_b200.AttentionFontRenderer")

@@ -112,9 +112,10 @@ def row_buckets(P: int, n: int) -> List[Tuple[int, int]]:
 import ctypes as _C
 
 _SMALL_GROUP = None
-# shared memory per SM left to the background AdamW sweep (4 stages x 8 KB + barriers + the 1 KB the
-# hardware reserves per CTA); the wgrad / dgrad GEMM rings shrink from 6 to 5 stages for it
-BG_SMEM_RESERVE = 33 * 1024
+# ring depth of the background AdamW sweep: stages x 8 KB (+ the 1 KB the hardware reserves per CTA)
+# of every SM's shared memory are left to it by the dgrad GEMM (ring of 5 instead of 6 stages) and
+# fit beside the front-end kernels' 184 / 2 x 78 KB
+BG_DEFAULT_STAGES = 4
 
 
 class PeerLink:
@@ -259,13 +260,17 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
     P = wgrad.shape[0]
 
     if world == 1 and getattr(optimizer, "background", False):
-        # compute stream : wgrad chunk 0 | 1 | ... | dgrad GEMM | front-end backward | small AdamW
-        # side stream    :                 AdamW(chunk 0) | AdamW(chunk 1) | ...   (background
-        #                  kernel: one 128-thread CTA per SM beside whatever the compute stream runs)
+        # compute stream : wgrad | dgrad GEMM | front-end backward | small AdamW | next front-end fwd
+        # side stream    :         AdamW sweep over fc_output.weight (background kernel: one
+        #                          128-thread CTA per SM beside whatever the compute stream runs)
         # The join is deferred to the next fc_output GEMM, so the next front-end forward runs under
-        # the tail of the sweep too. The sweep writes the inactive bf16 copy: dgrad reads the old one.
+        # the tail of the sweep too. The sweep writes the inactive bf16 copy: dgrad reads the old
+        # one. bg_chunks > 1 splits wgrad / sweep into row chunks (the sweep of chunk k starts
+        # under wgrad chunk k + 1); measured slower: the wgrad GEMM and the sweep are both
+        # HBM-heavy and gain nothing from sharing the GPU (tools/overlap_probe2.py).
         model.join_pending()
-        model.set_smem_reserve(BG_SMEM_RESERVE)
+        stages = optimizer.bg_stages or BG_DEFAULT_STAGES
+        model.set_smem_reserve(stages * 8192 + 1024)
         side = model.side_stream()
         chunks = row_buckets(P, max(1, optimizer.bg_chunks))
         last = len(chunks) - 1
@@ -279,7 +284,7 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
                 side.wait_event(ev)
                 if i == 0:
                     mark("adamw_begin")
-                optimizer.step_rows_bg(t_step, r0, r1, optimizer.bg_ctas, optimizer.bg_stages)
+                optimizer.step_rows_bg(t_step, r0, r1, optimizer.bg_ctas, stages)
                 if i == last:
                     mark("adamw_end")
         if marks is None:
@@ -588,7 +593,7 @@ class Trainer:
         best_model_state = None
         n_train, n_val = len(self.train_loader), len(self.val_loader)
         slots = torch.zeros(max(n_train, n_val, 1), dtype=torch.float32, device=self.device)
-        history = []
+        history, lr_trace = [], []
         epoch = -1
         for epoch in range(cfg.num_epochs):
             model.train()
@@ -621,6 +626,7 @@ class Trainer:
             else:
                 patience_counter += 1
             lr_now = self.optimizer.param_groups[0]["lr"]
+            lr_trace.append(lr_now)
             if epoch % cfg.render_every == 0:                           # model.py:349-360
                 status = (f"Epoch {epoch}, Train Loss: {avg_train_loss:.6f}, "
                           f"Val Loss: {avg_val_loss:.6f}, LR: {lr_now:.6f}")
@@ -646,7 +652,8 @@ class Trainer:
         if self.rank == 0 and cfg.output_dir:
             final_epoch = epoch + 1 if patience_counter < cfg.early_stopping_patience else epoch
             self._write_results(final_epoch, best_val_loss, patience_counter)
-        self.history = history
+        self.history, self.lr_trace = history, lr_trace
+        self.best_val_loss, self.early_stopped = best_val_loss, patience_counter >= cfg.early_stopping_patience
         return model
 
     def _load_best(self, best_model_state):

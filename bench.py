@@ -15,8 +15,14 @@ the per-GPU batch stays 1024, gradients are all-reduced over NCCL.
   value   whole-job glyphs/s with the batches already resident in HBM (CUDA events, max over ranks)
   e2e     the same step driven through the public API with HOST buffers: every step copies its
           tokens + uint8 sheets from pinned host memory and reads the loss back
-  roofline  the dominant kernel (single GPU: the wgrad GEMM with the AdamW step of fc_output.weight
-            in its epilogue, HBM-bound; N > 1: the row-sharded AdamW kernel) timed live with CUDA events
+  roofline  the dominant HBM-bound kernel (single GPU: the AdamW sweep over fc_output.weight -- by
+            default the background ring kernel that shares the SMs with the rest of backward, or with
+            --step-mode fused the wgrad GEMM with the AdamW epilogue; N > 1: the row-sharded AdamW
+            kernel) timed live with CUDA events on the stream it runs on
+  gpu_eager_baseline  the reference's step as plain eager PyTorch on the same B200 (fp32 as the
+            reference configures it, and under autocast(bf16)), the "existing Blackwell path" bar
+  dp_parity (N > 1) the data-parallel step against the single-GPU step on the same global batch,
+            checked before the timed region; a mismatch fails the run
   render    batched inference render glyphs/s (uint8 sheets), device-resident and end to end
   cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
 `--impl reference` times only that CPU path (the reference arm of the contract).
@@ -178,7 +184,15 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args.gpus, args.gpus == 1),
+        "data": "synthetic",
+        "config": {"workload": "config[0] reference default on CPU: the reference's training step "
+                               "(model.py:291-311: forward, mse_loss, backward, AdamW) at its CPU batch of "
+                               f"{CPU_BATCH} (model.py:411), same FiraCode model (100 chars -> 80x240, 122.9 M "
+                               "parameters), train-mode dropout, fp32, oracle port of the reference",
+                   "implementation": "oracle/afr_oracle.py (CPU restatement pinned to the reference's outputs; "
+                                     "measured faster than the unmodified reference in the build container)",
+                   "batch": CPU_BATCH, "device": "host CPU", "threads": cores,
+                   "max_length": 100, "sheet": "80x240", "params": 122912896, "parallelism": "single process"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,15 +201,70 @@ def run_reference_arm(args, rank):
     emit_line(line)
 
 
-def load_fused_traffic():
-    """DRAM bytes (read + write) of one launch of the fused wgrad+AdamW kernel from the committed
-    `ncu --set full` capture (profiles/*_fused_traffic.json), or None before it exists."""
-    path = os.path.join(REPO, "profiles", "r01_fused_traffic.json")
+def load_traffic(name, default=None):
+    """DRAM bytes (read + write) of one launch of a kernel from a committed `ncu --set full` capture
+    (profiles/<name>), or `default` before it exists."""
     try:
-        with open(path) as f:
+        with open(os.path.join(REPO, "profiles", name)) as f:
             return float(json.load(f)["dram_bytes_read_plus_write"])
     except (OSError, KeyError, ValueError):
-        return FUSED_TRAFFIC_NCU
+        return default
+
+
+def load_fused_traffic():
+    return load_traffic("r01_fused_traffic.json", FUSED_TRAFFIC_NCU)
+
+
+def gpu_eager_baseline(device, steps=8, warmup=3):
+    """The reference's training step as plain eager PyTorch on the SAME B200 (the "existing
+    Blackwell library path": ATen / cuBLAS kernels, torch.optim.AdamW), batch 1024, train-mode
+    dropout, timed with CUDA events: once in fp32 exactly as the reference configures the device
+    (model.py:86-93 sets no TF32 / autocast), once under torch.autocast(bfloat16). The module
+    arithmetic is the oracle's restatement of model.py:158-204 (the reference itself cannot travel
+    to the GPU box); the optimizer is torch's own AdamW with the reference's hyper-parameters."""
+    from oracle import afr_oracle as orc
+    import torch.nn.functional as F
+    cfg = orc.OracleConfig()
+    out = {}
+    strings = orc.dataset_strings(BATCH_PER_GPU)
+    tokens = orc.encode_strings(strings, cfg.max_length).to(device)
+    targets = orc.targets_to_f32(orc.synthetic_targets_u8(strings, cfg, seed=1234)).to(device)
+    gen = torch.Generator(device=device).manual_seed(SEED)
+    prev_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for name, autocast in (("fp32", False), ("autocast_bf16", True)):
+            params = {k: torch.nn.Parameter(v.to(device)) for k, v in orc.init_state(cfg, seed=SEED).items()}
+            opt = torch.optim.AdamW(params.values(), lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
+            ev = []
+            for i in range(warmup + steps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                masks = {"embed": torch.rand((BATCH_PER_GPU, 100, 32), generator=gen, device=device) >= cfg.p_embed,
+                         "attn": torch.rand((BATCH_PER_GPU, 4, 100, 100), generator=gen, device=device) >= cfg.p_attn,
+                         "fc1": torch.rand((BATCH_PER_GPU, 100, 64), generator=gen, device=device) >= cfg.p_fc1}
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    y = orc.forward(params, tokens, cfg, masks)
+                    loss = F.mse_loss(y.float(), targets.view(y.shape))
+                loss.backward()
+                opt.step()
+                e1.record()
+                if i >= warmup:
+                    ev.append((e0, e1))
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+            out[name] = {"ms_per_step": ms, "value": BATCH_PER_GPU / (ms / 1e3), "unit": UNIT,
+                         "final_loss": float(loss.detach())}
+            del params, opt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev_tf32
+    out["what"] = ("reference step (model.py:291-311) as eager PyTorch on this GPU: oracle restatement of the module, "
+                   f"torch.optim.AdamW, batch {BATCH_PER_GPU}, train-mode dropout, data resident, {steps} steps "
+                   f"after {warmup} warm-up, CUDA events")
+    return out
 
 
 def measure_render(model, device, rank, world, dist, bmp_set=False):
@@ -295,11 +364,15 @@ def measure_render(model, device, rank, world, dist, bmp_set=False):
             "output": "uint8 sheets (helpers.py:33 quantisation fused in the GEMM epilogue)"}
 
 
-def workload_config(n_gpus, fused=False, dp_mode=None):
+def workload_config(n_gpus, step_mode="two-kernel", dp_mode=None):
     return {"workload": "config[1] FiraCode model 100 chars -> 80x240, fused fwd/bwd/AdamW, "
                         "1024 glyphs per GPU per step (model.py:409)",
-            "optimizer": ("AdamW of fc_output.weight inside the wgrad GEMM epilogue (gradient not materialised)"
-                          if fused else "AdamW sweep kernel over fc_output.weight"),
+            "optimizer": {"fused": "AdamW of fc_output.weight inside the wgrad GEMM epilogue (gradient not materialised)",
+                          "background": "AdamW of fc_output.weight as a background sweep (128-thread cp.async ring "
+                                        "CTAs on a second stream, co-resident with dgrad / front-end backward / the "
+                                        "next front-end forward)",
+                          "two-kernel": "AdamW sweep kernel over fc_output.weight"}[step_mode],
+            "step_mode": step_mode,
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
             "max_length": 100, "sheet": "80x240", "params": 122912896,
             "parallelism": (f"dp{n_gpus} ({dp_mode}): batch sharded; AdamW of fc_output.weight sharded by rows, "
@@ -328,8 +401,17 @@ def main():
     ap.add_argument("--comm-ctas", type=int, default=0,
                     help="N > 1: SMs left to the communication kernel (0 = PeerLink.default_ctas / 32 for "
                          "NCCL); the persistent kernels use the rest")
+    ap.add_argument("--step-mode", default="auto", choices=["auto", "background", "fused", "two-kernel"],
+                    help="single GPU: how optimizer.step() of fc_output.weight runs. background = sweep kernel "
+                         "on a second stream sharing the SMs with the rest of backward (default), fused = in the "
+                         "wgrad GEMM's epilogue, two-kernel = wgrad then a stand-alone sweep")
+    ap.add_argument("--bg-stages", type=int, default=0, help="background sweep: ring stages of 8 KB (0 = default)")
+    ap.add_argument("--bg-chunks", type=int, default=0, help="background sweep: row chunks of wgrad / sweep (0 = default)")
+    ap.add_argument("--bg-ctas", type=int, default=0, help="background sweep: CTAs (0 = one per SM)")
     ap.add_argument("--no-fuse", action="store_true",
-                    help="single GPU: keep wgrad and the AdamW sweep as two kernels (gradient materialised)")
+                    help="single GPU: same as --step-mode two-kernel")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-B200 baseline")
+    ap.add_argument("--no-dp-parity", action="store_true", help="N > 1: skip the parity check before timing")
     ap.add_argument("--overlap-dgrad", action="store_true",
                     help="single GPU: run the dgrad GEMM co-resident under the wgrad+AdamW GEMM (measured slower)")
     ap.add_argument("--no-render", action="store_true", help="skip the batched-render measurement")
@@ -368,9 +450,22 @@ def main():
     # model: the reference's construction under its seed (model.py:87-90,402)
     torch.manual_seed(SEED)
     model = AttentionFontRenderer().to(device).train()
-    fused = world == 1 and not args.no_fuse
+    if args.no_fuse:
+        args.step_mode = "two-kernel"
+    step_mode = ("background" if args.step_mode == "auto" else args.step_mode) if world == 1 else "two-kernel"
+    fused = step_mode == "fused"
+    bg_kw = {}
+    if step_mode == "background":
+        bg_kw = dict(background=True)
+        if args.bg_stages:
+            bg_kw["bg_stages"] = args.bg_stages
+        if args.bg_chunks:
+            bg_kw["bg_chunks"] = args.bg_chunks
+        if args.bg_ctas:
+            bg_kw["bg_ctas"] = args.bg_ctas
     opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fused,
-                     overlap_dgrad=fused and args.overlap_dgrad)
+                     overlap_dgrad=fused and args.overlap_dgrad, **bg_kw)
+    dp_parity = None
     if world > 1:
         from ai_font_renderer_b200.training import PeerLink
         if args.dp_mode == "auto":
@@ -390,6 +485,19 @@ def main():
         elif args.dp_mode == "nccl":
             sms = torch.cuda.get_device_properties(device).multi_processor_count
             model.set_sm_limit(sms - int(os.environ.get("NCCL_MAX_CTAS", "32")))
+        if not args.no_dp_parity:
+            # correctness of the shipped data-parallel mode at THIS world size, before anything is
+            # timed: two steps of the sharded step against the single-GPU step on the same global
+            # batch (tools/dp_check.py). A mismatch fails the run.
+            sys.path.insert(0, os.path.join(REPO, "tools"))
+            import dp_check
+            ok, dp_parity = dp_check.compare(rank, world, device, args.dp_mode, steps=2, per_rank=96,
+                                             ctas=args.comm_ctas or PeerLink.default_ctas(world))
+            if not ok:
+                if rank == 0:
+                    emit_line({"error": "data-parallel parity check failed", "dp_parity": dp_parity})
+                dist.destroy_process_group()
+                return 3
     n_rot = 8
     tok_h, tgt_h = fast_synthetic_batch(B * n_rot, seed=1234 + rank)
     tok_h, tgt_h = tok_h.pin_memory(), tgt_h.pin_memory()
@@ -455,6 +563,7 @@ def main():
         e0.record()
         for i in range(k):
             fn(i, step_marks[i]) if with_events else fn(i)
+        model.join_pending()      # a deferred optimizer sweep (side stream) belongs to the timed steps
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -504,6 +613,7 @@ def main():
     # the same sweep alone on the device (nothing else running), for reference
     iso = []
     if world == 1:
+        model.join_pending()
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t_step = opt.begin_step()
@@ -511,6 +621,8 @@ def main():
             e0.record()
             if fused:
                 opt.wgrad_step_rows(t_step, 0, P_PIX)   # dZ / features of the last step are still there
+            elif step_mode == "background":
+                opt.step_rows_bg(t_step, 0, P_PIX, opt.bg_ctas, opt.bg_stages)
             else:
                 opt.step_rows(t_step, 0, P_PIX)
             e1.record()
@@ -547,6 +659,14 @@ def main():
                        "adamw_gather_kernel (peer gradient rows + AdamW + bf16 rows to peers)")
         adamw_bytes = (24 + 4 + 2) * owned
         traffic = None
+    elif step_mode == "background":
+        # the same 30 B/parameter as the plain sweep (p, g, m, v read; p, m, v + bf16 copy written),
+        # timed begin -> end on ITS stream while dgrad / the front-end backward / the next
+        # front-end forward run beside it on the same SMs
+        kernel_name = ("adamw_ring_kernel (background AdamW sweep over fc_output.weight + bf16 shadow, "
+                       "co-resident with the compute kernels of the step)")
+        adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
+        traffic = load_traffic("r02_ring_traffic.json")
     else:
         kernel_name = "adamw_kernel (fc_output.weight sweep + bf16 shadow)"
         adamw_bytes = ADAMW_BYTES_PER_PARAM * N_PARAMS_W
@@ -558,7 +678,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(world, fused, args.dp_mode if world > 1 else None),
+        "config": workload_config(world, step_mode, args.dp_mode if world > 1 else None),
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(feeder.h2d_bytes_per_batch), "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -590,6 +710,12 @@ def main():
     if render is not None:
         line["render"] = render
         line["render_bmp_set"] = render_bmp
+    if dp_parity is not None:
+        line["dp_parity"] = dp_parity
+    if world == 1 and not args.no_gpu_eager:
+        del model, opt, feeder, tok_d, tgt_d
+        torch.cuda.empty_cache()
+        line["gpu_eager_baseline"] = gpu_eager_baseline(device)
     if world == 1 and not args.no_cpu_baseline:
         cpu_value, cpu_sec = cpu_train_glyphs_per_sec(steps=6, warmup=2)
         line["cpu_baseline"] = {

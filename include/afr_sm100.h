@@ -128,9 +128,12 @@ int afr_bind_shadow(afr_ctx* ctx, void* copy0, void* copy1);
  * A data-parallel caller therefore leaves the collective its SMs: the persistent kernels launch
  * at most `sms` CTAs (values outside [1, #SMs] restore the default, all SMs). */
 int afr_set_sm_limit(afr_ctx* ctx, int sms);
-/* Shared memory (bytes per SM, 0..96 KB) the GEMM launches leave free -- their operand rings get
- * shallower -- so that a background kernel (afr_adamw_rows_bg: stages x 8 KB + 1 KB) finds room
- * beside them on every SM. 0 restores the full-depth rings. */
+/* Room for a background kernel (afr_adamw_rows_bg: stages x 8 KB + 1 KB of shared memory, 4 warps
+ * of 40 registers) beside the kernels that follow the wgrad GEMM in a training step: with
+ * bytes > 0 (0..96 KB) the dgrad GEMM (and afr_train_wgrad_to) launch with an operand ring that
+ * leaves `bytes` of the SM's shared memory free, and the front-end backward / training front-end
+ * forward launch as register-capped variants (112 / 64 registers) so that a warp of the
+ * background kernel fits on every scheduler partition. 0 restores the full footprints. */
 int afr_set_smem_reserve(afr_ctx* ctx, int bytes);
 int afr_shadow_index(const afr_ctx* ctx);
 int afr_shadow_commit(afr_ctx* ctx);

@@ -135,7 +135,7 @@ def features(state, tokens: torch.Tensor, cfg: OracleConfig, masks=None) -> torc
     f = _dropout(f, m.get("fc1"), cfg.p_fc1)                                  # model.py:184
     feats = f.reshape(B, S * Fh)                                              # model.py:187
     if S < L:                                                                 # model.py:190-193
-        feats = torch.cat([feats, torch.zeros(B, (L - S) * Fh, dtype=feats.dtype)], dim=1)
+        feats = torch.cat([feats, torch.zeros(B, (L - S) * Fh, dtype=feats.dtype, device=feats.device)], dim=1)
     return feats
 
 
