@@ -494,8 +494,15 @@ class AttentionFontRenderer(nn.Module):
     def kernel_launches(self) -> int:
         return self._ctx.launch_count() if self._ctx is not None else 0
 
+    def state_dict(self, *args, **kwargs):
+        """The optimizer step of fc_output.weight may still be running on the side stream
+        (background sweep / data-parallel gather): join it before the weights are handed out."""
+        self.join_pending()
+        return super().state_dict(*args, **kwargs)
+
     # nn.Module hooks that can move / replace parameter storage
     def _apply(self, fn, recurse=True):
+        self.join_pending()
         out = super()._apply(fn, recurse)
         if self._ctx is not None:
             self._ctx.close()

@@ -63,6 +63,9 @@ class TrainConfig:
     # no-ops and the saved weights are the LAST epoch's. False reproduces that (default: drop-in);
     # True keeps a real clone of the best epoch's weights and restores it.
     restore_best_weights: bool = False
+    # single GPU: optimizer.step() of fc_output.weight as the background sweep on a second stream
+    # (FusedAdamW(background=True)); False = inside the wgrad GEMM's epilogue
+    background_adamw: bool = True
     quiet: bool = False
 
 
@@ -301,6 +304,9 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
         mark("tail")
         return
 
+    if getattr(model, "_smem_reserve", 0):
+        model.set_smem_reserve(0)           # full footprints again after a background-sweep step
+
     if world == 1 and getattr(optimizer, "fuse_wgrad", False):
         # one kernel per bucket: wgrad GEMM whose epilogue applies AdamW to the fc_output.weight
         # tiles (the gradient never reaches HBM); 'adamw_*' marks bracket that kernel
@@ -463,7 +469,7 @@ class Trainer:
         self.val_loader = tud.DataLoader(val_ds, batch_size=batch_size, shuffle=False, generator=g,
                                          num_workers=0)
         self.optimizer = FusedAdamW(model, lr=cfg.learning_rate, weight_decay=cfg.weight_decay,
-                                    betas=cfg.betas)                                  # model.py:273
+                                    betas=cfg.betas, background=cfg.background_adamw)  # model.py:273
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(
             self.optimizer, mode="min", factor=cfg.scheduler_factor,
             patience=cfg.scheduler_patience, min_lr=cfg.min_learning_rate)            # model.py:276-278
@@ -649,6 +655,7 @@ class Trainer:
             self._load_best(best_model_state)                           # model.py:369-371
             say(f"Training completed, Best Val Loss: {best_val_loss:.6f}")
         self.gather_master()
+        model.join_pending()
         if self.rank == 0 and cfg.output_dir:
             final_epoch = epoch + 1 if patience_counter < cfg.early_stopping_patience else epoch
             self._write_results(final_epoch, best_val_loss, patience_counter)

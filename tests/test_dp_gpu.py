@@ -23,14 +23,19 @@ def _free_port():
     return port
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["peer", "peer-side", "nvls", "nccl"])
-def test_row_sharded_data_parallel_step_equals_single_gpu_step(mode):
-    """peer: gradient rows / bf16 weights move through NVLink peer memory inside the AdamW kernel, on
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("mode", ["nvls-side", "peer", "peer-side", "nvls", "nccl"])
+def test_row_sharded_data_parallel_step_equals_single_gpu_step(mode, world):
+    """nvls-side is the default mode bench.py / the Trainer pick on an NVSwitch box (bench.py also
+    runs this comparison at its own world size before timing and prints it as `dp_parity`).
+    peer: gradient rows / bf16 weights move through NVLink peer memory inside the AdamW kernel, on
     the compute stream on all SMs; peer-side: the same kernel on a side stream on a few SMs;
     nvls: the same with the gradient summed inside the NVSwitch (multimem.ld_reduce) and the bf16
     rows multicast (multimem.st); nccl: reduce-scatter + all-gather."""
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world > 2 and mode not in ("nvls-side", "peer-side", "nccl"):
+        pytest.skip("inline modes are covered at 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(REPO, "tools", "dp_check.py"), mode]
