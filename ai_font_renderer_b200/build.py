@@ -15,8 +15,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libafr_sm100.so")
 STAMP_PATH = LIB_PATH + ".stamp"
-SOURCES = ["afr_api.cu", "afr_gemm.cu", "afr_frontend.cu", "afr_elementwise.cu"]
-HEADERS = ["afr_ptx.cuh", "afr_gemm.cuh", "afr_internal.h", "../../include/afr_sm100.h"]
+SOURCES = ["afr_api.cu", "afr_gemm.cu", "afr_frontend.cu", "afr_wide.cu", "afr_elementwise.cu"]
+HEADERS = ["afr_ptx.cuh", "afr_gemm.cuh", "afr_philox.cuh", "afr_internal.h", "../../include/afr_sm100.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

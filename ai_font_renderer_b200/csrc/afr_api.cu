@@ -54,6 +54,20 @@ struct afr_ctx {
   bool cta2 = true;                  // forward / dgrad / wgrad GEMMs run as CTA pairs (AFR_CTA2=0: single CTAs)
   long long launches = 0;
   std::string err;
+  // ---- wide front-end (embed_dim / heads / fc1 width other than 32 / 4 / 64): afr_wide.cu + GEMMs
+  bool wide = false;
+  int E = kE, H = kHeads, F = kF;
+  struct Wide {
+    float *e32 = nullptr, *qkv32 = nullptr, *a32 = nullptr, *f32 = nullptr;          // forward
+    __nv_bfloat16 *e16 = nullptr, *ctx16 = nullptr, *h16 = nullptr;
+    __nv_bfloat16 *win16 = nullptr, *wo16 = nullptr, *w116 = nullptr;                // bf16 weights
+    float *xhat = nullptr, *rstd = nullptr, *dr32 = nullptr, *dctx32 = nullptr;      // training
+    float2* stat = nullptr;
+    uint32_t* abits = nullptr;
+    __nv_bfloat16 *df16 = nullptr, *dr16 = nullptr, *dqkv16 = nullptr;
+    float *splitk = nullptr, *ln_part = nullptr, *pos_part = nullptr, *emb_part = nullptr;
+    int max_splits = 0, max_ln_parts = 0;
+  } w;
 };
 
 namespace {
@@ -161,8 +175,14 @@ int ensure_shadow(afr_ctx* c, cudaStream_t st) {
   return AFR_OK;
 }
 
+int run_frontend_wide(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
+                      const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32);
+int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
+                               const Dropout& drop, const float* dfeat, cudaStream_t st);
+
 int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
                  const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32 = nullptr) {
+  if (c->wide) return run_frontend_wide(c, tokens, stride, B, S, drop, save_state, st, feats_f32);
   float* state = save_state ? c->fstate : nullptr;
   AFR_CUDA(c, launch_frontend_forward(c->params, tokens, stride, B, S, c->cfg.max_length,
                                       c->cfg.vocab, drop, c->feats, state, c->sms, st, feats_f32,
@@ -170,6 +190,132 @@ int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, i
            "frontend_forward");
   c->launches += 1;
   c->state_valid = state != nullptr;
+  return AFR_OK;
+}
+
+
+// ---------------------------------------------------------------- wide front-end sequencing
+WideDims wide_dims(const afr_ctx* c, int B, int S) {
+  WideDims d{};
+  d.B = B; d.S = S; d.L = c->cfg.max_length; d.E = c->E; d.H = c->H; d.dh = c->E / c->H; d.F = c->F;
+  d.vocab = c->cfg.vocab;
+  return d;
+}
+WideDrop wide_drop(const Dropout& drop) {
+  auto thr = [](double p) { return static_cast<uint32_t>(p * 65536.0 + 0.5); };
+  auto inv = [](double p) { return 1.0f / static_cast<float>(1.0 - p); };
+  WideDrop w{};
+  w.mode = drop.mode;
+  w.k0 = static_cast<uint32_t>(drop.seed); w.k1 = static_cast<uint32_t>(drop.seed >> 32);
+  w.step = static_cast<uint32_t>(drop.step); w.sample_offset = drop.sample_offset;
+  w.thr_e = thr(drop.p_embed); w.thr_a = thr(drop.p_attn); w.thr_f = thr(drop.p_fc1);
+  const bool on = drop.mode != 0;
+  w.inv_e = on ? inv(drop.p_embed) : 1.f; w.inv_a = on ? inv(drop.p_attn) : 1.f; w.inv_f = on ? inv(drop.p_fc1) : 1.f;
+  return w;
+}
+
+// D[M,N] (fp32, ld = ldo) = A * B^T (+ bias[n]) on the tcgen05 GEMM; k_splits > 1: partial sums
+// into c->w.splitk, summed into `out` afterwards (weight gradients: K = batch x positions)
+int wide_gemm(afr_ctx* c, const __nv_bfloat16* A, long long lda, bool a_mn, const __nv_bfloat16* B,
+              long long ldb, bool b_mn, int M, int N, int K, float* out, long long ldo, const float* bias,
+              int k_splits, cudaStream_t st, const char* what) {
+  GemmEpilogue ep{};
+  ep.kind = kEpiF32; ep.alpha = 1.f; ep.bias = bias; ep.use_tma_store = 1;
+  const bool split = k_splits > 1;
+  ep.cta2 = c->cta2 && !split;
+  ep.k_splits = split ? k_splits : 0;
+  ep.out = split ? c->w.splitk : out;
+  ep.ldo = split ? N : ldo;
+  const int bn = choose_bn(M, N, c->sms, "AFR_BN_WIDE", ep.cta2 != 0);
+  const char* msg = nullptr;
+  int splits_used = 1;
+  cudaError_t e = launch_gemm_bf16(A, lda, a_mn, B, ldb, b_mn, M, N, K, bn, ep, c->sms, st, nullptr, &msg,
+                                   &splits_used);
+  if (e != cudaSuccess) return msg ? fail(c, AFR_ERR_INVALID, std::string(what) + ": " + msg) : fail_cuda(c, e, what);
+  c->launches += 1;
+  if (split) {
+    // partial [splits][M rounded up to 128][N] -> out [M][N]
+    AFR_CUDA(c, launch_wide_splitk_reduce(c->w.splitk, splits_used, M, N, out, st), "splitk_reduce");
+    c->launches += 1;
+  }
+  return AFR_OK;
+}
+
+int run_frontend_wide(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
+                      const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32) {
+  if (drop.mode == 2)
+    return fail(c, AFR_ERR_INVALID, "injected dropout masks (mode 2) are not built for the wide front-end");
+  auto& w = c->w;
+  const WideDims d = wide_dims(c, B, S);
+  const WideDrop dr = wide_drop(drop);
+  const int E = c->E, F = c->F, R = B * S;
+  AFR_CUDA(c, ensure_err_flag_public(), "err flag");
+  AFR_CUDA(c, launch_wide_split_weight(c->params.win, 3 * E, E, w.win16, st), "split bf16(in_proj)");
+  AFR_CUDA(c, launch_wide_split_weight(c->params.wo, E, E, w.wo16, st), "split bf16(out_proj)");
+  AFR_CUDA(c, launch_wide_split_weight(c->params.w1, F, E, w.w116, st), "split bf16(fc1)");
+  AFR_CUDA(c, launch_wide_embed(d, dr, tokens, stride, c->params.emb, c->params.pos, w.e32, w.e16,
+                                frontend_error_flag(), c->sms, st), "wide_embed");
+  c->launches += 4;
+  int rc;
+  // forward GEMMs: split-bf16 operands, K = 3E (x_hi w_hi + x_lo w_hi + x_hi w_lo)
+  if ((rc = wide_gemm(c, w.e16, 3 * E, false, w.win16, 3 * E, false, R, 3 * E, 3 * E, w.qkv32, 3 * E,
+                      c->params.bin, 1, st, "gemm(in_proj)"))) return rc;
+  AFR_CUDA(c, launch_wide_attention_fwd(d, dr, w.qkv32, w.ctx16, save_state ? w.stat : nullptr,
+                                        save_state ? w.abits : nullptr, st), "wide_attention_fwd");
+  if ((rc = wide_gemm(c, w.ctx16, 3 * E, false, w.wo16, 3 * E, false, R, E, 3 * E, w.a32, E, c->params.bo, 1, st,
+                      "gemm(out_proj)"))) return rc;
+  AFR_CUDA(c, launch_wide_ln_fwd(R, E, w.e32, w.a32, c->params.lnw, c->params.lnb, save_state ? w.xhat : nullptr,
+                                 save_state ? w.rstd : nullptr, w.h16, c->sms, st), "wide_ln_fwd");
+  if ((rc = wide_gemm(c, w.h16, 3 * E, false, w.w116, 3 * E, false, R, F, 3 * E, w.f32, F, c->params.b1, 1, st,
+                      "gemm(fc1)"))) return rc;
+  AFR_CUDA(c, launch_wide_act_fwd(d, dr, w.f32, c->feats, feats_f32, c->sms, st), "wide_act_fwd");
+  c->launches += 3;
+  c->state_valid = save_state;
+  return AFR_OK;
+}
+
+int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
+                               const Dropout& drop, const float* dfeat, cudaStream_t st) {
+  auto& w = c->w;
+  const WideDims d = wide_dims(c, B, S);
+  const WideDrop dr = wide_drop(drop);
+  const int E = c->E, F = c->F, R = B * S;
+  int splits = R / 64 / 8;                      // >= 8 k-blocks of 64 rows per piece
+  if (splits > w.max_splits) splits = w.max_splits;
+  if (splits < 1) splits = 1;
+  int rc;
+  // fc1 + ReLU + dropout1
+  AFR_CUDA(c, launch_wide_act_bwd(d, dr, w.f32, dfeat, w.df16, c->sms, st), "wide_act_bwd");
+  AFR_CUDA(c, launch_bias_grad(w.df16, R, F, 1.f, c->bias_scratch, c->grads.b1, st, F), "bias_grad(fc1)");
+  c->launches += 3;
+  // (the hi parts of the split operands: the first E columns of every 3E-wide row)
+  if ((rc = wide_gemm(c, w.df16, F, false, w.w116, 3 * E, true, R, E, F, w.a32, E, nullptr, 1, st,
+                      "gemm(d fc1 input)"))) return rc;
+  if ((rc = wide_gemm(c, w.df16, F, true, w.h16, 3 * E, true, F, E, R, c->grads.w1, E, nullptr, splits, st,
+                      "gemm(d fc1.weight)"))) return rc;
+  // LayerNorm + residual
+  AFR_CUDA(c, launch_wide_ln_bwd(R, E, w.a32, w.xhat, w.rstd, c->params.lnw, w.dr32, w.dr16, w.ln_part,
+                                 w.max_ln_parts, c->grads.lnw, c->grads.lnb, c->sms, st), "wide_ln_bwd");
+  AFR_CUDA(c, launch_bias_grad(w.dr16, R, E, 1.f, c->bias_scratch, c->grads.bo, st, E), "bias_grad(out_proj)");
+  c->launches += 4;
+  // attention out-projection
+  if ((rc = wide_gemm(c, w.dr16, E, false, w.wo16, 3 * E, true, R, E, E, w.dctx32, E, nullptr, 1, st,
+                      "gemm(d ctx)"))) return rc;
+  if ((rc = wide_gemm(c, w.dr16, E, true, w.ctx16, 3 * E, true, E, E, R, c->grads.wo, E, nullptr, splits, st,
+                      "gemm(d out_proj.weight)"))) return rc;
+  AFR_CUDA(c, launch_wide_attention_bwd(d, dr, w.qkv32, w.dctx32, w.ctx16, w.stat, w.abits, w.dqkv16, st),
+           "wide_attention_bwd");
+  AFR_CUDA(c, launch_bias_grad(w.dqkv16, R, 3 * E, 1.f, c->bias_scratch, c->grads.bin, st, 3 * E), "bias_grad(in_proj)");
+  c->launches += 3;
+  // in-projection
+  if ((rc = wide_gemm(c, w.dqkv16, 3 * E, false, w.win16, 3 * E, true, R, E, 3 * E, w.a32, E, nullptr, 1, st,
+                      "gemm(d e)"))) return rc;
+  if ((rc = wide_gemm(c, w.dqkv16, 3 * E, true, w.e16, 3 * E, true, 3 * E, E, R, c->grads.win, E, nullptr, splits, st,
+                      "gemm(d in_proj.weight)"))) return rc;
+  // embedding + positions
+  AFR_CUDA(c, launch_wide_embed_bwd(d, dr, tokens, stride, w.dr32, w.a32, w.pos_part, w.emb_part, c->num_sms,
+                                    c->grads.pos, c->grads.emb, c->sms, st), "wide_embed_bwd");
+  c->launches += 3;
   return AFR_OK;
 }
 
@@ -200,9 +346,12 @@ const char* afr_last_error(const afr_ctx* ctx) {
 int afr_create(const afr_config* cfg, afr_ctx** out) {
   if (cfg == nullptr || out == nullptr) return fail(nullptr, AFR_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->embed_dim != kE || cfg->num_heads != kHeads || cfg->hidden != kF)
-    return fail(nullptr, AFR_ERR_INVALID,
-                "front-end kernels are built for embed_dim=32, num_heads=4, hidden=64");
+  const bool wide = cfg->embed_dim != kE || cfg->num_heads != kHeads || cfg->hidden != kF;
+  if (wide) {
+    const char* why = nullptr;
+    if (!wide_shape_supported(cfg->embed_dim, cfg->num_heads, cfg->hidden, cfg->max_length, &why))
+      return fail(nullptr, AFR_ERR_INVALID, std::string("unsupported front-end shape: ") + why);
+  }
   if (cfg->max_length < 1 || cfg->max_length > kMaxL || cfg->vocab < 1 || cfg->max_batch < 1)
     return fail(nullptr, AFR_ERR_INVALID, "max_length must be in [1,128], vocab >= 1, max_batch >= 1");
   const long long P = static_cast<long long>(cfg->sheet_h) * cfg->sheet_w;
@@ -224,10 +373,12 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
   c->sms = c->num_sms;
   c->K = cfg->max_length * cfg->hidden;
   c->P = static_cast<int>(P);
+  c->wide = wide;
+  c->E = cfg->embed_dim; c->H = cfg->num_heads; c->F = cfg->hidden;
   { const char* e2 = std::getenv("AFR_CTA2"); c->cta2 = !(e2 && std::atoi(e2) == 0); }
   c->lay.init(cfg->max_length, cfg->vocab);
   c->fsl.init(cfg->max_length);
-  if (cfg->training &&
+  if (cfg->training && !wide &&
       frontend_backward_smem_bytes(cfg->max_length, cfg->vocab) > prop.sharedMemPerBlockOptin) {
     delete c;
     return fail(nullptr, AFR_ERR_INVALID,
@@ -251,9 +402,45 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
       afr_destroy(c);
       return fail(nullptr, AFR_ERR_INVALID, "training path supports vocab up to ~100k rows");
     }
-    alloc(reinterpret_cast<void**>(&c->partials),
-          static_cast<size_t>(c->num_sms) * c->lay.total * 4);
-    alloc(reinterpret_cast<void**>(&c->fstate), Bm * c->fsl.stride * 4);
+    if (!wide) {
+      alloc(reinterpret_cast<void**>(&c->partials),
+            static_cast<size_t>(c->num_sms) * c->lay.total * 4);
+      alloc(reinterpret_cast<void**>(&c->fstate), Bm * c->fsl.stride * 4);
+    }
+  }
+  if (wide) {
+    const size_t R = Bm * cfg->max_length, E = c->E, F = c->F, H = c->H;
+    auto& w = c->w;
+    alloc(reinterpret_cast<void**>(&w.e32), R * E * 4);
+    alloc(reinterpret_cast<void**>(&w.e16), R * 3 * E * 2);      // split bf16 rows [hi | lo | hi], see afr_wide.cu
+    alloc(reinterpret_cast<void**>(&w.qkv32), R * 3 * E * 4);
+    alloc(reinterpret_cast<void**>(&w.ctx16), R * 3 * E * 2);
+    alloc(reinterpret_cast<void**>(&w.a32), R * E * 4);
+    alloc(reinterpret_cast<void**>(&w.h16), R * 3 * E * 2);      // [hi | lo | hi], see afr_wide.cu
+    alloc(reinterpret_cast<void**>(&w.f32), R * F * 4);
+    alloc(reinterpret_cast<void**>(&w.win16), 3 * E * 3 * E * 2);   // split bf16 rows [hi | hi | lo]
+    alloc(reinterpret_cast<void**>(&w.wo16), E * 3 * E * 2);
+    alloc(reinterpret_cast<void**>(&w.w116), F * 3 * E * 2);     // [hi | hi | lo]
+    if (cfg->training) {
+      alloc(reinterpret_cast<void**>(&w.xhat), R * E * 4);
+      alloc(reinterpret_cast<void**>(&w.rstd), R * 4);
+      alloc(reinterpret_cast<void**>(&w.stat), Bm * H * cfg->max_length * sizeof(float2));
+      alloc(reinterpret_cast<void**>(&w.abits), Bm * H * cfg->max_length * 4 * sizeof(uint32_t));
+      alloc(reinterpret_cast<void**>(&w.df16), R * F * 2);
+      alloc(reinterpret_cast<void**>(&w.dr32), R * E * 4);
+      alloc(reinterpret_cast<void**>(&w.dr16), R * E * 2);
+      alloc(reinterpret_cast<void**>(&w.dctx32), R * E * 4);
+      alloc(reinterpret_cast<void**>(&w.dqkv16), R * 3 * E * 2);
+      w.max_splits = c->num_sms;
+      const size_t max_mn = ((3 * E + 127) / 128 * 128) * E > ((F + 127) / 128 * 128) * E
+                                ? ((3 * E + 127) / 128 * 128) * E : ((F + 127) / 128 * 128) * E;
+      alloc(reinterpret_cast<void**>(&w.splitk), static_cast<size_t>(w.max_splits) * max_mn * 4);
+      w.max_ln_parts = c->num_sms * 4;
+      alloc(reinterpret_cast<void**>(&w.ln_part), static_cast<size_t>(w.max_ln_parts) * 2 * E * 4);
+      alloc(reinterpret_cast<void**>(&w.pos_part), static_cast<size_t>(c->num_sms) * cfg->max_length * E * 4);
+      if (static_cast<size_t>(cfg->vocab) * E * 4 <= 128 * 1024)
+        alloc(reinterpret_cast<void**>(&w.emb_part), static_cast<size_t>(c->num_sms) * cfg->vocab * E * 4);
+    }
   }
   if (e != cudaSuccess) {
     std::string msg = std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e);
@@ -272,6 +459,13 @@ int afr_destroy(afr_ctx* c) {
   cudaFree(c->dz); cudaFree(c->dfeat);
   cudaFree(c->logits); cudaFree(c->loss_partials); cudaFree(c->bias_scratch);
   cudaFree(c->partials); cudaFree(c->fstate);
+  {
+    auto& w = c->w;
+    void* ptrs[] = {w.e32, w.qkv32, w.a32, w.f32, w.e16, w.ctx16, w.h16, w.win16, w.wo16, w.w116, w.xhat, w.rstd,
+                    w.dr32, w.dctx32, w.stat, w.abits, w.df16, w.dr16, w.dqkv16, w.splitk, w.ln_part, w.pos_part,
+                    w.emb_part};
+    for (void* q : ptrs) cudaFree(q);
+  }
   delete c;
   return AFR_OK;
 }
@@ -514,6 +708,8 @@ int afr_train_frontend_backward(afr_ctx* c, void* stream) {
     return fail(c, AFR_ERR_STATE, "front-end records of this batch were overwritten by another forward");
   DeviceGuard guard(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->wide)
+    return run_frontend_backward_wide(c, c->tokens, c->token_stride, c->B, c->S, c->drop, c->dfeat, st);
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
                                        c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
@@ -813,8 +1009,8 @@ int afr_adamw_small(afr_ctx* c, double lr, double beta1, double beta2, double ep
   if (step < 1) return fail(c, AFR_ERR_INVALID, "step must be >= 1");
   DeviceGuard guard(c->cfg.device);
   const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
-  const int L = c->cfg.max_length, V = c->cfg.vocab;
-  const int sizes[10] = {L * kE, V * kE, 3 * kE * kE, 3 * kE, kE * kE, kE, kE, kE, kF * kE, kF};
+  const int L = c->cfg.max_length, V = c->cfg.vocab, E = c->E, F = c->F;
+  const int sizes[10] = {L * E, V * E, 3 * E * E, 3 * E, E * E, E, E, E, F * E, F};
   float* const* pp = reinterpret_cast<float* const*>(&c->params);
   float* const* gg = reinterpret_cast<float* const*>(&c->grads);
   float* const* mm = reinterpret_cast<float* const*>(&c->m);
@@ -927,6 +1123,9 @@ int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token
                 "afr_debug_frontend_backward needs afr_debug_frontend_forward on the same batch first");
   DeviceGuard guard(c->cfg.device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->wide)
+    return run_frontend_backward_wide(c, reinterpret_cast<const long long*>(tokens), token_stride, B, S,
+                                      to_dropout(dropout), dfeat, st);
   int grid = 0;
   AFR_CUDA(c, launch_frontend_backward(c->params, reinterpret_cast<const long long*>(tokens),
                                        token_stride, B, S, c->cfg.max_length, c->cfg.vocab,

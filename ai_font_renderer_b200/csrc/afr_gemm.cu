@@ -93,7 +93,7 @@ int gemm_num_tiles(int M, int N, int BN, bool cta2) {
 cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
                              const __nv_bfloat16* B, long long ldb, bool b_mn, int M, int N, int K,
                              int BN, const GemmEpilogue& epi, int num_sms, cudaStream_t stream,
-                             int* num_tiles_out, const char** err_msg) {
+                             int* num_tiles_out, const char** err_msg, int* k_splits_out) {
   static const char* kBadShape = "gemm: need M,N,K > 0, N % 32 == 0, BN % 32 == 0, 32 <= BN <= 256";
   static const char* kBadAlign = "gemm: operand pointers / leading dimensions must be 16-byte aligned";
   static const char* kBadMap = "gemm: cuTensorMapEncodeTiled failed";
@@ -121,12 +121,26 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
   else       ok &= encode_2d(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, 64, kBK);
   if (!b_mn) ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, kBK, BN / kctas);
   else       ok &= encode_2d(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, 64, kBK);
+  // split-K: whole 128-row tiles only (a tile must not reach into the next piece's rows)
+  int k_splits = epi.k_splits > 1 ? epi.k_splits : 1;
+  const int num_kb_all = (K + kBK - 1) / kBK;
+  if (k_splits > num_kb_all) k_splits = num_kb_all;
+  int kb_per_split = (num_kb_all + k_splits - 1) / k_splits;
+  k_splits = (num_kb_all + kb_per_split - 1) / kb_per_split;
+  if (k_splits > 1 && (epi.kind != kEpiF32 || cta2 || epi.bias != nullptr)) {
+    if (err_msg) *err_msg = "gemm: split-K needs the fp32 epilogue without bias and single CTAs";
+    return cudaErrorInvalidValue;
+  }
+  p.k_splits = k_splits;
+  p.kb_per_split = kb_per_split;
+  p.split_rows = ((M + kBM - 1) / kBM) * kBM;
   int use_tma_store = epi.use_tma_store;
   if (epi.kind == kEpiF32 && use_tma_store) {
     if ((reinterpret_cast<uintptr_t>(epi.out) & 15) || (epi.ldo % 4) != 0) {
       use_tma_store = 0;  // unaligned output: fall back to direct stores
     } else {
-      ok &= encode_2d(&p.tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.out, M, N, epi.ldo, 32, 32);
+      ok &= encode_2d(&p.tm_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, epi.out,
+                      k_splits > 1 ? static_cast<long long>(p.split_rows) * k_splits : M, N, epi.ldo, 32, 32);
     }
   }
   // ---- shared / tensor memory footprint
@@ -201,8 +215,9 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
   p.out = epi.out; p.ldo = epi.ldo; p.bias = epi.bias; p.alpha = epi.alpha;
   p.clamp01 = epi.clamp01; p.use_tma_store = use_tma_store;
   p.target = epi.target; p.target_is_f32 = epi.target_is_f32; p.loss_partials = epi.loss_partials;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   if (num_tiles_out) *num_tiles_out = num_tiles;
+  if (k_splits_out) *k_splits_out = p.k_splits;
   int grid = num_tiles * kctas < num_sms ? num_tiles * kctas : num_sms;
   if (cta2) grid &= ~1;
 

@@ -98,6 +98,13 @@ struct GemmParams {
   int compact;           // 1: no alignment slack in the dynamic shared memory (base must be 1 KB aligned)
   int adam_sets;         // slab sets per epilogue warp (threads = 64 + 128 * warps per quadrant)
   int adam_sub;          // epilogue warps per TMEM lane quadrant (1..kMaxAdamSub)
+  // split-K (kEpiF32 only; 1 = off): the K range is cut into k_splits pieces of kb_per_split
+  // k-blocks, piece ks of tile (m, n) accumulates into rows [ks * M, ks * M + M) of an output of
+  // k_splits * M rows (summed by a second kernel in a fixed order). For the weight gradients of
+  // the wide front-end, whose M x N is one to three tiles and whose K is batch x positions.
+  int k_splits;
+  int kb_per_split;
+  int split_rows;        // rows per K piece in the output: M rounded up to a whole tile
 };
 
 // CTA2: the kernel runs as clusters of two CTAs (one TPC) that execute 256-row MMAs together
@@ -143,8 +150,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int tile_step = static_cast<int>(gridDim.x) / kCtas;
   const int row_base = cta_rank * kBM;                             // this CTA's rows inside a tile
   constexpr int kTileM = kBM * kCtas;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = (p.K + kBK - 1) / kBK;
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = tiles_mn * p.k_splits;
+  const int num_kb_all = (p.K + kBK - 1) / kBK;
+  // k-blocks of the K piece a tile works on (the last piece may be shorter, never empty)
+  auto kb_count = [&](int tile) {
+    if (p.k_splits == 1) return num_kb_all;
+    const int ks = tile / tiles_mn;
+    return min(p.kb_per_split, num_kb_all - ks * p.kb_per_split);
+  };
   const int BN = p.BN;
   // TMEM accumulator buffers of 256 columns, or 128 when the tile is at most 128 wide: 2 or 4 of
   // them in the full 512-column allocation, 2 x 128 in the co-resident footprint (256 columns, so
@@ -205,8 +219,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       uint32_t phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m0 = (tile % p.num_m_tiles) * kTileM + row_base;
-        const int n0 = (tile / p.num_m_tiles) * BN + cta_rank * bn_cta;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int n0 = ((tile / p.num_m_tiles) % p.num_n_tiles) * BN + cta_rank * bn_cta;
+        const int kb0 = (tile / tiles_mn) * p.kb_per_split;
+        const int num_kb = kb_count(tile);
+        for (int kbl = 0; kbl < num_kb; ++kbl) {
+          const int kb = kb0 + kbl;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem_a + stage * kAStageBytes;
           uint8_t* sb = smem_b + stage * kBStage;
@@ -252,6 +269,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_stride);
+        const int num_kb = kb_count(tile);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -438,9 +456,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     int store_buf = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int m0 = (tile % p.num_m_tiles) * kTileM + row_base;
-      const int n0 = (tile / p.num_m_tiles) * BN;
+      const int n0 = ((tile / p.num_m_tiles) % p.num_n_tiles) * BN;
       const int m = m0 + row_in_tile;
       const bool row_ok = m < p.M;
+      const int split_row = (tile / tiles_mn) * p.split_rows;   // output row offset of this K piece
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       float loss_acc = 0.f;
@@ -482,12 +501,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              ptx::tma_store_2d(&p.tm_c, buf, n, m0 + q * 32);
+              ptx::tma_store_2d(&p.tm_c, buf, n, split_row + m0 + q * 32);
               ptx::tma_store_commit();
             }
             store_buf ^= 1;
           } else if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(split_row + m) * p.ldo + n;
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
               *reinterpret_cast<float4*>(o + 4 * ch) =

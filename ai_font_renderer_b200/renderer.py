@@ -46,7 +46,7 @@ class _Context:
         cfg = _lib.AfrConfig(
             device=device.index if device.index is not None else torch.cuda.current_device(),
             vocab=model.embedding.num_embeddings, max_length=model.max_length,
-            embed_dim=model.embedding_dim, num_heads=NUM_ATTENTION_HEADS, hidden=FC1_WIDTH,
+            embed_dim=model.embedding_dim, num_heads=model.num_heads, hidden=model.fc1_width,
             sheet_h=model.sheet_height, sheet_w=model.sheet_width, max_batch=max_batch,
             training=1 if training else 0)
         handle = C.c_void_p()
@@ -152,23 +152,31 @@ class AttentionFontRenderer(nn.Module):
     """Reference: class AttentionFontRenderer, model.py:129-204."""
 
     def __init__(self, max_length: int = MAX_CHARS_PER_SHEET, sheet_height: int = SHEET_HEIGHT,
-                 sheet_width: int = SHEET_WIDTH, vocab: int = VOCAB):
+                 sheet_width: int = SHEET_WIDTH, vocab: int = VOCAB, embedding_dim: int = EMBEDDING_DIM,
+                 num_heads: int = NUM_ATTENTION_HEADS, fc1_width: int = FC1_WIDTH):
+        """The reference's constructor takes max_length only (model.py:130); its other sizes are
+        module constants (model.py:64-66,79-81,148). They are arguments here so that the scaled
+        workloads of BASELINE.json can be built: sheet size, vocabulary (config 5), and the
+        width of the net -- embedding_dim / num_heads / fc1_width other than 32 / 4 / 64 select
+        the GEMM-based front-end (csrc/afr_wide.cu; config 4: 128 / 8 / 128)."""
         super().__init__()
         self.max_length = max_length
         self.sheet_height = sheet_height
         self.sheet_width = sheet_width
-        self.embedding_dim = EMBEDDING_DIM
+        self.embedding_dim = embedding_dim
+        self.num_heads = num_heads
+        self.fc1_width = fc1_width
         # Same sub-modules, same order as model.py:136-152 => same RNG draws, same state_dict.
         self.embedding = nn.Embedding(vocab, self.embedding_dim)
         self.embedding_dropout = nn.Dropout(DROPOUT_RATE)
         self.positional_encoding = nn.Parameter(torch.zeros(max_length, self.embedding_dim))
         nn.init.normal_(self.positional_encoding, mean=0, std=0.02)
         self.attention = nn.MultiheadAttention(embed_dim=self.embedding_dim,
-                                               num_heads=NUM_ATTENTION_HEADS, dropout=DROPOUT_RATE)
+                                               num_heads=num_heads, dropout=DROPOUT_RATE)
         self.layer_norm = nn.LayerNorm(self.embedding_dim)
-        self.fc1 = nn.Linear(self.embedding_dim, FC1_WIDTH)
+        self.fc1 = nn.Linear(self.embedding_dim, fc1_width)
         self.dropout1 = nn.Dropout(DROPOUT_RATE + 0.05)
-        self.fc_output = nn.Linear(FC1_WIDTH * max_length, sheet_height * sheet_width)
+        self.fc_output = nn.Linear(fc1_width * max_length, sheet_height * sheet_width)
         # dropout generator of the fused kernels: keyed by torch's seed, advanced every train step
         self.dropout_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self.dropout_step = 0
@@ -327,8 +335,8 @@ class AttentionFontRenderer(nn.Module):
             d.mode = 2
             keep = {}
             for key, shape in (("embed", (batch, seq, self.embedding_dim)),
-                               ("attn", (batch, NUM_ATTENTION_HEADS, seq, seq)),
-                               ("fc1", (batch, seq, FC1_WIDTH))):
+                               ("attn", (batch, self.num_heads, seq, seq)),
+                               ("fc1", (batch, seq, self.fc1_width))):
                 m = masks[key].to(device=self.fc_output.weight.device, dtype=torch.uint8).contiguous()
                 if tuple(m.shape) != shape:
                     raise ValueError(f"mask '{key}' must have shape {shape}, got {tuple(m.shape)}")
