@@ -286,7 +286,8 @@ int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long st
   int rc;
   // fc1 + ReLU + dropout1
   AFR_CUDA(c, launch_wide_act_bwd(d, dr, w.f32, dfeat, w.df16, c->sms, st), "wide_act_bwd");
-  AFR_CUDA(c, launch_bias_grad(w.df16, R, F, 1.f, c->bias_scratch, c->grads.b1, st, F), "bias_grad(fc1)");
+  AFR_CUDA(c, launch_wide_colsum_bf16(w.df16, R, F, w.ln_part, w.max_ln_parts, c->grads.b1, c->sms, st),
+           "bias_grad(fc1)");
   c->launches += 3;
   // (the hi parts of the split operands: the first E columns of every 3E-wide row)
   if ((rc = wide_gemm(c, w.df16, F, false, w.w116, 3 * E, true, R, E, F, w.a32, E, nullptr, 1, st,
@@ -296,7 +297,8 @@ int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long st
   // LayerNorm + residual
   AFR_CUDA(c, launch_wide_ln_bwd(R, E, w.a32, w.xhat, w.rstd, c->params.lnw, w.dr32, w.dr16, w.ln_part,
                                  w.max_ln_parts, c->grads.lnw, c->grads.lnb, c->sms, st), "wide_ln_bwd");
-  AFR_CUDA(c, launch_bias_grad(w.dr16, R, E, 1.f, c->bias_scratch, c->grads.bo, st, E), "bias_grad(out_proj)");
+  AFR_CUDA(c, launch_wide_colsum_bf16(w.dr16, R, E, w.ln_part, w.max_ln_parts, c->grads.bo, c->sms, st),
+           "bias_grad(out_proj)");
   c->launches += 4;
   // attention out-projection
   if ((rc = wide_gemm(c, w.dr16, E, false, w.wo16, 3 * E, true, R, E, E, w.dctx32, E, nullptr, 1, st,
@@ -305,7 +307,8 @@ int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long st
                       "gemm(d out_proj.weight)"))) return rc;
   AFR_CUDA(c, launch_wide_attention_bwd(d, dr, w.qkv32, w.dctx32, w.ctx16, w.stat, w.abits, w.dqkv16, st),
            "wide_attention_bwd");
-  AFR_CUDA(c, launch_bias_grad(w.dqkv16, R, 3 * E, 1.f, c->bias_scratch, c->grads.bin, st, 3 * E), "bias_grad(in_proj)");
+  AFR_CUDA(c, launch_wide_colsum_bf16(w.dqkv16, R, 3 * E, w.ln_part, w.max_ln_parts, c->grads.bin, c->sms, st),
+           "bias_grad(in_proj)");
   c->launches += 3;
   // in-projection
   if ((rc = wide_gemm(c, w.dqkv16, 3 * E, false, w.win16, 3 * E, true, R, E, 3 * E, w.a32, E, nullptr, 1, st,
@@ -436,7 +439,8 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
                                 ? ((3 * E + 127) / 128 * 128) * E : ((F + 127) / 128 * 128) * E;
       alloc(reinterpret_cast<void**>(&w.splitk), static_cast<size_t>(w.max_splits) * max_mn * 4);
       w.max_ln_parts = c->num_sms * 4;
-      alloc(reinterpret_cast<void**>(&w.ln_part), static_cast<size_t>(w.max_ln_parts) * 2 * E * 4);
+      alloc(reinterpret_cast<void**>(&w.ln_part),
+            static_cast<size_t>(w.max_ln_parts) * (3 * E > F ? 3 * E : F) * 4);   // LayerNorm / bias-gradient partial rows
       alloc(reinterpret_cast<void**>(&w.pos_part), static_cast<size_t>(c->num_sms) * cfg->max_length * E * 4);
       if (static_cast<size_t>(cfg->vocab) * E * 4 <= 128 * 1024)
         alloc(reinterpret_cast<void**>(&w.emb_part), static_cast<size_t>(c->num_sms) * cfg->vocab * E * 4);

@@ -102,7 +102,7 @@ wide_embed_kernel(WideDims d, WideDrop dr, const long long* __restrict__ tokens,
 // log2 domain (MUFU.EX2), one Philox block per 8 keys. Leaves the context rows as bf16 (A operand
 // of the out-projection GEMM) and, in training, (row max, 1 / row sum) and the keep bits.
 template <int DH>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 wide_attention_fwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx16,
                           float2* __restrict__ stat, uint32_t* __restrict__ abits) {
   extern __shared__ __align__(16) float smem[];
@@ -383,7 +383,7 @@ wide_colsum_partials_kernel(const float* __restrict__ partials, int n, int width
 //   pass B, thread = (head, key)  : dk = sum_q dS q / sqrt(dh) ; dv = sum_q P_kept d(ctx) / (1 - p)
 // Output: d(q | k | v) rows as bf16 [B*S, 3E] (operand of the in-projection's dgrad / wgrad GEMMs).
 template <int DH>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 wide_attention_bwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv, const float* __restrict__ dctx,
                           const __nv_bfloat16* __restrict__ ctx16, const float2* __restrict__ stat,
                           const uint32_t* __restrict__ abits, __nv_bfloat16* __restrict__ dqkv16) {
@@ -576,6 +576,33 @@ wide_embed_bwd_kernel(WideDims d, WideDrop dr, const long long* __restrict__ tok
       emb_partials[static_cast<long long>(blockIdx.x) * d.vocab * E + i] = hist[i];
 }
 
+// Column sums of a bf16 matrix [rows, width] (bias gradients: d(in_proj / out_proj / fc1 bias) =
+// sum over all token rows). CTA c sums rows c, c + grid, ... for every column (a thread owns a pair
+// of adjacent columns) and leaves one partial row; wide_colsum_partials_kernel adds them in order.
+__global__ void __launch_bounds__(256)
+wide_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int width, float* __restrict__ partials) {
+  const int pairs = width / 2;
+  const int rows_per_iter = 256 / pairs > 0 ? 256 / pairs : 1;      // several rows at once when narrow
+  const int lane_pair = threadIdx.x % pairs, lane_row = threadIdx.x / pairs;
+  __shared__ float2 red[256];
+  float2 acc = make_float2(0.f, 0.f);
+  if (threadIdx.x < pairs * rows_per_iter) {
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_iter + lane_row; r < rows;
+         r += static_cast<long long>(gridDim.x) * rows_per_iter) {
+      const float2 v = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(x + r * width)[lane_pair]);
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < pairs) {
+    float2 s = red[threadIdx.x];
+    for (int k = 1; k < rows_per_iter; ++k) { s.x += red[threadIdx.x + k * pairs].x; s.y += red[threadIdx.x + k * pairs].y; }
+    partials[static_cast<long long>(blockIdx.x) * width + 2 * threadIdx.x] = s.x;
+    partials[static_cast<long long>(blockIdx.x) * width + 2 * threadIdx.x + 1] = s.y;
+  }
+}
+
 // out[m][n] = sum over the K pieces of partials[ks][m][n]; a piece has rows_pad >= M rows (split-K
 // weight gradients, fixed summation order)
 __global__ void __launch_bounds__(256)
@@ -628,7 +655,7 @@ cudaError_t launch_wide_attention_fwd(const WideDims& d, const WideDrop& dr, con
                                       __nv_bfloat16* ctx16, float2* stat, uint32_t* abits, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(2) * (d.S + 8) * d.E * 4;
   int threads = d.H * ((d.S + 31) & ~31);
-  if (threads > 1024) threads = 1024;
+  if (threads > 512) threads = 512;      // 128 registers per thread: q / acc rows stay in registers
   cudaError_t e;
   switch (d.dh) {
     case 8:
@@ -653,7 +680,7 @@ cudaError_t launch_wide_attention_bwd(const WideDims& d, const WideDrop& dr, con
                                       __nv_bfloat16* dqkv16, cudaStream_t st) {
   const size_t smem = (static_cast<size_t>(4) * d.S * d.E + static_cast<size_t>(d.S) * d.H) * 4;
   int threads = d.H * ((d.S + 31) & ~31);
-  if (threads > 1024) threads = 1024;
+  if (threads > 512) threads = 512;
   cudaError_t e;
   switch (d.dh) {
     case 8:
@@ -761,6 +788,19 @@ cudaError_t launch_wide_embed_bwd(const WideDims& d, const WideDrop& dr, const l
     e = cudaGetLastError();
   }
   return e;
+}
+
+cudaError_t launch_wide_colsum_bf16(const __nv_bfloat16* x, long long rows, int width, float* partials,
+                                    int max_partials, float* out, int num_sms, cudaStream_t st) {
+  if (width < 2 || (width % 2) != 0 || width > 512) return cudaErrorInvalidValue;
+  int grid = num_sms * 4;
+  if (grid > max_partials) grid = max_partials;
+  if (grid > rows) grid = static_cast<int>(rows);
+  wide_colsum_bf16_kernel<<<grid, 256, 0, st>>>(x, rows, width, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  wide_colsum_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, grid, width, out, width, nullptr);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_wide_split_weight(const float* w, int rows, int E, __nv_bfloat16* out, cudaStream_t st) {

@@ -384,6 +384,173 @@ def workload_config(n_gpus, step_mode="two-kernel", dp_mode=None):
                   "through the 126 MB L2 and rotates over 8 resident batches"}
 
 
+
+# ------------------------------------------------------------------------------------ config 4
+CFG4 = dict(max_length=64, sheet_height=64, sheet_width=64, vocab=128, embedding_dim=128, num_heads=8,
+            fc1_width=128)
+CFG4_BATCH = 8192
+
+
+def run_config4(args, rank, local_rank, world):
+    """BASELINE.json configs[3]: scaled synthetic workload -- 64 x 64 glyph bitmaps, 64-char strings,
+    widened net (embed 128, 8 heads, fc1 128: fc_output 8192 -> 4096), 8192 glyphs per GPU per step
+    (65,536 global at 8 GPUs, weak scaling). An extension: the reference has no such configuration
+    (restated-oracle parity, tests/test_wide_gpu.py). Same step as config 2: forward + clamp/MSE +
+    backward + AdamW, batch resident / from pinned host memory for e2e."""
+    import torch.distributed as dist
+    from ai_font_renderer_b200.data import HostBatchFeeder
+    from ai_font_renderer_b200.optim import FusedAdamW
+    from ai_font_renderer_b200.renderer import AttentionFontRenderer
+    from ai_font_renderer_b200.training import backward_and_step, row_buckets
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+    args.warmup = max(3, args.warmup)
+    B = args.batch if args.batch != BATCH_PER_GPU else CFG4_BATCH
+    gB = B * world
+    L, H_, W_ = CFG4["max_length"], CFG4["sheet_height"], CFG4["sheet_width"]
+    P, K = H_ * W_, L * CFG4["fc1_width"]
+    torch.manual_seed(SEED)
+    model = AttentionFontRenderer(**CFG4).to(device).train()
+    step_mode = ("background" if args.step_mode == "auto" else args.step_mode) if world == 1 else "two-kernel"
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=step_mode == "fused",
+                     background=step_mode == "background")
+    dp_mode = None
+    if world > 1:
+        from ai_font_renderer_b200.training import PeerLink
+        dp_mode = args.dp_mode
+        if dp_mode == "auto":
+            dp_mode = "nvls-side" if PeerLink.nvls_available() else "peer-side"
+        if dp_mode != "nccl":
+            PeerLink(model, ctas=args.comm_ctas or 16, inline=dp_mode in ("peer", "nvls"), nvls=dp_mode.startswith("nvls"))
+    n_rot = 4
+    g = torch.Generator().manual_seed(1234 + rank)
+    n = B * n_rot
+    lengths = torch.randint(10, L + 1, (n, 1), generator=g)
+    letters = torch.randint(65, 91, (n, L), generator=g)
+    letters[torch.rand((n, L), generator=g) < 0.148] = 32
+    tok_h = torch.where(torch.arange(L).unsqueeze(0) < lengths, letters, torch.zeros_like(letters)).long()
+    # U-shaped grey levels, 80 % white (SURVEY 8d config 4)
+    tgt_h = torch.where(torch.rand((n, H_, W_), generator=g) < 0.8, torch.full((n, H_, W_), 255, dtype=torch.uint8),
+                        (torch.randint(0, 4, (n, H_, W_), generator=g) * 64).to(torch.uint8))
+    tok_h, tgt_h = tok_h.pin_memory(), tgt_h.pin_memory()
+    tok_d, tgt_d = tok_h.to(device), tgt_h.to(device)
+    buckets = row_buckets(P, 1)
+    count = float(gB) * P
+    loss_buf = torch.zeros(args.steps + args.warmup + 8, dtype=torch.float32, device=device)
+
+    def step_resident(i):
+        s = (i % n_rot) * B
+        model.fused_forward_loss(tok_d[s:s + B], tgt_d[s:s + B], loss_count=count, sample_offset=rank * B,
+                                 loss_out=loss_buf[i])
+        backward_and_step(model, opt, buckets, world)
+
+    feeder = HostBatchFeeder(tok_h, tgt_h, B, device)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_ready, loss_copied = torch.cuda.Event(), torch.cuda.Event()
+
+    def step_e2e(i):
+        x_dev, t_dev = feeder.get(i)
+        loss = model.fused_forward_loss(x_dev, t_dev, loss_count=count, sample_offset=rank * B)
+        loss_ready.record()
+        with torch.cuda.stream(feeder.copy_stream):
+            feeder.copy_stream.wait_event(loss_ready)
+            loss_host.copy_(loss.view(1), non_blocking=True)
+            loss_copied.record()
+        backward_and_step(model, opt, buckets, world)
+        feeder.done(i)
+        loss_copied.synchronize()
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.kernel_launches()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        model.join_pending()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = model.kernel_launches() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, launches
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches = timed(step_resident, args.steps)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    model.check_tokens_in_range()
+    # the three fc_output GEMMs alone (tensor-bound part of the step), CUDA events around each
+    ctx = model._ctx
+    st = torch.cuda.current_stream(device).cuda_stream
+    model.fused_forward_loss(tok_d[:B], tgt_d[:B], loss_count=count)
+    gemm_ms = {}
+    for name, call in (("wgrad", lambda: ctx.lib.afr_train_wgrad(ctx.handle, 0, P, st)),
+                       ("dgrad", lambda: ctx.lib.afr_train_dgrad_gemm(ctx.handle, st))):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            ctx.check(call())
+        e1.record()
+        torch.cuda.synchronize()
+        gemm_ms[name] = e0.elapsed_time(e1) / 5
+    final_loss = float(loss_buf[args.steps - 1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peaks = load_peaks()
+    value = gB * args.steps / (ms_res / 1e3)
+    flop_gemm = 2.0 * B * K * P
+    front_flop = B * (2.0 * L * 128 * (384 + 128 + 128) * 3 * 3 + 2.0 * 8 * L * L * 16 * 2 * 3.5)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "config[3] scaled synthetic: 64x64 glyph sheets, 64-char strings, widened net "
+                               "(embed 128, 8 heads, fc1 128; fc_output 8192 -> 4096), 8192 glyphs per GPU per step "
+                               "(65,536 global at 8 GPUs); extension of the reference, restated-oracle parity",
+                   "batch_per_gpu": B, "global_batch": gB, "max_length": L, "sheet": f"{H_}x{W_}",
+                   "params": sum(p.numel() for p in model.parameters()), "step_mode": step_mode,
+                   "parallelism": f"dp{world} ({dp_mode})" if world > 1 else "single",
+                   "l2": "no flush: one step streams > 5 GB of activations through the 126 MB L2 and rotates over "
+                         "4 resident batches"},
+        "e2e": {"value": gB * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": int(feeder.h2d_bytes_per_batch), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (fc_output wgrad GEMM, 4096 x 8192 x 8192)",
+                     "bound": "tensor", "achieved": flop_gemm / (gemm_ms["wgrad"] / 1e3) / 1e12,
+                     "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                     "frac": flop_gemm / (gemm_ms["wgrad"] / 1e3) / 1e12 / peaks["tf_burst"], "traffic": None,
+                     "ms_per_launch": gemm_ms["wgrad"], "dgrad_ms": gemm_ms["dgrad"],
+                     "dgrad_tflops": flop_gemm / (gemm_ms["dgrad"] / 1e3) / 1e12,
+                     "peak_source": peaks["source"],
+                     "note": "the step is dominated by the fp32 SIMT attention kernels of the wide front-end "
+                             "(profiles/r02_config4_launches.csv), not by this GEMM"},
+        "train_tflops_whole_step": value * (3 * 2.0 * K * P + front_flop / B) / 1e12 / world,
+        "final_loss": final_loss,
+    }
+    emit_line(line)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -410,6 +577,10 @@ def main():
     ap.add_argument("--bg-ctas", type=int, default=0, help="background sweep: CTAs (0 = one per SM)")
     ap.add_argument("--no-fuse", action="store_true",
                     help="single GPU: same as --step-mode two-kernel")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+                    help="BASELINE.json workload: 2 = configs[1], the reference's model on one B200 (the metric's "
+                         "configuration, default); 4 = configs[3], the scaled synthetic workload (64x64 sheets, "
+                         "64-char strings, widened net 128/8/128, 8192 glyphs per GPU = 64k global at 8 GPUs)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-B200 baseline")
     ap.add_argument("--no-dp-parity", action="store_true", help="N > 1: skip the parity check before timing")
     ap.add_argument("--overlap-dgrad", action="store_true",
@@ -426,6 +597,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return 0
+    if args.config == 4:
+        return run_config4(args, rank, local_rank, world)
 
     import torch.distributed as dist
     from ai_font_renderer_b200.data import HostBatchFeeder, fast_synthetic_batch

@@ -241,3 +241,28 @@ def test_default_background_step_is_bit_identical_to_two_kernel_step(default_sta
             assert torch.equal(out[0]["state"][k], other["state"][k]), k
         for k in ("m", "v", "shadow"):
             assert torch.equal(out[0][k], other[k]), k
+
+
+# ------------------------------------------------------------------------------------ config 5, public API
+def test_render_strings_of_cjk_text_on_a_bmp_vocabulary_model(tmp_path):
+    """render_strings (helpers.py:46-74) on a model whose embedding covers the Unicode BMP: the
+    tokens are ord() of every character (helpers.py:57), the BMP files hold the oracle's pixels."""
+    from ai_font_renderer_b200.data import read_bmp_grey
+    from ai_font_renderer_b200.render import render_strings
+    cfg = orc.OracleConfig(vocab=65536, max_length=24, sheet_h=16, sheet_w=64)
+    state = orc.init_state(cfg, seed=5)
+    model = make_model(cfg, state).eval()
+    strings = ["\u65e5\u672c\u8a9e\u306e\u30c6\u30ad\u30b9\u30c8", "HELLO \u4e16\u754c", "\uffff\u00e9A", ""]
+    render_strings(model, strings, str(tmp_path), cfg.sheet_h, cfg.sheet_w, dev())
+    tokens = torch.zeros((len(strings), cfg.max_length), dtype=torch.int64)
+    for i, s_ in enumerate(strings):
+        tokens[i, :len(s_)] = torch.tensor([ord(c) for c in s_], dtype=torch.int64)
+    q_ref = orc.quantise_u8(orc.forward(state, tokens, cfg))
+    for i in range(len(strings)):
+        got = read_bmp_grey(str(tmp_path / f"string_{i}.bmp"))
+        assert ((got >= 128) == (q_ref[i] >= 128)).mean() >= 0.999
+        assert (np.abs(got.astype(int) - q_ref[i].astype(int)) <= 2).mean() >= 0.999
+    small = make_model(orc.OracleConfig(max_length=24, sheet_h=16, sheet_w=64),
+                       orc.init_state(orc.OracleConfig(max_length=24, sheet_h=16, sheet_w=64), seed=5)).eval()
+    with pytest.raises(IndexError):
+        render_strings(small, strings, str(tmp_path / "x"), 16, 64, dev())

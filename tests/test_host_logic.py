@@ -308,3 +308,20 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_encode_uses_ord_for_any_code_point_and_render_checks_the_vocabulary():
+    """helpers.py:57 encodes with ord(): code points above 255 (CJK, the BMP render set of
+    BASELINE config 5) must survive; a code point outside the embedding table is the reference's
+    IndexError (model.py:167), raised on the host before anything is launched."""
+    from types import SimpleNamespace
+    from ai_font_renderer_b200.data import encode
+    from ai_font_renderer_b200.render import check_token_range, strings_to_tokens
+    tok = encode(["A\u00e9\u4e2d\uffff", "\u65e5\u672c"], 6)
+    assert tok.tolist() == [[65, 0xE9, 0x4E2D, 0xFFFF, 0, 0], [0x65E5, 0x672C, 0, 0, 0, 0]]
+    small = SimpleNamespace(embedding=SimpleNamespace(num_embeddings=128), max_length=6)
+    big = SimpleNamespace(embedding=SimpleNamespace(num_embeddings=65536), max_length=6)
+    check_token_range(big, tok)
+    with pytest.raises(IndexError):
+        check_token_range(small, tok)
+    check_token_range(small, strings_to_tokens(["HELLO"], 6))
