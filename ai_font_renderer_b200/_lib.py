@@ -107,6 +107,12 @@ SIGNATURES = {
     "afr_adamw_rows_bg": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                     C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
     "afr_train_wgrad_to": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "afr_train_wgrad_to_bf16": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "afr_adamw_rows_gather_bf16": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                             C.c_int64, C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P),
+                                             C.c_int, C.c_int, _P]),
+    "afr_adamw_rows_gather_nvls_bf16": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                  C.c_int64, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "afr_adamw_small": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_int64, _P]),
     "afr_train_wgrad_adamw": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,

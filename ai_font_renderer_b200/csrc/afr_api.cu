@@ -855,8 +855,21 @@ int afr_adamw_rows_bg(afr_ctx* c, double lr, double beta1, double beta2, double 
   return AFR_OK;
 }
 
+static int wgrad_to_impl(afr_ctx* c, int row_begin, int row_end, void* grad_rows, bool bf16_out, int with_bias,
+                         void* stream);
+
 int afr_train_wgrad_to(afr_ctx* c, int row_begin, int row_end, float* grad_rows, int with_bias,
                        void* stream) {
+  return wgrad_to_impl(c, row_begin, row_end, grad_rows, false, with_bias, stream);
+}
+
+int afr_train_wgrad_to_bf16(afr_ctx* c, int row_begin, int row_end, void* grad_rows_bf16, int with_bias,
+                            void* stream) {
+  return wgrad_to_impl(c, row_begin, row_end, grad_rows_bf16, true, with_bias, stream);
+}
+
+static int wgrad_to_impl(afr_ctx* c, int row_begin, int row_end, void* grad_rows, bool bf16_out, int with_bias,
+                         void* stream) {
   if (!c) return AFR_ERR_INVALID;
   if (!c->fwd_done) return fail(c, AFR_ERR_STATE, "afr_train_wgrad_to before a training forward");
   if (grad_rows == nullptr) return fail(c, AFR_ERR_INVALID, "afr_train_wgrad_to: grad_rows is NULL");
@@ -870,6 +883,7 @@ int afr_train_wgrad_to(afr_ctx* c, int row_begin, int row_end, float* grad_rows,
   GemmEpilogue ep{};
   ep.kind = kEpiF32;
   ep.out = grad_rows;
+  ep.out_bf16 = bf16_out ? 1 : 0;
   ep.ldo = c->K; ep.alpha = c->grad_scale; ep.use_tma_store = env_int("AFR_NO_TMA_STORE") ? 0 : 1;
   const char* msg = nullptr;
   ep.cta2 = c->cta2; ep.smem_reserve = c->smem_reserve;
@@ -1002,6 +1016,65 @@ int afr_adamw_rows_gather_nvls(afr_ctx* c, double lr, double beta1, double beta2
            "adamw_gather_nvls(fc_output.weight rows)");
   c->launches += 1;
   c->shadow_rows_swept += row_end - row_begin;   // completed by the multicast stores; afr_shadow_commit
+  return AFR_OK;
+}
+
+
+int afr_adamw_rows_gather_bf16(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, int64_t step, int row_begin, int row_end,
+                               const void* const* peer_grads, void* const* peer_shadows, int world,
+                               int ctas, void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_state) return fail(c, AFR_ERR_STATE, "params / adam state not bound");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
+    return fail(c, AFR_ERR_INVALID, "bad step or row range");
+  if (peer_grads == nullptr || peer_shadows == nullptr || world < 1 || world > 8 || ctas < 1)
+    return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_gather_bf16: need 1..8 peers and ctas >= 1");
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  const long long n = static_cast<long long>(row_end - row_begin) * c->K;
+  if ((n % 8) != 0 || (off % 8) != 0) return fail(c, AFR_ERR_INVALID, "row range must cover whole 16-byte bf16 groups");
+  const __nv_bfloat16* g[8];
+  __nv_bfloat16* sh[8];
+  for (int q = 0; q < world; ++q) {
+    if (peer_grads[q] == nullptr || peer_shadows[q] == nullptr)
+      return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_gather_bf16: null peer pointer");
+    g[q] = static_cast<const __nv_bfloat16*>(peer_grads[q]) + off;
+    sh[q] = static_cast<__nv_bfloat16*>(peer_shadows[q]) + off;
+  }
+  DeviceGuard guard(c->cfg.device);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  AFR_CUDA(c, launch_adamw_gather_bf16(c->params.wout + off, c->m.wout + off, c->v.wout + off, n, h, g, sh,
+                                       world, ctas, static_cast<cudaStream_t>(stream)),
+           "adamw_gather_bf16(fc_output.weight rows)");
+  c->launches += 1;
+  c->shadow_rows_swept += row_end - row_begin;
+  return AFR_OK;
+}
+
+int afr_adamw_rows_gather_nvls_bf16(afr_ctx* c, double lr, double beta1, double beta2, double eps,
+                                    double weight_decay, int64_t step, int row_begin, int row_end,
+                                    const void* grad_multicast, void* shadow_multicast, int ctas,
+                                    void* stream) {
+  if (!c) return AFR_ERR_INVALID;
+  if (!c->has_params || !c->has_state) return fail(c, AFR_ERR_STATE, "params / adam state not bound");
+  if (!c->cfg.training) return fail(c, AFR_ERR_STATE, "context created with training = 0");
+  if (step < 1 || row_begin < 0 || row_end > c->P || row_begin >= row_end)
+    return fail(c, AFR_ERR_INVALID, "bad step or row range");
+  if (grad_multicast == nullptr || shadow_multicast == nullptr || ctas < 1)
+    return fail(c, AFR_ERR_INVALID, "afr_adamw_rows_gather_nvls_bf16: null multicast pointer or ctas < 1");
+  const long long off = static_cast<long long>(row_begin) * c->K;
+  const long long n = static_cast<long long>(row_end - row_begin) * c->K;
+  if ((n % 8) != 0 || (off % 8) != 0) return fail(c, AFR_ERR_INVALID, "row range must cover whole 16-byte bf16 groups");
+  DeviceGuard guard(c->cfg.device);
+  const AdamHyper h = make_hyper(lr, beta1, beta2, eps, weight_decay, step);
+  AFR_CUDA(c, launch_adamw_gather_nvls_bf16(c->params.wout + off, c->m.wout + off, c->v.wout + off, n, h,
+                                            static_cast<const __nv_bfloat16*>(grad_multicast) + off,
+                                            static_cast<__nv_bfloat16*>(shadow_multicast) + off, ctas,
+                                            static_cast<cudaStream_t>(stream)),
+           "adamw_gather_nvls_bf16(fc_output.weight rows)");
+  c->launches += 1;
+  c->shadow_rows_swept += row_end - row_begin;
   return AFR_OK;
 }
 

@@ -271,6 +271,99 @@ adamw_gather_nvls_kernel(float* __restrict__ p, float* __restrict__ m, float* __
   for (; i < n4; i += stride) adamw_group_nvls(p, m, v, i, ld_reduce_mc(g_mc, i), h, sh_mc);
 }
 
+// ---- bf16 gradients over NVLink: half the egress of the fp32 forms above. Groups of 8 elements.
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float4& lo, float4& hi) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
+  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+  lo = make_float4(a.x, a.y, b.x, b.y);
+  hi = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ uint4 adamw_group8(float* p, float* m, float* v, long long i8, const float4& glo,
+                                              const float4& ghi, const AdamPairConst& c) {
+  float4 p0 = reinterpret_cast<float4*>(p)[2 * i8], p1 = reinterpret_cast<float4*>(p)[2 * i8 + 1];
+  float4 m0 = reinterpret_cast<float4*>(m)[2 * i8], m1 = reinterpret_cast<float4*>(m)[2 * i8 + 1];
+  float4 v0 = reinterpret_cast<float4*>(v)[2 * i8], v1 = reinterpret_cast<float4*>(v)[2 * i8 + 1];
+  adamw_quad(p0, glo, m0, v0, c);
+  adamw_quad(p1, ghi, m1, v1, c);
+  reinterpret_cast<float4*>(p)[2 * i8] = p0; reinterpret_cast<float4*>(p)[2 * i8 + 1] = p1;
+  reinterpret_cast<float4*>(m)[2 * i8] = m0; reinterpret_cast<float4*>(m)[2 * i8 + 1] = m1;
+  reinterpret_cast<float4*>(v)[2 * i8] = v0; reinterpret_cast<float4*>(v)[2 * i8 + 1] = v1;
+  const __nv_bfloat162 a = __floats2bfloat162_rn(p0.x, p0.y), b = __floats2bfloat162_rn(p0.z, p0.w);
+  const __nv_bfloat162 cc = __floats2bfloat162_rn(p1.x, p1.y), d = __floats2bfloat162_rn(p1.z, p1.w);
+  return make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                    *reinterpret_cast<const uint32_t*>(&cc), *reinterpret_cast<const uint32_t*>(&d));
+}
+struct GatherPeers16 {
+  const __nv_bfloat16* g[kMaxPeers];
+  __nv_bfloat16* sh[kMaxPeers];
+  int world;
+};
+__global__ void __launch_bounds__(1024, 1)
+adamw_gather_bf16_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long long n8,
+                         AdamHyper h, GatherPeers16 peers) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int W = peers.world;
+  const AdamPairConst c(h);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    uint4 g[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < W)
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(g[q].x), "=r"(g[q].y), "=r"(g[q].z), "=r"(g[q].w)
+                     : "l"(reinterpret_cast<const uint4*>(peers.g[q]) + i));
+    float4 slo, shi;
+    unpack_bf16x8(g[0], slo, shi);
+#pragma unroll
+    for (int q = 1; q < kMaxPeers; ++q)
+      if (q < W) {
+        float4 lo, hi;
+        unpack_bf16x8(g[q], lo, hi);
+        slo.x += lo.x; slo.y += lo.y; slo.z += lo.z; slo.w += lo.w;
+        shi.x += hi.x; shi.y += hi.y; shi.z += hi.z; shi.w += hi.w;
+      }
+    const uint4 packed = adamw_group8(p, m, v, i, slo, shi, c);
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      if (q < W) reinterpret_cast<uint4*>(peers.sh[q])[i] = packed;
+  }
+}
+// in-switch sum of the bf16 gradients with fp32 accumulation
+__device__ __forceinline__ uint4 ld_reduce_mc_bf16(const __nv_bfloat16* g_mc, long long i8) {
+  uint4 s;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(s.x), "=r"(s.y), "=r"(s.z), "=r"(s.w)
+               : "l"(reinterpret_cast<const uint4*>(g_mc) + i8)
+               : "memory");
+  return s;
+}
+__global__ void __launch_bounds__(1024, 1)
+adamw_gather_nvls_bf16_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long long n8,
+                              AdamHyper h, const __nv_bfloat16* g_mc, __nv_bfloat16* sh_mc) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const AdamPairConst c(h);
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto one = [&](long long j, const uint4& s) {
+    float4 lo, hi;
+    unpack_bf16x8(s, lo, hi);
+    const uint4 packed = adamw_group8(p, m, v, j, lo, hi, c);
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(
+                     reinterpret_cast<uint4*>(sh_mc) + j),
+                 "r"(packed.x), "r"(packed.y), "r"(packed.z), "r"(packed.w)
+                 : "memory");
+  };
+  for (; i + 3 * stride < n8; i += 4 * stride) {
+    uint4 s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = ld_reduce_mc_bf16(g_mc, i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(i + u * stride, s[u]);
+  }
+  for (; i < n8; i += stride) one(i, ld_reduce_mc_bf16(g_mc, i));
+}
+
 constexpr int kMaxSmallJobs = 16;
 struct SmallJobs { SmallAdamJob j[kMaxSmallJobs]; int n; };
 
@@ -464,6 +557,25 @@ cudaError_t launch_adamw_gather_nvls(float* p, float* m, float* v, long long n, 
                                      const float* g_mc, __nv_bfloat16* sh_mc, int ctas, cudaStream_t s) {
   if ((n % 4) != 0 || ctas < 1 || g_mc == nullptr || sh_mc == nullptr) return cudaErrorInvalidValue;
   adamw_gather_nvls_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 4, h, g_mc, sh_mc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_gather_bf16(float* p, float* m, float* v, long long n, const AdamHyper& h,
+                                     const __nv_bfloat16* const* peer_g, __nv_bfloat16* const* peer_shadow,
+                                     int world, int ctas, cudaStream_t s) {
+  if (world < 1 || world > kMaxPeers || (n % 8) != 0 || ctas < 1) return cudaErrorInvalidValue;
+  GatherPeers16 peers{};
+  peers.world = world;
+  for (int q = 0; q < world; ++q) { peers.g[q] = peer_g[q]; peers.sh[q] = peer_shadow[q]; }
+  adamw_gather_bf16_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 8, h, peers);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adamw_gather_nvls_bf16(float* p, float* m, float* v, long long n, const AdamHyper& h,
+                                          const __nv_bfloat16* g_mc, __nv_bfloat16* sh_mc, int ctas,
+                                          cudaStream_t s) {
+  if ((n % 8) != 0 || ctas < 1 || g_mc == nullptr || sh_mc == nullptr) return cudaErrorInvalidValue;
+  adamw_gather_nvls_bf16_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 8, h, g_mc, sh_mc);
   return cudaGetLastError();
 }
 

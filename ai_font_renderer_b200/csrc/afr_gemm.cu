@@ -135,6 +135,15 @@ cudaError_t launch_gemm_bf16(const __nv_bfloat16* A, long long lda, bool a_mn,
   p.kb_per_split = kb_per_split;
   p.split_rows = ((M + kBM - 1) / kBM) * kBM;
   int use_tma_store = epi.use_tma_store;
+  p.out_bf16 = 0;
+  if (epi.kind == kEpiF32 && epi.out_bf16) {
+    if ((reinterpret_cast<uintptr_t>(epi.out) & 15) || (epi.ldo % 8) != 0 || k_splits > 1) {
+      if (err_msg) *err_msg = "gemm: bf16 output needs a 16-byte aligned pointer, ldo % 8 == 0 and no split-K";
+      return cudaErrorInvalidValue;
+    }
+    p.out_bf16 = 1;
+    use_tma_store = 0;
+  }
   if (epi.kind == kEpiF32 && use_tma_store) {
     if ((reinterpret_cast<uintptr_t>(epi.out) & 15) || (epi.ldo % 4) != 0) {
       use_tma_store = 0;  // unaligned output: fall back to direct stores

@@ -105,6 +105,7 @@ struct GemmParams {
   int k_splits;
   int kb_per_split;
   int split_rows;        // rows per K piece in the output: M rounded up to a whole tile
+  int out_bf16;          // kEpiF32: the output is bf16 [M, ldo] (direct 64-byte row stores), not fp32
 };
 
 // CTA2: the kernel runs as clusters of two CTAs (one TPC) that execute 256-row MMAs together
@@ -489,7 +490,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             if (p.clamp01) z = fminf(fmaxf(z, 0.f), 1.f);
             v[j] = z;
           }
-          if (p.use_tma_store) {
+          if (p.out_bf16) {
+            // bf16 output (the data-parallel gradient that crosses NVLink): a lane owns a row,
+            // its 32 columns are 64 contiguous bytes = two full sectors
+            if (row_ok) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.ldo + n;
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                const __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * ch], v[8 * ch + 1]);
+                const __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * ch + 2], v[8 * ch + 3]);
+                const __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * ch + 4], v[8 * ch + 5]);
+                const __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * ch + 6], v[8 * ch + 7]);
+                *reinterpret_cast<uint4*>(o + 8 * ch) =
+                    make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                               *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+              }
+            }
+          } else if (p.use_tma_store) {
             uint8_t* buf = my_stage + store_buf * kEpiWarpBufBytes;
             if (lane == 0) ptx::tma_store_wait_read<1>();
             __syncwarp();

@@ -140,6 +140,21 @@ class FusedAdamW(torch.optim.Optimizer):
                                                      grad_mc, shadow_mc, ctas, _stream_ptr(ctx.device)))
 
     @torch.no_grad()
+    def step_rows_gather_any(self, t: int, row_begin: int, row_end: int, link, shadow_index: int, world: int):
+        """Dispatch over the four forms of the gather / AdamW / broadcast kernel a PeerLink selects:
+        peer loads or NVSwitch multicast, fp32 or bf16 gradient buffers."""
+        ctx, _ = self._bucket
+        st = _stream_ptr(ctx.device)
+        args = (ctx.handle, *self._hyper(), t, row_begin, row_end)
+        lib = ctx.lib
+        if link.nvls:
+            fn = lib.afr_adamw_rows_gather_nvls_bf16 if link.grad_bf16 else lib.afr_adamw_rows_gather_nvls
+            ctx.check(fn(*args, link.grad_mc, link.shadow_mc[shadow_index], link.ctas, st))
+        else:
+            fn = lib.afr_adamw_rows_gather_bf16 if link.grad_bf16 else lib.afr_adamw_rows_gather
+            ctx.check(fn(*args, link.grad_ptrs, link.shadow_ptrs[shadow_index], world, link.ctas, st))
+
+    @torch.no_grad()
     def step_small(self, t: int):
         ctx, _ = self._bucket
         ctx.check(ctx.lib.afr_adamw_small(ctx.handle, *self._hyper(), t, _stream_ptr(ctx.device)))

@@ -477,6 +477,17 @@ class AttentionFontRenderer(nn.Module):
         c = self._ctx
         c.check(c.lib.afr_train_wgrad(c.handle, row_begin, row_end, _stream_ptr(self.fc_output.weight.device)))
 
+    def wgrad_rows_to(self, row_begin: int, row_end: int, dst: torch.Tensor, bf16: bool = False,
+                      with_bias: bool = True):
+        """afr_train_wgrad_to(_bf16): the gradient rows go to `dst` ([H*W, 64*max_length], fp32 or
+        bf16 -- e.g. a peer-mapped buffer) instead of fc_output.weight.grad."""
+        c = self._ctx
+        K = self.fc_output.weight.shape[1]
+        ptr = dst.data_ptr() + row_begin * K * dst.element_size()
+        fn = c.lib.afr_train_wgrad_to_bf16 if bf16 else c.lib.afr_train_wgrad_to
+        c.check(fn(c.handle, row_begin, row_end, ptr, 1 if with_bias else 0,
+                   _stream_ptr(self.fc_output.weight.device)))
+
     def dgrad_gemm(self):
         """d(features) = d(logits) W on the current stream (first half of afr_train_dgrad)."""
         c = self._ctx

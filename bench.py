@@ -379,7 +379,9 @@ def workload_config(n_gpus, step_mode="two-kernel", dp_mode=None):
                             + ("gradient rows summed inside the NVSwitch (multimem.ld_reduce), bf16 rows multicast"
                                if (dp_mode or "").startswith("nvls") else
                                "NCCL reduce-scatter / all-gather" if dp_mode == "nccl" else
-                               "gradient rows read from / bf16 rows stored to NVLink peer memory")) if n_gpus > 1 else "single",
+                               "gradient rows read from / bf16 rows stored to NVLink peer memory")
+                            + ("; gradient rows cross the links as bf16, summed in fp32" if (dp_mode or "").endswith("-bf16") else "")
+                            ) if n_gpus > 1 else "single",
             "l2": "no flush: one step streams 3.9 GB (fp32 master, grads, Adam moments, bf16 shadow) "
                   "through the 126 MB L2 and rotates over 8 resident batches"}
 
@@ -560,7 +562,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
-    ap.add_argument("--dp-mode", default="auto", choices=["auto", "peer", "peer-side", "nvls", "nvls-side", "nccl"],
+    ap.add_argument("--dp-mode", default="auto",
+                    choices=["auto", "peer", "peer-side", "nvls", "nvls-side", "nccl", "peer-bf16", "peer-side-bf16",
+                             "nvls-bf16", "nvls-side-bf16"],
                     help="N > 1: 'peer' = row-sharded AdamW reading/writing NVLink peer memory in one "
                          "kernel on all SMs of the compute stream, 'peer-side' = the same kernel on a side "
                          "stream on --comm-ctas SMs under the rest of backward, 'nccl' = reduce-scatter / "
@@ -647,10 +651,11 @@ def main():
             # on a side stream under the rest of backward; with NVSwitch multicast (NVLS) its inbound
             # traffic and SM time shrink (2 GPUs 1.65 vs 1.82 ms, 8 GPUs 1.51 vs 1.55 ms)
             args.dp_mode = "nvls-side" if PeerLink.nvls_available() else ("peer" if world == 2 else "peer-side")
-        if args.dp_mode in ("peer", "peer-side", "nvls", "nvls-side"):
+        dp_base = args.dp_mode[:-5] if args.dp_mode.endswith("-bf16") else args.dp_mode
+        if dp_base in ("peer", "peer-side", "nvls", "nvls-side"):
             try:
-                PeerLink(model, ctas=args.comm_ctas, inline=args.dp_mode in ("peer", "nvls"),
-                         nvls=args.dp_mode.startswith("nvls"))
+                PeerLink(model, ctas=args.comm_ctas, inline=dp_base in ("peer", "nvls"),
+                         nvls=dp_base.startswith("nvls"), grad_bf16=args.dp_mode.endswith("-bf16"))
             except Exception as exc:     # no symmetric memory / peer access on this system
                 sys.stderr.write(f"[bench] PeerLink unavailable ({exc}); falling back to --dp-mode nccl\n")
                 args.dp_mode = "nccl"
@@ -830,7 +835,7 @@ def main():
         kernel_name = ("adamw_gather_nvls_kernel (in-switch gradient sum + AdamW + multicast bf16 rows)"
                        if args.dp_mode.startswith("nvls") else
                        "adamw_gather_kernel (peer gradient rows + AdamW + bf16 rows to peers)")
-        adamw_bytes = (24 + 4 + 2) * owned
+        adamw_bytes = (24 + (2 if args.dp_mode.endswith("-bf16") else 4) + 2) * owned
         traffic = None
     elif step_mode == "background":
         # the same 30 B/parameter as the plain sweep (p, g, m, v read; p, m, v + bf16 copy written),
@@ -865,7 +870,8 @@ def main():
                      "alone_ms_per_sweep": adamw_iso_ms,
                      "alone_frac": (adamw_bytes / (adamw_iso_ms / 1e3) / 1e9 / peaks["hbm"]) if adamw_iso_ms else None,
                      "tensor_flop_per_launch": (2 * B * K_FEAT * P_PIX // launches_per_step) if fused else 0,
-                     "nvlink_egress_bytes_per_step": (4 * (N_PARAMS_W // world) * (world - 1)) if world > 1 else 0,
+                     "nvlink_egress_bytes_per_step": ((2 if args.dp_mode.endswith("-bf16") else 4)
+                                                      * (N_PARAMS_W // world) * (world - 1)) if world > 1 else 0,
                      "peak_source": peaks["source"]},
         "gemm": {"tflops_incl_frontend_and_epilogues": gemm_tf,
                  "frac_of_bf16_sustained_peak": gemm_tf / peaks["tf_sustained"],

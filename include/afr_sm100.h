@@ -236,6 +236,23 @@ int afr_adamw_rows_bg(afr_ctx* ctx, double lr, double beta1, double beta2, doubl
  * with_bias != 0 also writes fc_output.bias.grad[row_begin:row_end] (bound gradients). */
 int afr_train_wgrad_to(afr_ctx* ctx, int row_begin, int row_end, float* grad_rows, int with_bias,
                        void* stream);
+/* afr_train_wgrad_to with a bf16 destination: the data-parallel gradient that crosses NVLink, at
+ * half the bytes of the fp32 form (the sum over ranks is still taken in fp32, below). */
+int afr_train_wgrad_to_bf16(afr_ctx* ctx, int row_begin, int row_end, void* grad_rows_bf16, int with_bias,
+                            void* stream);
+/* afr_adamw_rows_gather / afr_adamw_rows_gather_nvls for bf16 gradient buffers (peer_grads[q] /
+ * grad_multicast = base of a bf16 [H*W, 64*max_length] buffer written by afr_train_wgrad_to_bf16):
+ * every rank ships half the bytes per step; the per-element sum over ranks is accumulated in fp32
+ * (registers, or inside the NVSwitch: multimem.ld_reduce .acc::f32 .bf16x2). Replaces the
+ * all-reduce of model.py:309-310's gradient in a data-parallel run. */
+int afr_adamw_rows_gather_bf16(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, int64_t step, int row_begin, int row_end,
+                               const void* const* peer_grads, void* const* peer_shadows, int world,
+                               int ctas, void* stream);
+int afr_adamw_rows_gather_nvls_bf16(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
+                                    double weight_decay, int64_t step, int row_begin, int row_end,
+                                    const void* grad_multicast, void* shadow_multicast, int ctas,
+                                    void* stream);
 int afr_adamw_small(afr_ctx* ctx, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int64_t step, void* stream);
 /* loss.backward() w.r.t. fc_output.weight / .bias (model.py:309) AND optimizer.step() of

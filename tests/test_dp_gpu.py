@@ -24,7 +24,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("mode", ["nvls-side", "peer", "peer-side", "nvls", "nccl"])
+@pytest.mark.parametrize("mode", ["nvls-side", "nvls-side-bf16", "peer-side-bf16", "peer", "peer-side", "nvls", "nccl"])
 def test_row_sharded_data_parallel_step_equals_single_gpu_step(mode, world):
     """nvls-side is the default mode bench.py / the Trainer pick on an NVSwitch box (bench.py also
     runs this comparison at its own world size before timing and prints it as `dp_parity`).
@@ -34,7 +34,7 @@ def test_row_sharded_data_parallel_step_equals_single_gpu_step(mode, world):
     rows multicast (multimem.st); nccl: reduce-scatter + all-gather."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    if world > 2 and mode not in ("nvls-side", "peer-side", "nccl"):
+    if world > 2 and mode not in ("nvls-side", "nvls-side-bf16", "peer-side", "nccl"):
         pytest.skip("inline modes are covered at 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),

@@ -38,9 +38,12 @@ def compare(rank, world, dev, mode, steps=3, per_rank=96, ctas=16):
 
     solo, solo_opt = make()
     dp, dp_opt = make()
-    if mode in ("peer", "peer-side", "nvls", "nvls-side"):
+    grad_bf16 = mode.endswith("-bf16")          # gradient rows cross NVLink as bf16 (fp32 accumulation)
+    base = mode[:-5] if grad_bf16 else mode
+    if base in ("peer", "peer-side", "nvls", "nvls-side"):
         from ai_font_renderer_b200.training import PeerLink
-        PeerLink(dp, ctas=ctas, inline=mode in ("peer", "nvls"), nvls=mode.startswith("nvls"))
+        PeerLink(dp, ctas=ctas, inline=base in ("peer", "nvls"), nvls=base.startswith("nvls"),
+                 grad_bf16=grad_bf16)
     lo, hi = shard_bounds(gB, rank, world)
     worst_loss = 0.0
     for _ in range(steps):
@@ -69,7 +72,10 @@ def compare(rank, world, dev, mode, steps=3, per_rank=96, ctas=16):
             if a.numel() < 1e6 and k != "attention.in_proj_bias"),   # key-bias slice: zero true gradient
     ], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
-    ok = bool(res[0] < 1e-5 and res[1] < 1e-4 and res[3] < 1e-5 and res[4] < 1e-3)
+    # bf16 gradient rows: each rank's contribution is rounded to 8 mantissa bits before the fp32
+    # sum, which moves Adam's normalised update by < 1 %: weights within 1e-3 of the fp32 exchange
+    tol_w, tol_rows = (2e-3, 1e-3) if grad_bf16 else (1e-4, 1e-5)
+    ok = bool(res[0] < 1e-5 and res[1] < tol_w and res[3] < tol_rows and res[4] < 1e-3)
     out = {"world": world, "mode": mode, "steps": steps, "global_batch": gB,
            "loss_rel": float(res[0]), "bf16_weights_rel": float(res[1]),
            "bf16_weights_frac_differing": float(res[2]), "owned_rows_rel": float(res[3]),
