@@ -66,6 +66,9 @@ class TrainConfig:
     # single GPU: optimizer.step() of fc_output.weight as the background sweep on a second stream
     # (FusedAdamW(background=True)); False = inside the wgrad GEMM's epilogue
     background_adamw: bool = True
+    # data parallel over NVSwitch: ship the fc_output.weight gradient rows as bf16 (half the NVLink
+    # egress; summed in fp32 inside the switch; weights within 1e-3 of the fp32 exchange)
+    dp_grad_bf16: bool = True
     quiet: bool = False
 
 
@@ -131,10 +134,14 @@ class PeerLink:
     wgrad GEMMs before and the next forward after. Construct on all ranks at the same time."""
 
     @staticmethod
-    def default_ctas(world: int) -> int:
+    def default_ctas(world: int, grad_bf16: bool = False) -> int:
         """SMs given to the gather/AdamW/broadcast kernel (measured on 2/4/8 B200, bench.py
         --comm-ctas sweeps): the owned shard -- and with it the kernel's local HBM work -- shrinks
-        with the number of ranks while its NVLink volume stays, so fewer SMs saturate it."""
+        with the number of ranks while its NVLink volume stays, so fewer SMs saturate it. With bf16
+        gradient rows the link volume halves and the kernel hides under the rest of backward on
+        half as many SMs (8 GPUs, profiles/r02: 24 CTAs 1.40 ms/step, 16: 1.29, 12: 1.27)."""
+        if grad_bf16:
+            return 32 if world <= 2 else (20 if world <= 4 else 12)
         return 48 if world <= 2 else (32 if world <= 4 else 24)
 
     def __init__(self, model, ctas: int = 0, group=None, inline: bool = False, nvls: bool = False,
@@ -153,7 +160,7 @@ class PeerLink:
         # ranks is still accumulated in fp32 (in the gather kernel's registers / inside the switch)
         self.grad_bf16 = grad_bf16
         sms_all = torch.cuda.get_device_properties(model.fc_output.weight.device).multi_processor_count
-        ctas = sms_all if inline else (ctas or self.default_ctas(self.world))
+        ctas = sms_all if inline else (ctas or self.default_ctas(self.world, grad_bf16))
         w = model.fc_output.weight
         dev = w.device
         self.ctas = ctas
@@ -504,7 +511,9 @@ class Trainer:
         nvls = bool(flag.item())
         err = None
         try:
-            PeerLink(model, nvls=nvls)
+            # NVSwitch multicast: the gradient rows cross the links as bf16 (fp32 accumulation in the
+            # switch); TrainConfig.dp_grad_bf16 = False keeps the fp32 exchange
+            PeerLink(model, nvls=nvls, grad_bf16=nvls and cfg.dp_grad_bf16)
         except Exception as exc:      # no peer access / symmetric memory on this system
             err = exc
         ok = torch.tensor([0 if err is not None else 1], device=self.device)

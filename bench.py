@@ -424,9 +424,11 @@ def run_config4(args, rank, local_rank, world):
         from ai_font_renderer_b200.training import PeerLink
         dp_mode = args.dp_mode
         if dp_mode == "auto":
-            dp_mode = "nvls-side" if PeerLink.nvls_available() else "peer-side"
+            dp_mode = "nvls-side-bf16" if PeerLink.nvls_available() else "peer-side"
         if dp_mode != "nccl":
-            PeerLink(model, ctas=args.comm_ctas or 16, inline=dp_mode in ("peer", "nvls"), nvls=dp_mode.startswith("nvls"))
+            base = dp_mode[:-5] if dp_mode.endswith("-bf16") else dp_mode
+            PeerLink(model, ctas=args.comm_ctas or 12, inline=base in ("peer", "nvls"), nvls=base.startswith("nvls"),
+                     grad_bf16=dp_mode.endswith("-bf16"))
     n_rot = 4
     g = torch.Generator().manual_seed(1234 + rank)
     n = B * n_rot
@@ -650,7 +652,9 @@ def main():
             # the NVLink egress of the gradient rows (0.43 GB per rank and step at 8 GPUs), so it hides
             # on a side stream under the rest of backward; with NVSwitch multicast (NVLS) its inbound
             # traffic and SM time shrink (2 GPUs 1.65 vs 1.82 ms, 8 GPUs 1.51 vs 1.55 ms)
-            args.dp_mode = "nvls-side" if PeerLink.nvls_available() else ("peer" if world == 2 else "peer-side")
+            # round 2: with NVLS the gradient rows cross the links as bf16 (fp32 accumulation inside the
+            # switch): 8 GPUs 1.27 vs 1.52 ms (profiles/r02)
+            args.dp_mode = "nvls-side-bf16" if PeerLink.nvls_available() else ("peer" if world == 2 else "peer-side")
         dp_base = args.dp_mode[:-5] if args.dp_mode.endswith("-bf16") else args.dp_mode
         if dp_base in ("peer", "peer-side", "nvls", "nvls-side"):
             try:
@@ -670,7 +674,8 @@ def main():
             sys.path.insert(0, os.path.join(REPO, "tools"))
             import dp_check
             ok, dp_parity = dp_check.compare(rank, world, device, args.dp_mode, steps=2, per_rank=96,
-                                             ctas=args.comm_ctas or PeerLink.default_ctas(world))
+                                             ctas=args.comm_ctas or PeerLink.default_ctas(
+                                                 world, args.dp_mode.endswith("-bf16")))
             if not ok:
                 if rank == 0:
                     emit_line({"error": "data-parallel parity check failed", "dp_parity": dp_parity})
