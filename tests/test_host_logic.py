@@ -325,3 +325,52 @@ def test_encode_uses_ord_for_any_code_point_and_render_checks_the_vocabulary():
     with pytest.raises(IndexError):
         check_token_range(small, tok)
     check_token_range(small, strings_to_tokens(["HELLO"], 6))
+
+
+def test_rank_without_samples_joins_the_side_stream_before_zeroing_and_keeps_its_dropout_step(monkeypatch):
+    """Data-parallel ragged last batch (global batch smaller than the world size): a rank whose
+    slice is empty must (a) join the previous step's gather kernel, which may still be reading its
+    peer-mapped gradient buffer, BEFORE zeroing that buffer, and (b) advance its dropout step like
+    the ranks that ran a forward. Host logic only: the model is a recording stand-in."""
+    from ai_font_renderer_b200 import training
+    calls = []
+
+    class P:
+        def __init__(self):
+            self.grad = torch.ones(3)
+
+    class FakeModel:
+        training = True
+        dropout_step = 7
+
+        def __init__(self):
+            self.params = [P(), P()]
+
+        def join_pending(self):
+            calls.append(("join", [float(p.grad.sum()) for p in self.params]))
+
+        def _ordered_params(self):
+            return self.params
+
+        def fused_forward_loss(self, *a, **k):
+            calls.append(("forward",))
+            self.dropout_step += 1
+
+    monkeypatch.setattr(training, "backward_and_step",
+                        lambda model, opt, buckets, world, has_samples=True, **k: calls.append(("step", has_samples)))
+    tr = training.Trainer.__new__(training.Trainer)
+    tr.model, tr.optimizer, tr.buckets, tr.P, tr.steps_done = FakeModel(), None, [(0, 4)], 4, 0
+    tr.device = torch.device("cpu")
+    tr.tokens = torch.zeros((8, 5), dtype=torch.int64)
+    tr.targets = torch.zeros((8, 2, 2), dtype=torch.uint8)
+    slot = torch.ones(())
+    tr.rank, tr.world = 3, 4
+    tr.train_batch(torch.arange(2), slot)                 # 2 samples, 4 ranks: rank 3 gets none
+    assert calls[0] == ("join", [3.0, 3.0])               # joined while the gradients were still intact
+    assert calls[1] == ("step", False)
+    assert all(float(p.grad.abs().sum()) == 0 for p in tr.model.params) and float(slot) == 0.0
+    assert tr.model.dropout_step == 8
+    calls.clear()
+    tr.rank = 0
+    tr.train_batch(torch.arange(2), slot)                 # rank 0 has a sample: normal path
+    assert calls == [("forward",), ("step", True)] and tr.model.dropout_step == 9
