@@ -76,6 +76,8 @@ SIGNATURES = {
     "afr_bind_adam_state": (C.c_int, [_P, C.POINTER(AfrTensors), C.POINTER(AfrTensors)]),
     "afr_sync_shadow": (C.c_int, [_P, _P]),
     "afr_bind_shadow": (C.c_int, [_P, _P, _P]),
+    "afr_bind_font_embedding": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
+    "afr_set_font_ids": (C.c_int, [_P, _P]),
     "afr_set_sm_limit": (C.c_int, [_P, C.c_int]),
     "afr_set_smem_reserve": (C.c_int, [_P, C.c_int]),
     "afr_shadow_index": (C.c_int, [_P]),

@@ -54,6 +54,11 @@ struct afr_ctx {
   bool cta2 = true;                  // forward / dgrad / wgrad GEMMs run as CTA pairs (AFR_CTA2=0: single CTAs)
   long long launches = 0;
   std::string err;
+  // ---- optional font conditioning (config 3): font_embedding [n_fonts, E] + its grad / Adam moments
+  float *font_p = nullptr, *font_g = nullptr, *font_m = nullptr, *font_v = nullptr;
+  int n_fonts = 0;
+  const int* font_ids = nullptr;        // for the next forward call
+  const int* font_ids_live = nullptr;   // of the training forward whose backward is pending
   // ---- wide front-end (embed_dim / heads / fc1 width other than 32 / 4 / 64): afr_wide.cu + GEMMs
   bool wide = false;
   int E = kE, H = kHeads, F = kF;
@@ -182,12 +187,20 @@ int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long st
 
 int run_frontend(afr_ctx* c, const long long* tokens, long long stride, int B, int S,
                  const Dropout& drop, bool save_state, cudaStream_t st, float* feats_f32 = nullptr) {
-  if (c->wide) return run_frontend_wide(c, tokens, stride, B, S, drop, save_state, st, feats_f32);
+  if (c->wide) {
+    if (c->font_ids != nullptr)
+      return fail(c, AFR_ERR_INVALID, "font conditioning is built for the reference widths only");
+    return run_frontend_wide(c, tokens, stride, B, S, drop, save_state, st, feats_f32);
+  }
   float* state = save_state ? c->fstate : nullptr;
+  FontCond font{c->font_p, c->font_ids, c->n_fonts};
+  if (c->font_ids != nullptr && c->font_p == nullptr)
+    return fail(c, AFR_ERR_STATE, "font ids set but no font_embedding bound (afr_bind_font_embedding)");
   AFR_CUDA(c, launch_frontend_forward(c->params, tokens, stride, B, S, c->cfg.max_length,
                                       c->cfg.vocab, drop, c->feats, state, c->sms, st, feats_f32,
-                                      save_state && c->smem_reserve > 0),
+                                      save_state && c->smem_reserve > 0, &font),
            "frontend_forward");
+  if (save_state) c->font_ids_live = c->font_ids;
   c->launches += 1;
   c->state_valid = state != nullptr;
   return AFR_OK;
@@ -529,6 +542,31 @@ int afr_bind_shadow(afr_ctx* c, void* copy0, void* copy1) {
   return AFR_OK;
 }
 
+int afr_bind_font_embedding(afr_ctx* c, int n_fonts, float* table, float* grad, float* exp_avg,
+                            float* exp_avg_sq) {
+  if (!c) return AFR_ERR_INVALID;
+  if (n_fonts == 0 && table == nullptr) {     // unbind
+    c->font_p = c->font_g = c->font_m = c->font_v = nullptr;
+    c->n_fonts = 0; c->font_ids = c->font_ids_live = nullptr;
+    return AFR_OK;
+  }
+  if (c->wide) return fail(c, AFR_ERR_INVALID, "font conditioning is built for the reference widths only");
+  if (n_fonts < 1 || n_fonts > kMaxFonts || table == nullptr)
+    return fail(c, AFR_ERR_INVALID, "afr_bind_font_embedding: 1..16 fonts and a non-null table");
+  if ((exp_avg == nullptr) != (exp_avg_sq == nullptr) || (exp_avg != nullptr && grad == nullptr))
+    return fail(c, AFR_ERR_INVALID, "afr_bind_font_embedding: Adam moments come in pairs and need a gradient");
+  c->font_p = table; c->font_g = grad; c->font_m = exp_avg; c->font_v = exp_avg_sq; c->n_fonts = n_fonts;
+  return AFR_OK;
+}
+
+int afr_set_font_ids(afr_ctx* c, const int32_t* font_ids) {
+  if (!c) return AFR_ERR_INVALID;
+  if (font_ids != nullptr && c->font_p == nullptr)
+    return fail(c, AFR_ERR_STATE, "afr_set_font_ids before afr_bind_font_embedding");
+  c->font_ids = font_ids;
+  return AFR_OK;
+}
+
 int afr_set_sm_limit(afr_ctx* c, int sms) {
   if (!c) return AFR_ERR_INVALID;
   if (sms < 1 || sms > c->num_sms) sms = c->num_sms;
@@ -715,12 +753,14 @@ int afr_train_frontend_backward(afr_ctx* c, void* stream) {
   if (c->wide)
     return run_frontend_backward_wide(c, c->tokens, c->token_stride, c->B, c->S, c->drop, c->dfeat, st);
   int grid = 0;
+  FontCond font{c->font_p, c->font_ids_live, c->n_fonts};
   AFR_CUDA(c, launch_frontend_backward(c->params, c->tokens, c->token_stride, c->B, c->S,
                                        c->cfg.max_length, c->cfg.vocab, c->drop, c->dfeat,
                                        c->fstate, c->partials, c->sms, &grid, c->sms, st,
-                                       c->smem_reserve > 0),
+                                       c->smem_reserve > 0, &font),
            "frontend_backward");
-  AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
+  AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st,
+                                       c->font_ids_live ? c->font_g : nullptr, c->n_fonts),
            "small_grad_reduce");
   c->launches += 2;
   return AFR_OK;
@@ -1092,10 +1132,13 @@ int afr_adamw_small(afr_ctx* c, double lr, double beta1, double beta2, double ep
   float* const* gg = reinterpret_cast<float* const*>(&c->grads);
   float* const* mm = reinterpret_cast<float* const*>(&c->m);
   float* const* vv = reinterpret_cast<float* const*>(&c->v);
-  SmallAdamJob jobs[11];
+  SmallAdamJob jobs[12];
   for (int i = 0; i < 10; ++i) jobs[i] = SmallAdamJob{pp[i], gg[i], mm[i], vv[i], sizes[i]};
   jobs[10] = SmallAdamJob{c->params.bout, c->grads.bout, c->m.bout, c->v.bout, c->P};
-  AFR_CUDA(c, launch_adamw_small(jobs, 11, h, static_cast<cudaStream_t>(stream)), "adamw(small)");
+  int njobs = 11;
+  if (c->font_p != nullptr && c->font_m != nullptr)
+    jobs[njobs++] = SmallAdamJob{c->font_p, c->font_g, c->font_m, c->font_v, c->n_fonts * E};
+  AFR_CUDA(c, launch_adamw_small(jobs, njobs, h, static_cast<cudaStream_t>(stream)), "adamw(small)");
   c->launches += 1;
   return AFR_OK;
 }
@@ -1204,12 +1247,14 @@ int afr_debug_frontend_backward(afr_ctx* c, const int64_t* tokens, int64_t token
     return run_frontend_backward_wide(c, reinterpret_cast<const long long*>(tokens), token_stride, B, S,
                                       to_dropout(dropout), dfeat, st);
   int grid = 0;
+  FontCond font{c->font_p, c->font_ids_live, c->n_fonts};
   AFR_CUDA(c, launch_frontend_backward(c->params, reinterpret_cast<const long long*>(tokens),
                                        token_stride, B, S, c->cfg.max_length, c->cfg.vocab,
                                        to_dropout(dropout), dfeat, c->fstate, c->partials,
-                                       c->sms, &grid, c->sms, st),
+                                       c->sms, &grid, c->sms, st, false, &font),
            "frontend_backward(debug)");
-  AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st),
+  AFR_CUDA(c, launch_small_grad_reduce(c->partials, grid, c->lay, c->grads, st,
+                                       c->font_ids_live ? c->font_g : nullptr, c->n_fonts),
            "small_grad_reduce(debug)");
   c->launches += 2;
   return AFR_OK;

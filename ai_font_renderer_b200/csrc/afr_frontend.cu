@@ -82,6 +82,7 @@ struct FrontArgs {
   float* partials;                // backward: [grid, lay.total]
   SmallLayout lay;
   int* err_flag;
+  FontCond font;                  // optional font conditioning (ids == nullptr: none)
 };
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -224,8 +225,14 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
             keep8 |= ((mk.y >> (8 * u)) & 0xFFu) ? (16u << u) : 0u;
           }
         }
-        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
         const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        if (a.font.ids != nullptr) {   // config 3: + font_embedding[font of this sample], before the dropout
+          const float* fr = a.font.table + static_cast<long long>(a.font.ids[b]) * kE + c0;
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(fr)), f1 = __ldg(reinterpret_cast<const float4*>(fr + 4));
+          ev[0] += f0.x; ev[1] += f0.y; ev[2] += f0.z; ev[3] += f0.w;
+          ev[4] += f1.x; ev[5] += f1.y; ev[6] += f1.z; ev[7] += f1.w;
+        }
         float ov[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -473,7 +480,7 @@ __global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a
 // =========================================================================== backward kernel
 struct BwdSmem {
   int w1, wo, win, lnw;
-  int xhat, df, dr, ctx, q, k, v, e, dctx, stat, abits, fbits, ebits, rstd, tok, hist, red, bars;
+  int xhat, df, dr, ctx, q, k, v, e, dctx, stat, abits, fbits, ebits, rstd, tok, hist, fonth, red, bars;
   int total;
 };
 __host__ __device__ inline BwdSmem make_bwd_smem(int L, int vocab) {
@@ -501,6 +508,7 @@ __host__ __device__ inline BwdSmem make_bwd_smem(int L, int vocab) {
   s.rstd = o; o += L4;
   s.tok = o;  o += L4;
   s.hist = o; o += vocab <= kEmbSmemMaxVocab ? vocab * kE : 0;
+  s.fonth = o; o += kMaxFonts * kE;   // d(font_embedding) of this CTA's samples
   s.red = o;  o += kWarps * kE * 2;
   o = (o + 3) & ~3;
   s.bars = o; o += 8;                // 4 mbarriers
@@ -526,6 +534,7 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
   } else {
     for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = 0.f;
   }
+  for (int i = tid; i < kMaxFonts * kE; i += kThreads) sm[o.fonth + i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
@@ -890,6 +899,7 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
       // embedding scatter-add. Rows hit by several positions are summed in position order:
       // deterministic, no atomics. Operands are fetched four positions ahead of the dependent
       // read-modify-write chain on the table.
+      float fsum = 0.f;    // d(font_embedding row of this sample)[lane] = sum over positions
       if (hist_smem) {
         float* hist = sm + o.hist + lane;
         int s = 0;
@@ -901,14 +911,22 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
           hist[t1 * kE] += v1;
           hist[t2 * kE] += v2;
           hist[t3 * kE] += v3;
+          fsum += (v0 + v1) + (v2 + v3);
         }
-        for (; s < S; ++s) hist[s_tok[s] * kE] += s_dr[s * kE + lane];
+        for (; s < S; ++s) {
+          const float v0 = s_dr[s * kE + lane];
+          hist[s_tok[s] * kE] += v0;
+          fsum += v0;
+        }
       } else {
         for (int s = 0; s < S; ++s) {
           float* pe = part + a.lay.off_emb + static_cast<long long>(s_tok[s]) * kE + lane;
-          __stcg(pe, __ldcg(pe) + s_dr[s * kE + lane]);
+          const float v0 = s_dr[s * kE + lane];
+          __stcg(pe, __ldcg(pe) + v0);
+          fsum += v0;
         }
       }
+      if (a.font.ids != nullptr) sm[o.fonth + a.font.ids[b] * kE + lane] += fsum;   // one writer per (font, lane)
     }
     AFR_TICK(14);
   }
@@ -956,6 +974,7 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
   }
   if (hist_smem)
     for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = sm[o.hist + i];
+  for (int i = tid; i < kMaxFonts * kE; i += kThreads) part[a.lay.off_font + i] = sm[o.fonth + i];
 }
 
 __global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const FrontArgs a) {
@@ -975,6 +994,8 @@ struct ReduceArgs {
   int grid, total;
   SmallLayout lay;
   Tensors g;
+  float* font_grad;   // [n_fonts, kE] or nullptr
+  int n_fonts;
 };
 __global__ void __launch_bounds__(256) small_grad_reduce_kernel(ReduceArgs r) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1000,7 +1021,11 @@ __global__ void __launch_bounds__(256) small_grad_reduce_kernel(ReduceArgs r) {
   else if (i < L.off_lnb) dst = r.g.lnw + (i - L.off_lnw);
   else if (i < L.off_w1) dst = r.g.lnb + (i - L.off_lnb);
   else if (i < L.off_b1) dst = r.g.w1 + (i - L.off_w1);
-  else dst = r.g.b1 + (i - L.off_b1);
+  else if (i < L.off_font) dst = r.g.b1 + (i - L.off_b1);
+  else {
+    if (r.font_grad == nullptr || i - L.off_font >= r.n_fonts * kE) return;
+    dst = r.font_grad + (i - L.off_font);
+  }
   *dst = s;
 }
 
@@ -1048,7 +1073,7 @@ size_t frontend_backward_smem_bytes(int L, int vocab) {
 cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, long long token_stride,
                                     int B, int S, int L, int vocab, const Dropout& drop,
                                     __nv_bfloat16* feats, float* state, int num_sms,
-                                    cudaStream_t stream, float* feats_f32, bool shared_sm) {
+                                    cudaStream_t stream, float* feats_f32, bool shared_sm, const FontCond* font) {
   if (S < 1 || S > L || L > kMaxL) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
@@ -1056,6 +1081,7 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
   a.w = w; a.tokens = tokens; a.token_stride = token_stride;
   a.B = B; a.S = S; a.L = L; a.vocab = vocab; a.drop = drop; a.feats = feats;
   a.feats_f32 = feats_f32;
+  if (font != nullptr) a.font = *font;
   a.state = state; a.sl.init(L);
   a.err_flag = g_err_flag;
   fill_dropout(a);
@@ -1081,7 +1107,7 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
                                      int B, int S, int L, int vocab, const Dropout& drop,
                                      const float* dfeat, const float* state, float* partials,
                                      int max_grid, int* grid_out, int num_sms, cudaStream_t stream,
-                                     bool shared_sm) {
+                                     bool shared_sm, const FontCond* font) {
   if (S < 1 || S > L || L > kMaxL || state == nullptr) return cudaErrorInvalidValue;
   cudaError_t e = ensure_err_flag();
   if (e != cudaSuccess) return e;
@@ -1089,6 +1115,7 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
   a.w = w; a.tokens = tokens; a.token_stride = token_stride;
   a.B = B; a.S = S; a.L = L; a.vocab = vocab; a.drop = drop;
   a.dfeat = dfeat; a.partials = partials; a.lay.init(L, vocab);
+  if (font != nullptr) a.font = *font;
   a.state = const_cast<float*>(state); a.sl.init(L);
   a.err_flag = g_err_flag;
   fill_dropout(a);
@@ -1113,8 +1140,8 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
 }
 
 cudaError_t launch_small_grad_reduce(const float* partials, int grid, const SmallLayout& lay,
-                                     const Tensors& grads, cudaStream_t stream) {
-  ReduceArgs r{partials, grid, lay.total, lay, grads};
+                                     const Tensors& grads, cudaStream_t stream, float* font_grad, int n_fonts) {
+  ReduceArgs r{partials, grid, lay.total, lay, grads, font_grad, n_fonts};
   small_grad_reduce_kernel<<<(lay.total + 255) / 256, 256, 0, stream>>>(r);
   return cudaGetLastError();
 }

@@ -39,12 +39,12 @@ class FusedAdamW(torch.optim.Optimizer):
         # fuse_wgrad.
         self.background = background
         self.bg_chunks, self.bg_ctas, self.bg_stages = bg_chunks, bg_ctas, bg_stages
-        super().__init__(model._ordered_params(), dict(lr=lr, betas=betas, eps=eps,
-                                                       weight_decay=weight_decay))
+        super().__init__(model._all_params(), dict(lr=lr, betas=betas, eps=eps,
+                                                   weight_decay=weight_decay))
 
     def _ensure_state(self):
         params = self.model._ordered_params()
-        for p in params:
+        for p in self.model._all_params():
             st = self.state[p]
             if len(st) == 0:
                 st["step"] = torch.tensor(0.0)
@@ -59,6 +59,10 @@ class FusedAdamW(torch.optim.Optimizer):
         ctx.bind_grads(model._param_grads())
         ctx.bind_adam_state([self.state[p]["exp_avg"] for p in params],
                             [self.state[p]["exp_avg_sq"] for p in params])
+        if model.n_fonts > 0:       # thirteenth tensor: font_embedding.weight (config 3)
+            fw = model.font_embedding.weight
+            model._font_state = (self.state[fw]["exp_avg"], self.state[fw]["exp_avg_sq"])
+            model._bind_fonts(ctx, model._font_ids.numel() if model._font_ids is not None else 0)
         return ctx, params
 
     def _hyper(self):
@@ -70,7 +74,7 @@ class FusedAdamW(torch.optim.Optimizer):
         return int(self.state[params[0]]["step"].item()) + 1
 
     def _advance(self, params):
-        for p in params:
+        for p in self.model._all_params():
             self.state[p]["step"] += 1
 
     @torch.no_grad()
@@ -167,6 +171,6 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = False):
         """The fused backward overwrites every gradient, so the trainer never needs this; it is
         kept with in-place semantics (the gradient buffers stay bound to the library)."""
-        for p in self.model._ordered_params():
+        for p in self.model._all_params():
             if p.grad is not None:
                 p.grad.zero_()

@@ -151,6 +151,24 @@ def render_strings(model, strings, output_dir, sheet_height, sheet_width, device
     reference it does not switch the model to eval(): callers do (model.py:314, helpers.py:103)."""
     os.makedirs(output_dir, exist_ok=True)
     strings = list(strings)
+    table_fonts = font_ids is not None and getattr(model, "n_fonts", 0) > 0   # font_embedding table model
+    if table_fonts:
+        # multi-font model with a font_embedding table: ordinary tokens, the font goes in beside them
+        for i, s in enumerate(strings):
+            if len(s) > model.max_length:
+                strings[i] = s[:model.max_length]
+                print(f"Warning: String truncated to {model.max_length} characters: {strings[i]}")
+        if strings:
+            tokens = strings_to_tokens(strings, model.max_length)
+            check_token_range(model, tokens)
+            fonts = torch.as_tensor(list(font_ids), dtype=torch.int32)
+            with torch.no_grad():
+                for lo in range(0, len(strings), batch_size):
+                    hi = min(len(strings), lo + batch_size)
+                    sheets = model.render_u8(tokens[lo:hi].to(device), font_ids=fonts[lo:hi])
+                    write_bmp_files(sheets.cpu().numpy(), output_dir, first_index=lo)
+        print(f"Saved {len(strings)} rendered strings to {output_dir}/")
+        return
     limit = model.max_length - (1 if font_ids is not None else 0)
     for i, s in enumerate(strings):
         if len(s) > limit:

@@ -153,12 +153,16 @@ class AttentionFontRenderer(nn.Module):
 
     def __init__(self, max_length: int = MAX_CHARS_PER_SHEET, sheet_height: int = SHEET_HEIGHT,
                  sheet_width: int = SHEET_WIDTH, vocab: int = VOCAB, embedding_dim: int = EMBEDDING_DIM,
-                 num_heads: int = NUM_ATTENTION_HEADS, fc1_width: int = FC1_WIDTH):
+                 num_heads: int = NUM_ATTENTION_HEADS, fc1_width: int = FC1_WIDTH, n_fonts: int = 0):
         """The reference's constructor takes max_length only (model.py:130); its other sizes are
         module constants (model.py:64-66,79-81,148). They are arguments here so that the scaled
         workloads of BASELINE.json can be built: sheet size, vocabulary (config 5), and the
         width of the net -- embedding_dim / num_heads / fc1_width other than 32 / 4 / 64 select
-        the GEMM-based front-end (csrc/afr_wide.cu; config 4: 128 / 8 / 128)."""
+        the GEMM-based front-end (csrc/afr_wide.cu; config 4: 128 / 8 / 128). n_fonts > 0 adds
+        multi-font conditioning (config 3): a thirteenth parameter `font_embedding.weight`
+        [n_fonts, embedding_dim] whose row is added to every token embedding of a sample before
+        the embedding dropout; it is constructed LAST, so the first twelve tensors keep the
+        reference's initial values under the same seed."""
         super().__init__()
         self.max_length = max_length
         self.sheet_height = sheet_height
@@ -177,6 +181,10 @@ class AttentionFontRenderer(nn.Module):
         self.fc1 = nn.Linear(self.embedding_dim, fc1_width)
         self.dropout1 = nn.Dropout(DROPOUT_RATE + 0.05)
         self.fc_output = nn.Linear(fc1_width * max_length, sheet_height * sheet_width)
+        self.n_fonts = n_fonts
+        if n_fonts > 0:
+            self.font_embedding = nn.Embedding(n_fonts, self.embedding_dim)
+        self._font_ids: Optional[torch.Tensor] = None
         # dropout generator of the fused kernels: keyed by torch's seed, advanced every train step
         self.dropout_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self.dropout_step = 0
@@ -198,6 +206,43 @@ class AttentionFontRenderer(nn.Module):
     def _ordered_params(self):
         sd = dict(self.named_parameters())
         return [sd[k] for k in _lib.STATE_DICT_KEYS]
+
+    def _all_params(self):
+        """The reference's 12 tensors, then font_embedding.weight if the model has one."""
+        ps = self._ordered_params()
+        if self.n_fonts > 0:
+            ps.append(self.font_embedding.weight)
+        return ps
+
+    def set_fonts(self, font_ids: Optional[torch.Tensor]):
+        """Font of every sample of the NEXT forward call (int tensor [B]); None = no conditioning."""
+        if font_ids is None:
+            self._font_ids = None
+        else:
+            if self.n_fonts <= 0:
+                raise ValueError("this model has no font_embedding (construct it with n_fonts > 0)")
+            dev = self.fc_output.weight.device
+            self._font_ids = font_ids.to(device=dev, dtype=torch.int32).contiguous()
+
+    def _bind_fonts(self, c: "_Context", batch: int):
+        """(Re)bind the font table / its gradient and Adam state when they exist, and hand the
+        library the font ids of the coming forward."""
+        if self.n_fonts <= 0:
+            return
+        w = self.font_embedding.weight
+        st = getattr(self, "_font_state", None)
+        has_grad = w.grad is not None
+        ptrs = (w.data_ptr(), w.grad.data_ptr() if has_grad else 0,
+                st[0].data_ptr() if (st and has_grad) else 0, st[1].data_ptr() if (st and has_grad) else 0)
+        if getattr(c, "font_bound", None) != ptrs:
+            c.check(c.lib.afr_bind_font_embedding(c.handle, self.n_fonts, ptrs[0], ptrs[1] or None,
+                                                  ptrs[2] or None, ptrs[3] or None))
+            c.font_bound = ptrs
+        ids = self._font_ids
+        if ids is not None and ids.numel() != batch:
+            raise ValueError(f"font ids for {ids.numel()} samples, batch of {batch}")
+        c.check(c.lib.afr_set_font_ids(c.handle, ids.data_ptr() if ids is not None else None))
+        c.keepalive["font_ids"] = ids
 
     def _context(self, batch: int, training: bool) -> _Context:
         params = self._ordered_params()
@@ -290,8 +335,10 @@ class AttentionFontRenderer(nn.Module):
         ones plus fc_output.bias are views into one flat buffer (`small_grad_flat`) so a
         data-parallel run reduces them with a single collective."""
         params = self._ordered_params()
-        if any(p.grad is None for p in params):
+        if any(p.grad is None for p in self._all_params()):
             small = [p for k, p in zip(_lib.STATE_DICT_KEYS, params) if k != "fc_output.weight"]
+            if self.n_fonts > 0:
+                small.append(self.font_embedding.weight)
             flat = torch.zeros(sum(p.numel() for p in small), dtype=torch.float32, device=params[0].device)
             off = 0
             for p in small:
@@ -357,6 +404,7 @@ class AttentionFontRenderer(nn.Module):
         x = self._check_tokens(x)
         B, S = x.shape[0], min(x.shape[1], self.max_length)
         c = self._context(B, training=False)
+        self._bind_fonts(c, B)
         if out is not None:
             want = torch.uint8 if kind == _lib.OUT_SHEET_U8 else torch.float32
             if (out.dtype != want or not out.is_contiguous() or out.device != x.device
@@ -392,25 +440,33 @@ class AttentionFontRenderer(nn.Module):
         return self._eval_forward(x, _lib.OUT_SHEET_F32)
 
     @torch.no_grad()
-    def render_u8(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def render_u8(self, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  font_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Eval forward + helpers.py:33 quantisation fused in the GEMM epilogue -> uint8 [B,H,W]
         (written into `out` if given: render.RenderPipeline reuses two device buffers)."""
+        if font_ids is not None or self.n_fonts > 0:
+            self.set_fonts(font_ids)
         return self._eval_forward(x, _lib.OUT_SHEET_U8, out=out)
 
     @torch.no_grad()
-    def logits(self, x: torch.Tensor) -> torch.Tensor:
+    def logits(self, x: torch.Tensor, font_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """fc_output before the clamp (model.py:196), eval mode -> fp32 [B, H*W]."""
+        if font_ids is not None or self.n_fonts > 0:
+            self.set_fonts(font_ids)
         return self._eval_forward(x, _lib.OUT_LOGITS_F32)
 
     # ------------------------------------------------------------------ fused training step
     def fused_forward_loss(self, tokens: torch.Tensor, targets: torch.Tensor,
                            loss_count: Optional[float] = None,
                            masks: Optional[Dict[str, torch.Tensor]] = None, dropout: bool = True,
-                           sample_offset: int = 0, loss_out: Optional[torch.Tensor] = None, marks=None):
+                           sample_offset: int = 0, loss_out: Optional[torch.Tensor] = None, marks=None,
+                           font_ids: Optional[torch.Tensor] = None):
         """model.py:299 + 304-306 in one pass; leaves d(loss)/d(logits) inside the library.
         targets: uint8 [B,H,W] (k/255 grey levels) or fp32 [B,H,W]. Returns the device loss scalar
         (sum of squared errors / loss_count; loss_count defaults to B*H*W = mse_loss's mean)."""
         tokens = self._check_tokens(tokens)
+        if font_ids is not None or self.n_fonts > 0:
+            self.set_fonts(font_ids)
         B, S = tokens.shape[0], min(tokens.shape[1], self.max_length)
         if targets.shape[0] != B or targets.numel() != B * self.sheet_height * self.sheet_width:
             raise ValueError("targets must be [B, H, W]")
@@ -424,6 +480,7 @@ class AttentionFontRenderer(nn.Module):
             targets = targets.to(tokens.device).contiguous()
         c = self._context(B, training=True)
         c.bind_grads(self._param_grads())
+        self._bind_fonts(c, B)
         drop = self.make_dropout(B, S, masks=masks, sample_offset=sample_offset,
                                  enabled=dropout and self.training)
         if loss_out is None:

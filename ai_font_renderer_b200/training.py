@@ -53,6 +53,8 @@ class TrainConfig:
     betas: Tuple[float, float] = (0.9, 0.99)
     test_strings: Sequence[str] = field(default_factory=list)
     test_font_ids: Optional[Sequence[int]] = None   # multi-font models: font of every test string
+    # models with a font_embedding table (AttentionFontRenderer(n_fonts=N)): font of every SAMPLE
+    sample_font_ids: Optional[torch.Tensor] = None
     render_every: int = 5
     grad_buckets: int = 8            # row buckets of fc_output.weight.grad (data parallel overlap)
     adam_buckets: int = 1            # single GPU: row buckets of the wgrad GEMM / AdamW sweep
@@ -466,6 +468,9 @@ class Trainer:
         u8 = targets_as_u8(targets)
         self.targets = (u8 if u8 is not None else targets.float()).to(device).contiguous()
         self.tokens = tokens.long().to(device).contiguous()
+        self.fonts = None
+        if cfg.sample_font_ids is not None:
+            self.fonts = torch.as_tensor(cfg.sample_font_ids, dtype=torch.int32).to(device).contiguous()
         n = tokens.shape[0]
         # model.py:232-242
         val_size = int(cfg.validation_split * n)
@@ -560,8 +565,10 @@ class Trainer:
         x = self.tokens.index_select(0, local)
         t = self.targets.index_select(0, local)
         count = float(gB) * self.P
+        fonts = self.fonts.index_select(0, local) if self.fonts is not None else None
         if hi > lo:
-            model.fused_forward_loss(x, t, loss_count=count, sample_offset=lo, loss_out=loss_slot)
+            model.fused_forward_loss(x, t, loss_count=count, sample_offset=lo, loss_out=loss_slot,
+                                     font_ids=fonts)
         else:   # this rank has no sample of a ragged last batch: contribute zeros
             # the previous step's gather kernel (side stream) may still be reading this rank's
             # peer-mapped dW buffer: join it BEFORE the buffer is zeroed on the compute stream
@@ -588,8 +595,9 @@ class Trainer:
         x = self.tokens.index_select(0, local)
         t = self.targets.index_select(0, local)
         # eval forward + MSE in the fused GEMM epilogue (model.eval() => dropout off)
+        fonts = self.fonts.index_select(0, local) if self.fonts is not None else None
         model.fused_forward_loss(x, t, loss_count=float(gB) * self.P, dropout=False,
-                                 loss_out=loss_slot)
+                                 loss_out=loss_slot, font_ids=fonts)
 
     def _epoch_losses(self, slots: torch.Tensor, n: int) -> float:
         """Sum of the per-batch mean losses, added on the host in batch order in double precision

@@ -123,6 +123,18 @@ int afr_sync_shadow(afr_ctx* ctx, void* stream);
  * written copy by itself; a sharded sweep (own rows only) is completed by the caller's
  * all-gather and then activated with afr_shadow_commit. */
 int afr_bind_shadow(afr_ctx* ctx, void* copy0, void* copy1);
+/* Multi-font conditioning (BASELINE.json configs[2]; an EXTENSION: the reference has one font,
+ * generate_font.ts:65-67 ships Montserrat unused): a thirteenth parameter font_embedding
+ * [n_fonts <= 16, embed_dim] whose row font_ids[b] is added to every token embedding of sample b
+ * before the embedding dropout (model.py:167-168 with `+ font_embedding(font)` in between).
+ * afr_bind_font_embedding binds the table and, for training, its gradient (overwritten by
+ * afr_train_frontend_backward) and, with the gradient, its two Adam moments (afr_adamw_small then
+ * steps the table); (0, NULL, ...) unbinds. afr_set_font_ids names the device array int32 [B] that the
+ * NEXT forward call (eval or training; the training backward reuses it) reads; NULL = no
+ * conditioning. Reference widths only. */
+int afr_bind_font_embedding(afr_ctx* ctx, int n_fonts, float* table, float* grad, float* exp_avg,
+                            float* exp_avg_sq);
+int afr_set_font_ids(afr_ctx* ctx, const int32_t* font_ids);
 /* The GEMMs and the front-end kernels are persistent (one CTA per SM, static tile order): a CTA
  * that cannot become resident because a collective's CTAs hold its SM delays the whole kernel.
  * A data-parallel caller therefore leaves the collective its SMs: the persistent kernels launch

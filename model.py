@@ -14,7 +14,8 @@ command line. Differences a user can see:
     (train on synthetic sheets when train_input/ is absent; real bitmaps need bun + node-canvas;
     `python -m ai_font_renderer_b200.fontgen` writes a FreeType-rasterised stand-in), --fonts N
     (multi-font conditioning, BASELINE config 3: train_input/fonts.txt names the font of every
-    sample, the font is a control token in position 0, vocabulary 128 + N, 101 positions).
+    sample, the font is a control token in position 0, vocabulary 128 + N, 101 positions; with
+    --font-table it is a font_embedding [N, 32] table added to the token embeddings instead).
 Launched under torchrun it trains data-parallel (one process per GPU, NCCL).
 """
 import datetime
@@ -146,9 +147,17 @@ def train_string_renderer(argv=()):
                 raise SystemExit(f"train_input/fonts.txt names {found} fonts, --fonts {n_fonts} given")
             dataset = (tokens, targets)
         over_fonts = {"test_font_ids": [i % n_fonts for i in range(len(test_strings))]}
+        if "--font-table" in argv:
+            # SURVEY 8d's form of the conditioning: ordinary tokens + a font_embedding [N, 32] table
+            # (thirteenth checkpoint tensor) instead of the control token in position 0
+            tokens_ct, sheets_ct = dataset
+            over_fonts["sample_font_ids"] = (tokens_ct[:, 0] - 128).to(torch.int32)
+            dataset = (tokens_ct[:, 1:].contiguous(), sheets_ct)
     print("Training attention-based sheet renderer with reduced embedding dimensions (32) and "
           "learned positional encoding...")
-    if n_fonts > 0:
+    if n_fonts > 0 and "--font-table" in argv:
+        model = AttentionFontRenderer(max_length=dataset[0].shape[1], n_fonts=n_fonts).to(device)
+    elif n_fonts > 0:
         model = AttentionFontRenderer(max_length=dataset[0].shape[1], vocab=128 + n_fonts).to(device)
     else:
         model = AttentionFontRenderer(max_length=MAX_CHARS_PER_SHEET).to(device)

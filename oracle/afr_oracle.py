@@ -109,14 +109,18 @@ def _dropout(x: torch.Tensor, keep: Optional[torch.Tensor], p: float) -> torch.T
     return x * noise
 
 
-def features(state, tokens: torch.Tensor, cfg: OracleConfig, masks=None) -> torch.Tensor:
-    """model.py:160-193 -> [B, max_length*hidden] (the A operand of fc_output)."""
+def features(state, tokens: torch.Tensor, cfg: OracleConfig, masks=None, font_ids=None) -> torch.Tensor:
+    """model.py:160-193 -> [B, max_length*hidden] (the A operand of fc_output).
+    font_ids (config 3, an extension of the reference): int [B]; state["font_embedding.weight"][font]
+    is added to every token embedding of the sample before the embedding dropout."""
     L, E, H, Fh = cfg.max_length, cfg.embed_dim, cfg.num_heads, cfg.hidden
     dh = E // H
     x = tokens[:, : min(tokens.shape[1], L)]                      # model.py:163-164
     B, S = x.shape
     m = masks or {}
     e = state["embedding.weight"][x]                              # model.py:167
+    if font_ids is not None:
+        e = e + state["font_embedding.weight"][font_ids.long()].unsqueeze(1)
     e = _dropout(e, m.get("embed"), cfg.p_embed)                  # model.py:168 (before positions)
     e = e + state["positional_encoding"][:S].unsqueeze(0)         # model.py:171-172
     # nn.MultiheadAttention -> F.multi_head_attention_forward (need_weights branch)
@@ -139,15 +143,15 @@ def features(state, tokens: torch.Tensor, cfg: OracleConfig, masks=None) -> torc
     return feats
 
 
-def logits(state, tokens, cfg: OracleConfig, masks=None) -> torch.Tensor:
+def logits(state, tokens, cfg: OracleConfig, masks=None, font_ids=None) -> torch.Tensor:
     """fc_output before the clamp (model.py:196) -> [B, H*W]."""
-    return F.linear(features(state, tokens, cfg, masks), state["fc_output.weight"],
+    return F.linear(features(state, tokens, cfg, masks, font_ids), state["fc_output.weight"],
                     state["fc_output.bias"])
 
 
-def forward(state, tokens, cfg: OracleConfig, masks=None) -> torch.Tensor:
+def forward(state, tokens, cfg: OracleConfig, masks=None, font_ids=None) -> torch.Tensor:
     """AttentionFontRenderer.forward (model.py:158-204) -> [B, H, W] in [0,1]."""
-    z = logits(state, tokens, cfg, masks)
+    z = logits(state, tokens, cfg, masks, font_ids)
     return torch.clamp(z, 0.0, 1.0).view(-1, cfg.sheet_h, cfg.sheet_w)        # model.py:199-202
 
 
@@ -190,20 +194,20 @@ class _Bf16OutputLayerLoss(torch.autograd.Function):
 
 
 def loss_and_grads(state, tokens, targets_f32, cfg: OracleConfig, masks=None,
-                   loss_count: Optional[float] = None, emulate_bf16: bool = False):
+                   loss_count: Optional[float] = None, emulate_bf16: bool = False, font_ids=None):
     """mse_loss(model(x), t) (model.py:270,304-306) and loss.backward() (model.py:309).
     loss_count overrides the mean's denominator (data-parallel shards pass global_B*H*W).
     emulate_bf16 rounds the three GEMMs' operands to bf16 like the kernels do.
     Returns (loss, grads dict, logits)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in state.items()}
     if emulate_bf16:
-        feats = features(params, tokens, cfg, masks)
+        feats = features(params, tokens, cfg, masks, font_ids)
         t = targets_f32.reshape(feats.shape[0], -1)
         count = float(loss_count) if loss_count is not None else float(t.numel())
         loss, z = _Bf16OutputLayerLoss.apply(feats, params["fc_output.weight"],
                                              params["fc_output.bias"], t, count)
     else:
-        z = logits(params, tokens, cfg, masks)
+        z = logits(params, tokens, cfg, masks, font_ids)
         y = torch.clamp(z, 0.0, 1.0).view(-1, cfg.sheet_h, cfg.sheet_w)
         t = targets_f32.view(y.shape)
         if loss_count is None:

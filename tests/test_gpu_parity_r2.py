@@ -266,3 +266,77 @@ def test_render_strings_of_cjk_text_on_a_bmp_vocabulary_model(tmp_path):
                        orc.init_state(orc.OracleConfig(max_length=24, sheet_h=16, sheet_w=64), seed=5)).eval()
     with pytest.raises(IndexError):
         render_strings(small, strings, str(tmp_path / "x"), 16, 64, dev())
+
+
+# ------------------------------------------------------------------------------------ config 3, font table
+def test_font_embedding_conditioning_matches_oracle(golden_small):
+    """BASELINE config 3 as SURVEY 8d specifies it (an extension: restated-oracle parity): a table
+    font_embedding [n_fonts, 32] whose row is added to the token embedding before the dropout.
+    fp32 front-end features / gradients incl. d(font_embedding) at 1e-5 / 5e-5, the full step at
+    the toy-batch tolerance, and two fonts learn different sheets for the same string."""
+    from ai_font_renderer_b200.optim import FusedAdamW
+    from ai_font_renderer_b200.renderer import AttentionFontRenderer
+    from conftest import state_from_npz
+    from test_gpu_parity import TOY_TOL, small_cfg
+    cfg = small_cfg(golden_small)
+    state = state_from_npz(golden_small, "state0")
+    g = torch.Generator().manual_seed(3)
+    state["font_embedding.weight"] = torch.randn((2, cfg.embed_dim), generator=g) * 0.5
+    model = AttentionFontRenderer(max_length=cfg.max_length, sheet_height=cfg.sheet_h, sheet_width=cfg.sheet_w,
+                                  vocab=cfg.vocab, n_fonts=2)
+    assert list(model.state_dict().keys())[:12] == list(orc.STATE_KEYS)
+    model.load_state_dict({k: v.clone() for k, v in state.items()})
+    model = model.to(dev()).train()
+    tokens = torch.from_numpy(golden_small["tokens"])
+    targets_u8 = torch.from_numpy(golden_small["targets_u8"]).clone()
+    B, S = tokens.shape
+    fonts = torch.tensor([0, 1, 0, 1, 1, 0][:B])
+    targets_u8[fonts == 1] = 255 - (255 - targets_u8[fonts == 1]) // 3        # font 1: lighter ink
+    tok = tokens.to(dev())
+    # --- fp32 front-end alone
+    params = {k: v.clone().requires_grad_(True) for k, v in state.items()}
+    feats_ref = orc.features(params, tokens, cfg, None, fonts)
+    dfeat = torch.randn(feats_ref.shape, generator=g) * 1e-3
+    feats_ref.backward(dfeat)
+    ctx = model._context(B, training=True)
+    ctx.bind_grads(model._param_grads())
+    model.set_fonts(fonts)
+    model._bind_fonts(ctx, B)
+    drop = model.make_dropout(B, S, enabled=False)
+    out = torch.empty((B, cfg.K), device=dev())
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.check(ctx.lib.afr_debug_frontend_forward(ctx.handle, tok.data_ptr(), tok.stride(0), B, S,
+                                                 C.byref(drop), out.data_ptr(), st))
+    assert rel_fro(out.cpu(), feats_ref.detach()) < FP32_TOL
+    assert rel_fro(out.cpu(), orc.features(state, tokens, cfg).detach()) > 1e-2       # the fonts matter
+    dfd = dfeat.to(dev())
+    ctx.check(ctx.lib.afr_debug_frontend_backward(ctx.handle, tok.data_ptr(), tok.stride(0), B, S,
+                                                  C.byref(drop), dfd.data_ptr(), st))
+    torch.cuda.synchronize()
+    got = grads_of(model)
+    for k in list(orc.STATE_KEYS[:10]) + ["font_embedding.weight"]:
+        a, b = got[k].clone(), params[k].grad.clone()
+        if k == "attention.in_proj_bias":
+            a[KBIAS] = 0
+            b[KBIAS] = 0
+        assert rel_fro(a, b) < 5 * FP32_TOL, (k, rel_fro(a, b))
+    # --- the full step through the GEMMs
+    loss = model.fused_train_step(tok, targets_u8.to(dev()), dropout=False, font_ids=fonts)
+    l_ref, g_ref, _ = orc.loss_and_grads(state, tokens, orc.targets_to_f32(targets_u8.numpy()), cfg,
+                                         font_ids=fonts)
+    assert abs(float(loss) - float(l_ref)) < 2e-3 * float(l_ref)
+    got = grads_of(model)
+    assert rel_fro(got["font_embedding.weight"], g_ref["font_embedding.weight"]) < TOY_TOL
+    # --- it trains, and the table separates the fonts
+    opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99))
+    w0 = model.font_embedding.weight.detach().clone()
+    first = float(loss)
+    for _ in range(60):
+        last = model.fused_train_step(tok, targets_u8.to(dev()), dropout=False, font_ids=fonts)
+        opt.step()
+    assert float(last) < 0.5 * first
+    assert float((model.font_embedding.weight.detach() - w0).abs().max()) > 1e-3
+    model.eval()
+    same = tok[:1].repeat(2, 1)
+    q = model.render_u8(same, font_ids=torch.tensor([0, 1])).cpu().float()
+    assert float((q[0] - q[1]).abs().mean()) > 1.0
