@@ -361,6 +361,7 @@ def test_rank_without_samples_joins_the_side_stream_before_zeroing_and_keeps_its
     tr = training.Trainer.__new__(training.Trainer)
     tr.model, tr.optimizer, tr.buckets, tr.P, tr.steps_done = FakeModel(), None, [(0, 4)], 4, 0
     tr.device = torch.device("cpu")
+    tr.fonts = None
     tr.tokens = torch.zeros((8, 5), dtype=torch.int64)
     tr.targets = torch.zeros((8, 2, 2), dtype=torch.uint8)
     slot = torch.ones(())
