@@ -339,4 +339,4 @@ def test_font_embedding_conditioning_matches_oracle(golden_small):
     model.eval()
     same = tok[:1].repeat(2, 1)
     q = model.render_u8(same, font_ids=torch.tensor([0, 1])).cpu().float()
-    assert float((q[0] - q[1]).abs().mean()) > 1.0
+    assert float((q[0] - q[1]).abs().mean()) > 0.2          # the same string renders differently per font
