@@ -581,6 +581,8 @@ def main():
     ap.add_argument("--bg-stages", type=int, default=0, help="background sweep: ring stages of 8 KB (0 = default)")
     ap.add_argument("--bg-chunks", type=int, default=0, help="background sweep: row chunks of wgrad / sweep (0 = default)")
     ap.add_argument("--bg-ctas", type=int, default=0, help="background sweep: CTAs (0 = one per SM)")
+    ap.add_argument("--bg-after-dgrad", type=int, default=-1,
+                    help="background sweep: 1 = start it after the dgrad GEMM, 0 = right after wgrad (-1 = default)")
     ap.add_argument("--no-fuse", action="store_true",
                     help="single GPU: same as --step-mode two-kernel")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4],
@@ -642,6 +644,8 @@ def main():
             bg_kw["bg_chunks"] = args.bg_chunks
         if args.bg_ctas:
             bg_kw["bg_ctas"] = args.bg_ctas
+        if args.bg_after_dgrad >= 0:
+            bg_kw["bg_after_dgrad"] = bool(args.bg_after_dgrad)
     opt = FusedAdamW(model, lr=1e-3, weight_decay=5e-4, betas=(0.9, 0.99), fuse_wgrad=fused,
                      overlap_dgrad=fused and args.overlap_dgrad, **bg_kw)
     dp_parity = None
