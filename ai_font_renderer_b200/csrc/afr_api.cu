@@ -69,6 +69,7 @@ struct afr_ctx {
     float *xhat = nullptr, *rstd = nullptr, *dr32 = nullptr, *dctx32 = nullptr;      // training
     float2* stat = nullptr;
     uint32_t* abits = nullptr;
+    uint8_t* ebits = nullptr;      // embedding-dropout keep bits, one byte per 8 channels
     __nv_bfloat16 *df16 = nullptr, *dr16 = nullptr, *dqkv16 = nullptr;
     float *splitk = nullptr, *ln_part = nullptr, *pos_part = nullptr, *emb_part = nullptr;
     int max_splits = 0, max_ln_parts = 0;
@@ -267,7 +268,7 @@ int run_frontend_wide(afr_ctx* c, const long long* tokens, long long stride, int
   AFR_CUDA(c, launch_wide_split_weight(c->params.wo, E, E, w.wo16, st), "split bf16(out_proj)");
   AFR_CUDA(c, launch_wide_split_weight(c->params.w1, F, E, w.w116, st), "split bf16(fc1)");
   AFR_CUDA(c, launch_wide_embed(d, dr, tokens, stride, c->params.emb, c->params.pos, w.e32, w.e16,
-                                frontend_error_flag(), c->sms, st), "wide_embed");
+                                save_state ? w.ebits : nullptr, frontend_error_flag(), c->sms, st), "wide_embed");
   c->launches += 4;
   int rc;
   // forward GEMMs: split-bf16 operands, K = 3E (x_hi w_hi + x_lo w_hi + x_hi w_lo)
@@ -329,8 +330,8 @@ int run_frontend_backward_wide(afr_ctx* c, const long long* tokens, long long st
   if ((rc = wide_gemm(c, w.dqkv16, 3 * E, true, w.e16, 3 * E, true, 3 * E, E, R, c->grads.win, E, nullptr, splits, st,
                       "gemm(d in_proj.weight)"))) return rc;
   // embedding + positions
-  AFR_CUDA(c, launch_wide_embed_bwd(d, dr, tokens, stride, w.dr32, w.a32, w.pos_part, w.emb_part, c->num_sms,
-                                    c->grads.pos, c->grads.emb, c->sms, st), "wide_embed_bwd");
+  AFR_CUDA(c, launch_wide_embed_bwd(d, dr, tokens, stride, w.dr32, w.a32, w.ebits, w.pos_part, w.emb_part,
+                                    2 * c->num_sms, c->grads.pos, c->grads.emb, c->sms, st), "wide_embed_bwd");
   c->launches += 3;
   return AFR_OK;
 }
@@ -442,6 +443,7 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
       alloc(reinterpret_cast<void**>(&w.rstd), R * 4);
       alloc(reinterpret_cast<void**>(&w.stat), Bm * H * cfg->max_length * sizeof(float2));
       alloc(reinterpret_cast<void**>(&w.abits), Bm * H * cfg->max_length * 4 * sizeof(uint32_t));
+      alloc(reinterpret_cast<void**>(&w.ebits), R * E / 8);
       alloc(reinterpret_cast<void**>(&w.df16), R * F * 2);
       alloc(reinterpret_cast<void**>(&w.dr32), R * E * 4);
       alloc(reinterpret_cast<void**>(&w.dr16), R * E * 2);
@@ -454,9 +456,9 @@ int afr_create(const afr_config* cfg, afr_ctx** out) {
       w.max_ln_parts = c->num_sms * 4;
       alloc(reinterpret_cast<void**>(&w.ln_part),
             static_cast<size_t>(w.max_ln_parts) * (3 * E > F ? 3 * E : F) * 4);   // LayerNorm / bias-gradient partial rows
-      alloc(reinterpret_cast<void**>(&w.pos_part), static_cast<size_t>(c->num_sms) * cfg->max_length * E * 4);
+      alloc(reinterpret_cast<void**>(&w.pos_part), static_cast<size_t>(2 * c->num_sms) * cfg->max_length * E * 4);
       if (static_cast<size_t>(cfg->vocab) * E * 4 <= 128 * 1024)
-        alloc(reinterpret_cast<void**>(&w.emb_part), static_cast<size_t>(c->num_sms) * cfg->vocab * E * 4);
+        alloc(reinterpret_cast<void**>(&w.emb_part), static_cast<size_t>(2 * c->num_sms) * cfg->vocab * E * 4);
     }
   }
   if (e != cudaSuccess) {
@@ -479,7 +481,7 @@ int afr_destroy(afr_ctx* c) {
   {
     auto& w = c->w;
     void* ptrs[] = {w.e32, w.qkv32, w.a32, w.f32, w.e16, w.ctx16, w.h16, w.win16, w.wo16, w.w116, w.xhat, w.rstd,
-                    w.dr32, w.dctx32, w.stat, w.abits, w.df16, w.dr16, w.dqkv16, w.splitk, w.ln_part, w.pos_part,
+                    w.dr32, w.dctx32, w.stat, w.abits, w.ebits, w.df16, w.dr16, w.dqkv16, w.splitk, w.ln_part, w.pos_part,
                     w.emb_part};
     for (void* q : ptrs) cudaFree(q);
   }

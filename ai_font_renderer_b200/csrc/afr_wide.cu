@@ -69,7 +69,7 @@ __device__ __forceinline__ Rng make_rng(const WideDrop& d, int b) {
 __global__ void __launch_bounds__(256)
 wide_embed_kernel(WideDims d, WideDrop dr, const long long* __restrict__ tokens, long long stride,
                   const float* __restrict__ emb, const float* __restrict__ pos, float* __restrict__ e32,
-                  __nv_bfloat16* __restrict__ e16, int* err_flag) {
+                  __nv_bfloat16* __restrict__ e16, uint8_t* __restrict__ ebits, int* err_flag) {
   const int g8 = d.E / 8;
   const long long total = static_cast<long long>(d.B) * d.S * g8;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
@@ -93,6 +93,7 @@ wide_embed_kernel(WideDims d, WideDrop dr, const long long* __restrict__ tokens,
     *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
     store_split8(e16 + r * 3 * d.E + c0, d.E, o);
+    if (ebits != nullptr) ebits[i] = static_cast<uint8_t>(keep);     // keep bits of these 8 channels
   }
 }
 
@@ -603,6 +604,62 @@ wide_colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int
   }
 }
 
+// Embedding backward, column-owner form (vocabulary table in shared memory): thread = channel c,
+// CTA = samples c, c + grid, ...; the thread walks the positions of a sample in order and adds into
+// ITS column of the per-CTA tables d(Pos)[s][c] and d(Emb)[tok[s]][c] -- no two threads share an
+// address, so plain read-modify-write, a fixed summation order, no atomics (the atomic version
+// above spent 1.0 ms per 8192-glyph step on shared-memory atomics: ~2 cycles per lane). Keep bits
+// come from the bytes the forward saved (one per 8 channels).
+__global__ void __launch_bounds__(256)
+wide_embed_bwd_cols_kernel(WideDims d, float inv_e, const long long* __restrict__ tokens, long long stride,
+                           const float* __restrict__ dr32, const float* __restrict__ de32,
+                           const uint8_t* __restrict__ ebits, float* __restrict__ pos_partials,
+                           float* __restrict__ emb_partials) {
+  extern __shared__ __align__(16) float sm[];
+  const int S = d.S, E = d.E, c = threadIdx.x;
+  float* hist = sm;                          // [vocab][E]
+  float* posacc = sm + d.vocab * E;          // [S][E]
+  int* stok = reinterpret_cast<int*>(posacc + S * E);
+  for (int i = c; i < d.vocab * E + S * E; i += E) sm[i] = 0.f;
+  __syncthreads();
+  for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+    for (int s = c; s < S; s += E) {
+      long long t = tokens[b * stride + s];
+      stok[s] = (t < 0 || t >= d.vocab) ? 0 : static_cast<int>(t);
+    }
+    __syncthreads();
+    const float* a = dr32 + static_cast<long long>(b) * S * E + c;
+    const float* g = de32 + static_cast<long long>(b) * S * E + c;
+    const uint8_t* kb = ebits != nullptr ? ebits + static_cast<long long>(b) * S * (E / 8) + (c >> 3) : nullptr;
+    const int bit = c & 7;
+    int s = 0;
+    for (; s + 8 <= S; s += 8) {
+      float v[8];
+      uint32_t keep[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = a[(s + u) * E] + g[(s + u) * E];
+        keep[u] = kb != nullptr ? (kb[(s + u) * (E / 8)] >> bit) & 1u : 1u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        posacc[(s + u) * E + c] += v[u];
+        if (keep[u]) hist[stok[s + u] * E + c] += v[u] * inv_e;
+      }
+    }
+    for (; s < S; ++s) {
+      const float v = a[s * E] + g[s * E];
+      const uint32_t keep = kb != nullptr ? (kb[s * (E / 8)] >> bit) & 1u : 1u;
+      posacc[s * E + c] += v;
+      if (keep) hist[stok[s] * E + c] += v * inv_e;
+    }
+    __syncthreads();
+  }
+  for (int i = c; i < S * E; i += E) pos_partials[static_cast<long long>(blockIdx.x) * S * E + i] = posacc[i];
+  for (int i = c; i < d.vocab * E; i += E)
+    emb_partials[static_cast<long long>(blockIdx.x) * d.vocab * E + i] = hist[i];
+}
+
 // out[m][n] = sum over the K pieces of partials[ks][m][n]; a piece has rows_pad >= M rows (split-K
 // weight gradients, fixed summation order)
 __global__ void __launch_bounds__(256)
@@ -644,10 +701,11 @@ bool wide_shape_supported(int E, int H, int F, int L, const char** why) {
 }
 
 cudaError_t launch_wide_embed(const WideDims& d, const WideDrop& dr, const long long* tokens, long long stride,
-                              const float* emb, const float* pos, float* e32, __nv_bfloat16* e16, int* err_flag,
-                              int num_sms, cudaStream_t st) {
+                              const float* emb, const float* pos, float* e32, __nv_bfloat16* e16, uint8_t* ebits,
+                              int* err_flag, int num_sms, cudaStream_t st) {
   const long long work = static_cast<long long>(d.B) * d.S * (d.E / 8);
-  wide_embed_kernel<<<grid_for(work, 256, num_sms), 256, 0, st>>>(d, dr, tokens, stride, emb, pos, e32, e16, err_flag);
+  wide_embed_kernel<<<grid_for(work, 256, num_sms), 256, 0, st>>>(d, dr, tokens, stride, emb, pos, e32, e16, ebits,
+                                                                err_flag);
   return cudaGetLastError();
 }
 
@@ -759,11 +817,32 @@ cudaError_t launch_wide_act_bwd(const WideDims& d, const WideDrop& dr, const flo
 }
 
 cudaError_t launch_wide_embed_bwd(const WideDims& d, const WideDrop& dr, const long long* tokens, long long stride,
-                                  const float* dr32, const float* de32, float* pos_partials, float* emb_partials,
-                                  int max_partials, float* dpos, float* demb, int num_sms, cudaStream_t st) {
+                                  const float* dr32, const float* de32, const uint8_t* ebits, float* pos_partials,
+                                  float* emb_partials, int max_partials, float* dpos, float* demb, int num_sms,
+                                  cudaStream_t st) {
+  const int n = d.S * d.E;
+  const long long emb_elems = static_cast<long long>(d.vocab) * d.E;
+  const size_t cols_smem = (static_cast<size_t>(emb_elems) + n) * 4 + static_cast<size_t>(d.S) * 4;
+  if (emb_partials != nullptr && cols_smem <= 110 * 1024 && (dr.mode == 0 || ebits != nullptr)) {
+    int grid = 2 * num_sms < d.B ? 2 * num_sms : d.B;
+    if (grid > max_partials) grid = max_partials;
+    cudaError_t e = set_smem(wide_embed_bwd_cols_kernel, cols_smem);
+    if (e != cudaSuccess) return e;
+    wide_embed_bwd_cols_kernel<<<grid, d.E, cols_smem, st>>>(d, dr.inv_e, tokens, stride, dr32, de32,
+                                                          dr.mode == 1 ? ebits : nullptr, pos_partials, emb_partials);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    wide_colsum_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos_partials, grid, n, dpos, n, nullptr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (d.S < d.L) {
+      e = cudaMemsetAsync(dpos + n, 0, static_cast<size_t>(d.L - d.S) * d.E * 4, st);
+      if (e != cudaSuccess) return e;
+    }
+    wide_colsum_partials_kernel<<<static_cast<int>((emb_elems + 255) / 256), 256, 0, st>>>(
+        emb_partials, grid, static_cast<int>(emb_elems), demb, static_cast<int>(emb_elems), nullptr);
+    return cudaGetLastError();
+  }
   int grid = num_sms < d.B ? num_sms : d.B;
   if (grid > max_partials) grid = max_partials;
-  const int n = d.S * d.E;
   const bool use_hist = emb_partials != nullptr;
   const size_t smem = use_hist ? static_cast<size_t>(d.vocab) * d.E * 4 : 0;
   cudaError_t e = set_smem(wide_embed_bwd_kernel, smem > 0 ? smem : 1024);
