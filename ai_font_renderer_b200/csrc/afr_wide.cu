@@ -14,6 +14,8 @@
 // from the same counter-based generator as the narrow path (afr_philox.cuh), so the oracle's
 // builtin_masks() reproduces them. Parity for this path is "restated-oracle parity" at the bf16
 // tolerance (2e-2): the reference has no such configuration.
+#include <cstdlib>
+
 #include "afr_internal.h"
 #include "afr_philox.cuh"
 #include "afr_ptx.cuh"
@@ -517,6 +519,276 @@ wide_attention_bwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv
   }
 }
 
+
+// ---------------------------------------------------------------------------- attention backward, tensor cores
+// The same two passes on warp-level bf16 MMAs (mma.sync.m16n8k16, fp32 accumulate): 16-row tiles of
+// one head per warp; S = Q K^T and dP = dO V^T per 8-key tile, soft-max recomputed from the saved
+// row statistics, dS = P (keep ? dP : 0 - D) converted in registers into the A fragment of the
+// next product (dQ += dS K; pass 2 with keys as rows: dK += dS^T Q, dV += P_kept^T dO). The score
+// product uses split-bf16 q and k (q_hi k_hi + q_lo k_hi + q_hi k_lo) so that the recomputed P
+// matches the forward's fp32 P; everything else is plain bf16 (the backward is smooth).
+// Operands sit in shared memory as bf16, row-major with 8 elements of padding per row (conflict-
+// free fragment loads) plus transposed copies of q, k, dO for the products whose reduction index
+// is the row index. These are the legacy tensor instructions: a head is 64 x 64 x 16, far too
+// small for a tcgen05 tile of 128 rows with its TMEM round trip per soft-max.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t lds_u32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+struct AttnMmaSmem {
+  int ldr, ldt, sp, nw;
+  size_t q_hi, q_lo, k_hi, k_lo, v, dO, qT, kT, dOT, stat, D, ab, total;   // byte offsets
+};
+__host__ __device__ inline AttnMmaSmem attn_mma_smem(int S, int E, int H) {
+  AttnMmaSmem m{};
+  m.sp = (S + 15) & ~15;
+  m.ldr = E + 8;
+  m.ldt = m.sp + 8;
+  m.nw = (S + 31) >> 5;
+  size_t o = 0;
+  const size_t row = static_cast<size_t>(m.sp) * m.ldr * 2, tr = static_cast<size_t>(E) * m.ldt * 2;
+  m.q_hi = o; o += row; m.q_lo = o; o += row; m.k_hi = o; o += row; m.k_lo = o; o += row;
+  m.v = o; o += row; m.dO = o; o += row;
+  m.qT = o; o += tr; m.kT = o; o += tr; m.dOT = o; o += tr;
+  m.stat = o; o += static_cast<size_t>(H) * m.sp * 8;
+  m.D = o; o += static_cast<size_t>(H) * m.sp * 4;
+  m.ab = o; o += static_cast<size_t>(H) * m.sp * m.nw * 4;
+  m.total = o;
+  return m;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(512, 1)
+wide_attention_bwd_mma_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv, const float* __restrict__ dctx,
+                              const __nv_bfloat16* __restrict__ ctx16, const float2* __restrict__ stat,
+                              const uint32_t* __restrict__ abits, __nv_bfloat16* __restrict__ dqkv16) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int KK = DH / 16, NT = DH / 8;
+  const int S = d.S, E = d.E, H = d.H, b = blockIdx.x;
+  const AttnMmaSmem L = attn_mma_smem(S, E, H);
+  const int SP = L.sp, LDR = L.ldr, LDT = L.ldt, NW = L.nw;
+  __nv_bfloat16* q_hi = reinterpret_cast<__nv_bfloat16*>(smraw + L.q_hi);
+  __nv_bfloat16* q_lo = reinterpret_cast<__nv_bfloat16*>(smraw + L.q_lo);
+  __nv_bfloat16* k_hi = reinterpret_cast<__nv_bfloat16*>(smraw + L.k_hi);
+  __nv_bfloat16* k_lo = reinterpret_cast<__nv_bfloat16*>(smraw + L.k_lo);
+  __nv_bfloat16* v_s = reinterpret_cast<__nv_bfloat16*>(smraw + L.v);
+  __nv_bfloat16* do_s = reinterpret_cast<__nv_bfloat16*>(smraw + L.dO);
+  __nv_bfloat16* qT = reinterpret_cast<__nv_bfloat16*>(smraw + L.qT);
+  __nv_bfloat16* kT = reinterpret_cast<__nv_bfloat16*>(smraw + L.kT);
+  __nv_bfloat16* doT = reinterpret_cast<__nv_bfloat16*>(smraw + L.dOT);
+  float2* st_s = reinterpret_cast<float2*>(smraw + L.stat);
+  float* D_s = reinterpret_cast<float*>(smraw + L.D);
+  uint32_t* ab_s = reinterpret_cast<uint32_t*>(smraw + L.ab);
+  const float* base = qkv + static_cast<long long>(b) * S * 3 * E;
+  const float qscale = rsqrtf(static_cast<float>(DH)) * kLog2e;
+  const float inv_a = dr.inv_a, inv_sqrt = rsqrtf(static_cast<float>(DH));
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+
+  // ---- stage the sample: bf16 (split for q, k), row-major + transposed; zero padding
+  for (int i = threadIdx.x; i < SP * E; i += blockDim.x) {
+    const int s = i / E, c = i % E;
+    float qv = 0.f, kv = 0.f, vv = 0.f, dv = 0.f;
+    if (s < S) {
+      qv = base[s * 3 * E + c] * qscale;
+      kv = base[s * 3 * E + E + c];
+      vv = base[s * 3 * E + 2 * E + c];
+      dv = dctx[(static_cast<long long>(b) * S + s) * E + c] * inv_a;
+    }
+    const __nv_bfloat16 qh = __float2bfloat16_rn(qv), kh = __float2bfloat16_rn(kv), dh = __float2bfloat16_rn(dv);
+    q_hi[s * LDR + c] = qh;
+    q_lo[s * LDR + c] = __float2bfloat16_rn(qv - __bfloat162float(qh));
+    k_hi[s * LDR + c] = kh;
+    k_lo[s * LDR + c] = __float2bfloat16_rn(kv - __bfloat162float(kh));
+    v_s[s * LDR + c] = __float2bfloat16_rn(vv);
+    do_s[s * LDR + c] = dh;
+    qT[c * LDT + s] = qh;
+    kT[c * LDT + s] = kh;
+    doT[c * LDT + s] = dh;
+  }
+  for (int i = threadIdx.x; i < E * 8; i += blockDim.x) {     // the 8 padding columns of the transposed copies
+    const int c = i >> 3, s = SP + (i & 7);
+    qT[c * LDT + s] = zero; kT[c * LDT + s] = zero; doT[c * LDT + s] = zero;
+  }
+  for (int i = threadIdx.x; i < H * SP; i += blockDim.x) {
+    const int h = i / SP, s = i % SP;
+    float2 stv = make_float2(0.f, 0.f);
+    float Dv = 0.f;
+    if (s < S) {
+      stv = stat[(static_cast<long long>(b) * H + h) * S + s];
+      const float* cg = dctx + (static_cast<long long>(b) * S + s) * E + h * DH;
+      const __nv_bfloat16* cx = ctx16 + (static_cast<long long>(b) * S + s) * 3 * E + h * DH;   // [hi | lo | hi]
+#pragma unroll
+      for (int j = 0; j < DH; ++j) Dv = fmaf(cg[j], __bfloat162float(cx[j]) + __bfloat162float(cx[E + j]), Dv);
+    }
+    st_s[i] = stv;
+    D_s[i] = Dv;
+    for (int w = 0; w < NW; ++w)
+      ab_s[i * NW + w] = s < S ? abits[((static_cast<long long>(b) * H + h) * S + s) * 4 + w] : 0u;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles = SP >> 4, tasks = H * tiles;
+
+  // ---- pass 1: rows = queries -> dq
+  for (int task = warp; task < tasks; task += nwarps) {
+    const int h = task / tiles, i0 = (task % tiles) << 4;
+    const int rA = i0 + g, rB = rA + 8;
+    uint32_t aqh[KK][4], aql[KK][4], ado[KK][4];
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const int c0 = h * DH + kk * 16 + 2 * t;
+      aqh[kk][0] = lds_u32(q_hi + rA * LDR + c0); aqh[kk][1] = lds_u32(q_hi + rB * LDR + c0);
+      aqh[kk][2] = lds_u32(q_hi + rA * LDR + c0 + 8); aqh[kk][3] = lds_u32(q_hi + rB * LDR + c0 + 8);
+      aql[kk][0] = lds_u32(q_lo + rA * LDR + c0); aql[kk][1] = lds_u32(q_lo + rB * LDR + c0);
+      aql[kk][2] = lds_u32(q_lo + rA * LDR + c0 + 8); aql[kk][3] = lds_u32(q_lo + rB * LDR + c0 + 8);
+      ado[kk][0] = lds_u32(do_s + rA * LDR + c0); ado[kk][1] = lds_u32(do_s + rB * LDR + c0);
+      ado[kk][2] = lds_u32(do_s + rA * LDR + c0 + 8); ado[kk][3] = lds_u32(do_s + rB * LDR + c0 + 8);
+    }
+    const float2 stA = st_s[h * SP + rA], stB = st_s[h * SP + rB];
+    const float DA = D_s[h * SP + rA], DB = D_s[h * SP + rB];
+    const uint32_t* wA = ab_s + (h * SP + rA) * NW;
+    const uint32_t* wB = ab_s + (h * SP + rB) * NW;
+    float dq[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f; }
+    for (int jj = 0; jj < tiles; ++jj) {
+      float ds[2][4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j0 = jj * 16 + half * 8;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          const int c0 = h * DH + kk * 16 + 2 * t;
+          const uint32_t bh0 = lds_u32(k_hi + (j0 + g) * LDR + c0), bh1 = lds_u32(k_hi + (j0 + g) * LDR + c0 + 8);
+          const uint32_t bl0 = lds_u32(k_lo + (j0 + g) * LDR + c0), bl1 = lds_u32(k_lo + (j0 + g) * LDR + c0 + 8);
+          mma_bf16_16816(c, aqh[kk], bh0, bh1);
+          mma_bf16_16816(c, aql[kk], bh0, bh1);
+          mma_bf16_16816(c, aqh[kk], bl0, bl1);
+          const uint32_t bv0 = lds_u32(v_s + (j0 + g) * LDR + c0), bv1 = lds_u32(v_s + (j0 + g) * LDR + c0 + 8);
+          mma_bf16_16816(e, ado[kk], bv0, bv1);
+        }
+        const int key0 = j0 + 2 * t, key1 = key0 + 1;
+        const uint32_t wa = wA[key0 >> 5], wb = wB[key0 >> 5];       // key0, key1 share a word (key0 is even)
+        const float pA0 = key0 < S ? ex2(c[0] - stA.x) * stA.y : 0.f, pA1 = key1 < S ? ex2(c[1] - stA.x) * stA.y : 0.f;
+        const float pB0 = key0 < S ? ex2(c[2] - stB.x) * stB.y : 0.f, pB1 = key1 < S ? ex2(c[3] - stB.x) * stB.y : 0.f;
+        ds[half][0] = pA0 * ((((wa >> (key0 & 31)) & 1u) ? e[0] : 0.f) - DA);
+        ds[half][1] = pA1 * ((((wa >> (key1 & 31)) & 1u) ? e[1] : 0.f) - DA);
+        ds[half][2] = pB0 * ((((wb >> (key0 & 31)) & 1u) ? e[2] : 0.f) - DB);
+        ds[half][3] = pB1 * ((((wb >> (key1 & 31)) & 1u) ? e[3] : 0.f) - DB);
+      }
+      const uint32_t ads[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]),
+                               pack2(ds[1][0], ds[1][1]), pack2(ds[1][2], ds[1][3])};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const __nv_bfloat16* kp = kT + (h * DH + nt * 8 + g) * LDT + jj * 16 + 2 * t;
+        mma_bf16_16816(dq[nt], ads, lds_u32(kp), lds_u32(kp + 8));
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = h * DH + nt * 8 + 2 * t;
+      if (rA < S)
+        *reinterpret_cast<uint32_t*>(dqkv16 + (static_cast<long long>(b) * S + rA) * 3 * E + col) =
+            pack2(dq[nt][0] * inv_sqrt, dq[nt][1] * inv_sqrt);
+      if (rB < S)
+        *reinterpret_cast<uint32_t*>(dqkv16 + (static_cast<long long>(b) * S + rB) * 3 * E + col) =
+            pack2(dq[nt][2] * inv_sqrt, dq[nt][3] * inv_sqrt);
+    }
+  }
+
+  // ---- pass 2: rows = keys -> dk, dv
+  for (int task = warp; task < tasks; task += nwarps) {
+    const int h = task / tiles, j0 = (task % tiles) << 4;
+    const int kA = j0 + g, kB = kA + 8;
+    uint32_t akh[KK][4], akl[KK][4], av[KK][4];
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const int c0 = h * DH + kk * 16 + 2 * t;
+      akh[kk][0] = lds_u32(k_hi + kA * LDR + c0); akh[kk][1] = lds_u32(k_hi + kB * LDR + c0);
+      akh[kk][2] = lds_u32(k_hi + kA * LDR + c0 + 8); akh[kk][3] = lds_u32(k_hi + kB * LDR + c0 + 8);
+      akl[kk][0] = lds_u32(k_lo + kA * LDR + c0); akl[kk][1] = lds_u32(k_lo + kB * LDR + c0);
+      akl[kk][2] = lds_u32(k_lo + kA * LDR + c0 + 8); akl[kk][3] = lds_u32(k_lo + kB * LDR + c0 + 8);
+      av[kk][0] = lds_u32(v_s + kA * LDR + c0); av[kk][1] = lds_u32(v_s + kB * LDR + c0);
+      av[kk][2] = lds_u32(v_s + kA * LDR + c0 + 8); av[kk][3] = lds_u32(v_s + kB * LDR + c0 + 8);
+    }
+    const bool okA = kA < S, okB = kB < S;
+    const int wsel = kA >> 5, shA = kA & 31, shB = kB & 31;      // kA and kB lie in the same 32-key word
+    float dk[NT][4], dvv[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+      dvv[nt][0] = dvv[nt][1] = dvv[nt][2] = dvv[nt][3] = 0.f;
+    }
+    for (int ii = 0; ii < tiles; ++ii) {
+      float dsT[2][4], pT[2][4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i0 = ii * 16 + half * 8;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          const int c0 = h * DH + kk * 16 + 2 * t;
+          const uint32_t bh0 = lds_u32(q_hi + (i0 + g) * LDR + c0), bh1 = lds_u32(q_hi + (i0 + g) * LDR + c0 + 8);
+          const uint32_t bl0 = lds_u32(q_lo + (i0 + g) * LDR + c0), bl1 = lds_u32(q_lo + (i0 + g) * LDR + c0 + 8);
+          mma_bf16_16816(c, akh[kk], bh0, bh1);
+          mma_bf16_16816(c, akl[kk], bh0, bh1);
+          mma_bf16_16816(c, akh[kk], bl0, bl1);
+          const uint32_t bd0 = lds_u32(do_s + (i0 + g) * LDR + c0), bd1 = lds_u32(do_s + (i0 + g) * LDR + c0 + 8);
+          mma_bf16_16816(e, av[kk], bd0, bd1);
+        }
+        const int q0 = i0 + 2 * t, q1 = q0 + 1;
+        const float2 st0 = st_s[h * SP + q0], st1 = st_s[h * SP + q1];     // (0, 0) for padded queries: p = 0
+        const float D0 = D_s[h * SP + q0], D1 = D_s[h * SP + q1];
+        const uint32_t w0 = ab_s[(h * SP + q0) * NW + wsel], w1 = ab_s[(h * SP + q1) * NW + wsel];
+        const float p00 = okA ? ex2(c[0] - st0.x) * st0.y : 0.f, p01 = okA ? ex2(c[1] - st1.x) * st1.y : 0.f;
+        const float p10 = okB ? ex2(c[2] - st0.x) * st0.y : 0.f, p11 = okB ? ex2(c[3] - st1.x) * st1.y : 0.f;
+        const bool k00 = (w0 >> shA) & 1u, k01 = (w1 >> shA) & 1u, k10 = (w0 >> shB) & 1u, k11 = (w1 >> shB) & 1u;
+        dsT[half][0] = p00 * ((k00 ? e[0] : 0.f) - D0); dsT[half][1] = p01 * ((k01 ? e[1] : 0.f) - D1);
+        dsT[half][2] = p10 * ((k10 ? e[2] : 0.f) - D0); dsT[half][3] = p11 * ((k11 ? e[3] : 0.f) - D1);
+        pT[half][0] = k00 ? p00 : 0.f; pT[half][1] = k01 ? p01 : 0.f;
+        pT[half][2] = k10 ? p10 : 0.f; pT[half][3] = k11 ? p11 : 0.f;
+      }
+      const uint32_t ads[4] = {pack2(dsT[0][0], dsT[0][1]), pack2(dsT[0][2], dsT[0][3]),
+                               pack2(dsT[1][0], dsT[1][1]), pack2(dsT[1][2], dsT[1][3])};
+      const uint32_t ap[4] = {pack2(pT[0][0], pT[0][1]), pack2(pT[0][2], pT[0][3]),
+                              pack2(pT[1][0], pT[1][1]), pack2(pT[1][2], pT[1][3])};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int off = (h * DH + nt * 8 + g) * LDT + ii * 16 + 2 * t;
+        mma_bf16_16816(dk[nt], ads, lds_u32(qT + off), lds_u32(qT + off + 8));
+        mma_bf16_16816(dvv[nt], ap, lds_u32(doT + off), lds_u32(doT + off + 8));
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = h * DH + nt * 8 + 2 * t;
+      // the stored q carries log2(e)/sqrt(dh): d(k) = sum dS q_raw / sqrt(dh) = dk * ln 2
+      if (okA) {
+        __nv_bfloat16* o = dqkv16 + (static_cast<long long>(b) * S + kA) * 3 * E + E + col;
+        *reinterpret_cast<uint32_t*>(o) = pack2(dk[nt][0] * kLn2, dk[nt][1] * kLn2);
+        *reinterpret_cast<uint32_t*>(o + E) = pack2(dvv[nt][0], dvv[nt][1]);
+      }
+      if (okB) {
+        __nv_bfloat16* o = dqkv16 + (static_cast<long long>(b) * S + kB) * 3 * E + E + col;
+        *reinterpret_cast<uint32_t*>(o) = pack2(dk[nt][2] * kLn2, dk[nt][3] * kLn2);
+        *reinterpret_cast<uint32_t*>(o + E) = pack2(dvv[nt][2], dvv[nt][3]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- embedding backward
 // de = d(residual) + d(through q|k|v); d(Pos)[s] = sum_b de; d(Emb)[tok] += keep ? de/(1-p) : 0.
 // CTA c handles samples c, c + grid, ...; thread owns a fixed set of (position, channel) pairs, so
@@ -736,10 +1008,22 @@ cudaError_t launch_wide_attention_fwd(const WideDims& d, const WideDrop& dr, con
 cudaError_t launch_wide_attention_bwd(const WideDims& d, const WideDrop& dr, const float* qkv, const float* dctx,
                                       const __nv_bfloat16* ctx16, const float2* stat, const uint32_t* abits,
                                       __nv_bfloat16* dqkv16, cudaStream_t st) {
+  cudaError_t e;
+  static const bool no_mma = std::getenv("AFR_WIDE_ATTN_SIMT") != nullptr;      // diagnostic: force the SIMT kernel
+  const AttnMmaSmem ml = attn_mma_smem(d.S, d.E, d.H);
+  if (!no_mma && (d.dh == 16 || d.dh == 32) && ml.total <= 220 * 1024) {
+    if (d.dh == 16) {
+      if ((e = set_smem(wide_attention_bwd_mma_kernel<16>, ml.total)) != cudaSuccess) return e;
+      wide_attention_bwd_mma_kernel<16><<<d.B, 512, ml.total, st>>>(d, dr, qkv, dctx, ctx16, stat, abits, dqkv16);
+    } else {
+      if ((e = set_smem(wide_attention_bwd_mma_kernel<32>, ml.total)) != cudaSuccess) return e;
+      wide_attention_bwd_mma_kernel<32><<<d.B, 512, ml.total, st>>>(d, dr, qkv, dctx, ctx16, stat, abits, dqkv16);
+    }
+    return cudaGetLastError();
+  }
   const size_t smem = (static_cast<size_t>(4) * d.S * d.E + static_cast<size_t>(d.S) * d.H) * 4;
   int threads = d.H * ((d.S + 31) & ~31);
   if (threads > 512) threads = 512;
-  cudaError_t e;
   switch (d.dh) {
     case 8:
       if ((e = set_smem(wide_attention_bwd_kernel<8>, smem)) != cudaSuccess) return e;
