@@ -593,26 +593,40 @@ wide_attention_bwd_mma_kernel(WideDims d, WideDrop dr, const float* __restrict__
   const float inv_a = dr.inv_a, inv_sqrt = rsqrtf(static_cast<float>(DH));
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
 
-  // ---- stage the sample: bf16 (split for q, k), row-major + transposed; zero padding
-  for (int i = threadIdx.x; i < SP * E; i += blockDim.x) {
-    const int s = i / E, c = i % E;
-    float qv = 0.f, kv = 0.f, vv = 0.f, dv = 0.f;
+  // ---- stage the sample: bf16 (split for q, k), row-major + transposed; zero padding.
+  // Four channels per thread and iteration (128-bit global loads, 64-bit row-major stores).
+  for (int i = threadIdx.x; i < SP * (E / 4); i += blockDim.x) {
+    const int s = i / (E / 4), c = (i % (E / 4)) * 4;
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv, vv = qv, dv = qv;
     if (s < S) {
-      qv = base[s * 3 * E + c] * qscale;
-      kv = base[s * 3 * E + E + c];
-      vv = base[s * 3 * E + 2 * E + c];
-      dv = dctx[(static_cast<long long>(b) * S + s) * E + c] * inv_a;
+      qv = *reinterpret_cast<const float4*>(base + s * 3 * E + c);
+      kv = *reinterpret_cast<const float4*>(base + s * 3 * E + E + c);
+      vv = *reinterpret_cast<const float4*>(base + s * 3 * E + 2 * E + c);
+      dv = *reinterpret_cast<const float4*>(dctx + (static_cast<long long>(b) * S + s) * E + c);
     }
-    const __nv_bfloat16 qh = __float2bfloat16_rn(qv), kh = __float2bfloat16_rn(kv), dh = __float2bfloat16_rn(dv);
-    q_hi[s * LDR + c] = qh;
-    q_lo[s * LDR + c] = __float2bfloat16_rn(qv - __bfloat162float(qh));
-    k_hi[s * LDR + c] = kh;
-    k_lo[s * LDR + c] = __float2bfloat16_rn(kv - __bfloat162float(kh));
-    v_s[s * LDR + c] = __float2bfloat16_rn(vv);
-    do_s[s * LDR + c] = dh;
-    qT[c * LDT + s] = qh;
-    kT[c * LDT + s] = kh;
-    doT[c * LDT + s] = dh;
+    const float q4[4] = {qv.x * qscale, qv.y * qscale, qv.z * qscale, qv.w * qscale};
+    const float k4[4] = {kv.x, kv.y, kv.z, kv.w};
+    const float d4[4] = {dv.x * inv_a, dv.y * inv_a, dv.z * inv_a, dv.w * inv_a};
+    __nv_bfloat16 qh[4], kh[4], dh4[4];
+    float ql[4], kl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      qh[u] = __float2bfloat16_rn(q4[u]); kh[u] = __float2bfloat16_rn(k4[u]); dh4[u] = __float2bfloat16_rn(d4[u]);
+      ql[u] = q4[u] - __bfloat162float(qh[u]);
+      kl[u] = k4[u] - __bfloat162float(kh[u]);
+      qT[(c + u) * LDT + s] = qh[u];
+      kT[(c + u) * LDT + s] = kh[u];
+      doT[(c + u) * LDT + s] = dh4[u];
+    }
+    auto st4 = [&](__nv_bfloat16* dst, float a0, float a1, float a2, float a3) {
+      *reinterpret_cast<uint2*>(dst + s * LDR + c) = make_uint2(pack2(a0, a1), pack2(a2, a3));
+    };
+    st4(q_hi, q4[0], q4[1], q4[2], q4[3]);
+    st4(q_lo, ql[0], ql[1], ql[2], ql[3]);
+    st4(k_hi, k4[0], k4[1], k4[2], k4[3]);
+    st4(k_lo, kl[0], kl[1], kl[2], kl[3]);
+    st4(v_s, vv.x, vv.y, vv.z, vv.w);
+    st4(do_s, d4[0], d4[1], d4[2], d4[3]);
   }
   for (int i = threadIdx.x; i < E * 8; i += blockDim.x) {     // the 8 padding columns of the transposed copies
     const int c = i >> 3, s = SP + (i & 7);
