@@ -126,14 +126,16 @@ wide_attention_fwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv
   for (int i = threadIdx.x; i < d.H * s_pad; i += blockDim.x) {
     const int h = i / s_pad, s = i % s_pad;
     if (s >= S) continue;
-    float q[DH], acc[DH];
+    // packed fp32 (FFMA2): q and the context accumulator as DH / 2 register pairs
+    float2 q2[DH / 2], acc2[DH / 2];
 #pragma unroll
     for (int j = 0; j < DH; j += 4) {
       const float4 v = *reinterpret_cast<const float4*>(base + s * 3 * E + h * DH + j);
-      q[j] = v.x * qscale; q[j + 1] = v.y * qscale; q[j + 2] = v.z * qscale; q[j + 3] = v.w * qscale;
+      q2[j / 2] = make_float2(v.x * qscale, v.y * qscale);
+      q2[j / 2 + 1] = make_float2(v.z * qscale, v.w * qscale);
     }
 #pragma unroll
-    for (int j = 0; j < DH; ++j) acc[j] = 0.f;
+    for (int j = 0; j < DH / 2; ++j) acc2[j] = make_float2(0.f, 0.f);
     float m = -INFINITY, l = 0.f;
     const uint32_t row = static_cast<uint32_t>(h * S + s);
     const float* kh = sk + h * DH;
@@ -146,21 +148,25 @@ wide_attention_fwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv
       float bm = m;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        float dsum = 0.f;
+        float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < DH; j += 4) {
           const float4 kv = *reinterpret_cast<const float4*>(kh + (t0 + u) * E + j);
-          dsum = fmaf(q[j], kv.x, dsum); dsum = fmaf(q[j + 1], kv.y, dsum);
-          dsum = fmaf(q[j + 2], kv.z, dsum); dsum = fmaf(q[j + 3], kv.w, dsum);
+          d2 = ptx::fma2(q2[j / 2], make_float2(kv.x, kv.y), d2);
+          d2 = ptx::fma2(q2[j / 2 + 1], make_float2(kv.z, kv.w), d2);
         }
+        const float dsum = d2.x + d2.y;
         sc[u] = (t0 + u < S) ? dsum : -INFINITY;
         bm = fmaxf(bm, sc[u]);
       }
       const float corr = ex2(m - bm);
       m = bm;
       l *= corr;
+      {
+        const float2 c2 = make_float2(corr, corr);
 #pragma unroll
-      for (int j = 0; j < DH; ++j) acc[j] *= corr;
+        for (int j = 0; j < DH / 2; ++j) acc2[j] = ptx::mul2(acc2[j], c2);
+      }
       uint32_t keep = 0xFFu;
       if (dr.mode == 1) keep = keep_bits8(rng.block(1u | (row << 2), static_cast<uint32_t>(blk)), dr.thr_a);
 #pragma unroll
@@ -169,11 +175,12 @@ wide_attention_fwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv
           const float p = ex2(sc[u] - m);
           l += p;                                   // the denominator counts dropped keys too
           const float pk = ((keep >> u) & 1u) ? p : 0.f;
+          const float2 p2 = make_float2(pk, pk);
 #pragma unroll
           for (int j = 0; j < DH; j += 4) {
             const float4 vv = *reinterpret_cast<const float4*>(vh + (t0 + u) * E + j);
-            acc[j] = fmaf(pk, vv.x, acc[j]); acc[j + 1] = fmaf(pk, vv.y, acc[j + 1]);
-            acc[j + 2] = fmaf(pk, vv.z, acc[j + 2]); acc[j + 3] = fmaf(pk, vv.w, acc[j + 3]);
+            acc2[j / 2] = ptx::fma2(p2, make_float2(vv.x, vv.y), acc2[j / 2]);
+            acc2[j / 2 + 1] = ptx::fma2(p2, make_float2(vv.z, vv.w), acc2[j / 2 + 1]);
           }
         }
       }
@@ -183,6 +190,9 @@ wide_attention_fwd_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv
         bits = 0;
       }
     }
+    float acc[DH];
+#pragma unroll
+    for (int j = 0; j < DH / 2; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
     const float linv = 1.f / l;
     const float scale = dr.inv_a * linv;
     __nv_bfloat16* out = ctx16 + (static_cast<long long>(b) * S + s) * 3 * E + h * DH;
