@@ -14,13 +14,16 @@
 //     (MUFU.EX2); the linear layers run one warp per position with the lane's weight row/column
 //     in registers and the activation row broadcast.
 //   * The training forward leaves a 86 KB record per sample (e, q, k, v, context, normalised
-//     residual, soft-max statistics and every dropout decision as bit masks). The backward stages
-//     it into shared memory with cp.async.bulk + mbarriers while the previous phase computes:
-//     nothing is recomputed, no random number is drawn twice.
+//     residual, soft-max statistics and every dropout decision as bit masks). The backward (three
+//     kernels, see below) stages it into shared memory with cp.async.bulk + mbarriers / cp.async:
+//     no random number is drawn twice; its attention part runs on warp-level TF32 MMAs (3xTF32).
 //   * The ten small weight gradients accumulate in registers across all samples of a CTA and
 //     leave as per-CTA partials that a second kernel sums in a fixed order: deterministic, no
 //     float atomics. The embedding scatter-add is a per-CTA shared-memory table walked in
 //     position order by one warp.
+#include <cstdlib>
+#include <initializer_list>
+
 #include "afr_internal.h"
 #include "afr_philox.cuh"
 #include "afr_ptx.cuh"
@@ -477,66 +480,55 @@ __global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a
   frontend_forward_body(a);
 }
 
-// =========================================================================== backward kernel
-struct BwdSmem {
-  int w1, wo, win, lnw;
-  int xhat, df, dr, ctx, q, k, v, e, dctx, stat, abits, fbits, ebits, rstd, tok, hist, fonth, red, bars;
-  int total;
+// =========================================================================== backward kernels
+// Three kernels per batch, each a loop over samples with the sample's operands in shared memory:
+//   K1 frontend_backward_head_kernel : fc1 / ReLU / dropout / LayerNorm backward, out-projection
+//      backward (B1, B1b) and dW1, db1, dWo, dbo (B2); hands d(residual), d(ctx) and D to the record
+//   K2 frontend_backward_attn_kernel : soft-max attention backward on warp-level TF32 MMAs
+//   K3 frontend_backward_tail_kernel : in-projection backward, dPos, d(embedding) (B4) and dWin,
+//      dbin (B5)
+// A single kernel holding all of it (round 1) needed 190 KB of shared memory per sample: one
+// 13-warp CTA per SM, 40 % of the issue slots and 61 % of the shared-memory pipe busy (ncu), half
+// of its time in the attention phase. Split, the attention part takes two CTAs of 14 warps per SM.
+
+// ---------------------------------------------------------------- K1: head of the backward
+struct HeadSmem {
+  int w1, wo, lnw, xhat, df, dr, ctx, fbits, rstd, red, bars, total;
 };
-__host__ __device__ inline BwdSmem make_bwd_smem(int L, int vocab) {
+__host__ __device__ inline HeadSmem make_head_smem(int L) {
   const int L4 = (L + 3) & ~3;
-  BwdSmem s{};
+  HeadSmem s{};
   int o = 0;
   s.w1 = o;  o += kF * kLdW;
   s.wo = o;  o += kE * kLdW;
-  s.win = o; o += 3 * kE * kLdW;
   s.lnw = o; o += kE;
   o = (o + 3) & ~3;
-  s.xhat = o; o += L * kE;        // xhat -> h (B1) -> dq (B3)
-  s.df = o;   o += L * kF;        // dfeat -> df (B1) ; second half -> dv (B3)
-  s.dr = o;   o += L * kE;        // d(residual) (B1) -> d(embedding rows) (B4)
-  s.ctx = o;  o += L * kE;        // ctx -> dk (B3)
-  s.q = o;    o += L * kE;
-  s.k = o;    o += L * kE;
-  s.v = o;    o += L * kE;
-  s.e = o;    o += L * kE;
-  s.dctx = o; o += L * kE;
-  s.stat = o; o += L * kHeads * 4;   // (m, 1/l, D, -)
-  s.abits = o; o += kHeads * L * 4;
+  s.xhat = o; o += L * kE;        // xhat -> h (B1)
+  s.df = o;   o += L * kF;        // dfeat -> df (B1)
+  s.dr = o;   o += L * kE;        // d(residual)
+  s.ctx = o;  o += L * kE;
   s.fbits = o; o += L4 * 2;
-  s.ebits = o; o += L4;
   s.rstd = o; o += L4;
-  s.tok = o;  o += L4;
-  s.hist = o; o += vocab <= kEmbSmemMaxVocab ? vocab * kE : 0;
-  s.fonth = o; o += kMaxFonts * kE;   // d(font_embedding) of this CTA's samples
   s.red = o;  o += kWarps * kE * 2;
   o = (o + 3) & ~3;
-  s.bars = o; o += 8;                // 4 mbarriers
+  s.bars = o; o += 4;             // 2 mbarriers
   s.total = o;
   return s;
 }
 
-__device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
+__device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) {
   extern __shared__ __align__(16) float sm[];
-  const BwdSmem o = make_bwd_smem(a.L, a.vocab);
+  const HeadSmem o = make_head_smem(a.L);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, S4 = (S + 3) & ~3, KF = a.L * kF;
-  const bool hist_smem = a.vocab <= kEmbSmemMaxVocab;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o.bars);
   float* part = a.partials + static_cast<long long>(blockIdx.x) * a.lay.total;
 
   load_matrix(a.w.w1, sm + o.w1, kF);
   load_matrix(a.w.wo, sm + o.wo, kE);
-  load_matrix(a.w.win, sm + o.win, 3 * kE);
   if (tid < kE) sm[o.lnw + tid] = a.w.lnw[tid];
-  if (hist_smem) {
-    for (int i = tid; i < a.vocab * kE; i += kThreads) sm[o.hist + i] = 0.f;
-  } else {
-    for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = 0.f;
-  }
-  for (int i = tid; i < kMaxFonts * kE; i += kThreads) sm[o.fonth + i] = 0.f;
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -545,42 +537,24 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
   float* s_df = sm + o.df;
   float* s_dr = sm + o.dr;
   float* s_ctx = sm + o.ctx;
-  float* s_q = sm + o.q;
-  float* s_k = sm + o.k;
-  float* s_v = sm + o.v;
-  float* s_e = sm + o.e;
-  float* s_dctx = sm + o.dctx;
-  float* s_stat = sm + o.stat;
-  const uint32_t* s_abits = reinterpret_cast<const uint32_t*>(sm + o.abits);
   const uint32_t* s_fbits = reinterpret_cast<const uint32_t*>(sm + o.fbits);
-  const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + o.ebits);
-  int* s_tok = reinterpret_cast<int*>(sm + o.tok);
-  float* s_dq = s_xhat;
-  float* s_dk = s_ctx;
-  float* s_dv = s_df + a.L * kE;
 
   // gradient accumulators that live in registers for the whole kernel
   // (lane = input channel c; a warp owns a band of output rows)
   float2 g_wa[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};    // warps 0-7: dW1[8w+2i, 8w+2i+1][c];
                                                                 // warps 8-11: dWo[8(w-8)+2i, +1][c]
-  float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // warps 0-11: dWin[8w+2i, 8w+2i+1][c]
   float g_vec = 0.f;               // lanes 0-7 of warps 0-7: db1[8w+lane]; of warps 8-11: dbo[8(w-8)+lane]
-  float g_bin = 0.f;               // warps 0-11, lanes 0-7: dbin[8w+lane]
   float g_gam = 0.f, g_bet = 0.f;  // (warp, lane = channel) partial of d(LayerNorm weight / bias)
-  float g_pos[kRowsPerWarp];       // d(positional_encoding)[warp + 13 i][lane]
-#pragma unroll
-  for (int i = 0; i < kRowsPerWarp; ++i) g_pos[i] = 0.f;
 
-  const float inv_e = a.inv_e, inv_a = a.inv_a, inv_f = a.inv_f;
+  const float inv_a = a.inv_a, inv_f = a.inv_f;
   uint32_t phase = 0;
-  AFR_TICK_DECL
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x, phase ^= 1u) {
-    // ---- stage this sample's record: four groups, each waited for right before its first use
+    float* st = a.state + static_cast<long long>(b) * a.sl.stride;
+    // ---- stage this sample's operands: two groups, each waited for right before its first use
     ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
     __syncthreads();
     if (tid == 0) {
-      const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
       const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
       ptx::mbar_arrive_expect_tx(&bars[0], row_bytes + 2u * row_bytes + S4 * 8u + S4 * 4u);
       ptx::bulk_load_1d(s_xhat, st + a.sl.xhat, row_bytes, &bars[0]);
@@ -589,32 +563,17 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
       ptx::bulk_load_1d(sm + o.rstd, st + a.sl.rstd, S4 * 4u, &bars[0]);
       ptx::mbar_arrive_expect_tx(&bars[1], row_bytes);
       ptx::bulk_load_1d(s_ctx, st + a.sl.ctx, row_bytes, &bars[1]);
-      ptx::mbar_arrive_expect_tx(&bars[2], 3u * row_bytes + S * 64u + S * 64u);
-      ptx::bulk_load_1d(s_q, st + a.sl.q, row_bytes, &bars[2]);
-      ptx::bulk_load_1d(s_k, st + a.sl.k, row_bytes, &bars[2]);
-      ptx::bulk_load_1d(s_v, st + a.sl.v, row_bytes, &bars[2]);
-      ptx::bulk_load_1d(s_stat, st + a.sl.stat, S * 64u, &bars[2]);
-      ptx::bulk_load_1d(sm + o.abits, st + a.sl.abits, S * 64u, &bars[2]);
-      ptx::mbar_arrive_expect_tx(&bars[3], row_bytes + S4 * 4u);
-      ptx::bulk_load_1d(s_e, st + a.sl.e, row_bytes, &bars[3]);
-      ptx::bulk_load_1d(sm + o.ebits, st + a.sl.ebits, S4 * 4u, &bars[3]);
     }
-    if (tid < S) {
-      long long t = a.tokens[static_cast<long long>(b) * a.token_stride + tid];
-      if (t < 0 || t >= a.vocab) t = 0;
-      s_tok[tid] = static_cast<int>(t);
-    }
-    AFR_TICK(0);
 
     // ---- B1: df = dfeat * ReLU' * dropout ; dh = df W1 ; LayerNorm backward -> dr ; h --------
     ptx::mbar_wait(&bars[0], phase);
-    AFR_TICK(1);
     {
       float2 w1c[kF / 2];   // column `lane` of W1, packed along the feature index
 #pragma unroll
       for (int j = 0; j < kF / 2; ++j)
         w1c[j] = f2(sm[o.w1 + (2 * j) * kLdW + lane], sm[o.w1 + (2 * j + 1) * kLdW + lane]);
       const float gam = sm[o.lnw + lane], bet = a.w.lnb[lane];
+      float* g_dr = st + a.sl.dr;
       // two rows per iteration: their dependent chains (LDS -> FFMA2 chain -> butterflies) interleave
       for (int s0 = warp; s0 < S; s0 += 2 * kWarps) {
         const int s1 = s0 + kWarps;
@@ -659,23 +618,28 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
         float m1a = dhg_a, m2a = dhg_a * xh_a, m1b = dhg_b, m2b = dhg_b * xh_b;
         warp_sum2(m1a, m2a);
         warp_sum2(m1b, m2b);
-        s_dr[s0 * kE + lane] = rs_a * (dhg_a - m1a * (1.f / kE) - xh_a * (m2a * (1.f / kE)));
+        const float dr_a = rs_a * (dhg_a - m1a * (1.f / kE) - xh_a * (m2a * (1.f / kE)));
+        s_dr[s0 * kE + lane] = dr_a;
+        g_dr[s0 * kE + lane] = dr_a;                     // for K3
         s_xhat[s0 * kE + lane] = fmaf(xh_a, gam, bet);   // h, for dW1
         if (two) {
-          s_dr[s1 * kE + lane] = rs_b * (dhg_b - m1b * (1.f / kE) - xh_b * (m2b * (1.f / kE)));
+          const float dr_b = rs_b * (dhg_b - m1b * (1.f / kE) - xh_b * (m2b * (1.f / kE)));
+          s_dr[s1 * kE + lane] = dr_b;
+          g_dr[s1 * kE + lane] = dr_b;
           s_xhat[s1 * kE + lane] = fmaf(xh_b, gam, bet);
         }
       }
     }
-    // ---- B1b: dctx = dr Wo and D = dctx . ctx for the rows this warp just produced --------------
+    // ---- B1b: dctx = dr Wo and D = dctx . ctx for the rows this warp just produced (for K2) -----
     ptx::mbar_wait(&bars[1], phase);   // ctx
-    ptx::mbar_wait(&bars[2], phase);   // s_stat's (m, 1/l) arrive by bulk copy; D joins them below
     __syncwarp();
     {
       float2 woc[kE / 2];   // column `lane` of Wo, packed along the output channel
 #pragma unroll
       for (int c = 0; c < kE / 2; ++c)
         woc[c] = f2(sm[o.wo + (2 * c) * kLdW + lane], sm[o.wo + (2 * c + 1) * kLdW + lane]);
+      float* g_dc = st + a.sl.dctx;
+      float* g_stat = st + a.sl.stat;
       for (int s0 = warp; s0 < S; s0 += 2 * kWarps) {
         const int s1 = s0 + kWarps;
         const bool two = s1 < S;
@@ -699,23 +663,20 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
           pa += qa;
           pb += qb;
         }
-        s_dctx[s0 * kE + lane] = dca;
-        if ((lane & 7) == 0) s_stat[(s0 * kHeads + (lane >> 3)) * 4 + 2] = pa;
+        g_dc[s0 * kE + lane] = dca * inv_a;    // d(P_dropped) = d(ctx) V^T carries 1 / (1 - p)
+        if ((lane & 7) == 0) g_stat[(s0 * kHeads + (lane >> 3)) * 4 + 2] = pa;
         if (two) {
-          s_dctx[s1 * kE + lane] = dcb;
-          if ((lane & 7) == 0) s_stat[(s1 * kHeads + (lane >> 3)) * 4 + 2] = pb;
+          g_dc[s1 * kE + lane] = dcb * inv_a;
+          if ((lane & 7) == 0) g_stat[(s1 * kHeads + (lane >> 3)) * 4 + 2] = pb;
         }
       }
     }
-    AFR_TICK(2);
     __syncthreads();
-    AFR_TICK(3);
 
     // ---- B2: dW1, db1 (warps 0-7) | dWo, dbo (warps 8-11) --------------------------------------
     // lane = input channel c; a warp owns 8 output rows: per position one conflict-free scalar
     // load of the lane's own operand and warp-uniform LDS.128 of the row operand (1 clock each;
     // any non-uniform LDS.128 costs 4).
-    AFR_TICK(4);
     if (warp < 8) {
       const float* dfw = s_df + 8 * warp;
       float sum_b = 0.f;                  // lanes 0-7: db1[8w + lane]
@@ -745,99 +706,354 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
       }
       g_vec += sum_b;
     }
-    AFR_TICK(5);
-    __syncthreads();
-    AFR_TICK(6);
+  }
+  __syncthreads();
 
-    // ---- B3: attention backward ---------------------------------------------------------------
-    ptx::mbar_wait(&bars[2], phase);
-    AFR_TICK(7);
-    // pass A: thread = (query s, head h), stream over keys -> dq
-    for (int i = tid; i < S * kHeads; i += kThreads) {
-      int h, s;
-      slot_to_pair(i, S, h, s);
-      float2 q2[4], dc2[4];
-      {
-        const float4 q0 = lds4(s_q + s * kE + h * kDh), q1 = lds4(s_q + s * kE + h * kDh + 4);
-        q2[0] = f2(q0.x, q0.y); q2[1] = f2(q0.z, q0.w); q2[2] = f2(q1.x, q1.y); q2[3] = f2(q1.z, q1.w);
-        const float4 c0 = lds4(s_dctx + s * kE + h * kDh), c1 = lds4(s_dctx + s * kE + h * kDh + 4);
-        dc2[0] = f2(c0.x * inv_a, c0.y * inv_a); dc2[1] = f2(c0.z * inv_a, c0.w * inv_a);
-        dc2[2] = f2(c1.x * inv_a, c1.y * inv_a); dc2[3] = f2(c1.z * inv_a, c1.w * inv_a);
-      }
-      const float4 stt = lds4(s_stat + (s * kHeads + h) * 4);   // m, 1/l, D
-      const uint4 bw = *reinterpret_cast<const uint4*>(s_abits + (h * S + s) * 4);
-      float2 acc[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
-      const float* kh = s_k + h * kDh;
-      const float* vh = s_v + h * kDh;
+  // ---- flush this CTA's partial sums ------------------------------------------------------
+  sm[o.red + warp * kE + lane] = g_gam;
+  sm[o.red + (kWarps + warp) * kE + lane] = g_bet;
+  __syncthreads();
+  if (tid < 2 * kE) {
+    const int which = tid >> 5, c = tid & 31;
+    float acc = 0.f;
+    for (int w = 0; w < kWarps; ++w) acc += sm[o.red + (which * kWarps + w) * kE + c];
+    part[(which == 0 ? a.lay.off_lnw : a.lay.off_lnb) + c] = acc;
+  }
+  if (warp < 8) {
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t word = w == 0 ? bw.x : w == 1 ? bw.y : w == 2 ? bw.z : bw.w;
-        const int t_end = min(S, 32 * w + 32);
-#pragma unroll 4
-        for (int t = 32 * w; t < t_end; ++t) {
-          const float4 k0 = lds4(kh + t * kE), k1 = lds4(kh + t * kE + 4);
-          const float4 v0 = lds4(vh + t * kE), v1 = lds4(vh + t * kE + 4);
-          const float p = ex2(dot8(q2, k0, k1) - stt.x) * stt.y;
-          const float dp = dot8(dc2, v0, v1);                   // already carries 1/(1-p_drop)
-          const float ds = p * ((((word >> (t & 31)) & 1u) ? dp : 0.f) - stt.z);
-          axpy8(acc, ds, k0, k1);
+    for (int i = 0; i < 4; ++i) {
+      part[a.lay.off_w1 + (8 * warp + 2 * i) * kE + lane] = g_wa[i].x;
+      part[a.lay.off_w1 + (8 * warp + 2 * i + 1) * kE + lane] = g_wa[i].y;
+    }
+    if (lane < 8) part[a.lay.off_b1 + 8 * warp + lane] = g_vec;
+  } else if (warp < 12) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i) * kE + lane] = g_wa[i].x;
+      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i + 1) * kE + lane] = g_wa[i].y;
+    }
+    if (lane < 8) part[a.lay.off_bo + 8 * (warp - 8) + lane] = g_vec;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) frontend_backward_head_kernel(const FrontArgs a) {
+  frontend_backward_head_body(a);
+}
+// Register-capped variants of the backward kernels (a few spills): 13 warps of 128 registers fill
+// one scheduler partition's 16 K registers and no warp of another kernel fits beside them; capped,
+// the background AdamW sweep (afr_adamw_rows_bg, 4 warps x 40 registers) shares the SM.
+__global__ void __maxnreg__(112) frontend_backward_head_kernel_shared(const FrontArgs a) {
+  frontend_backward_head_body(a);
+}
+
+// ---------------------------------------------------------------- K2: attention backward
+// Per (sample, head): P = softmax(q k^T) recomputed from the forward's row statistics,
+//   dP = d(ctx) V^T / (1-p),  dS = P o (keep ? dP : 0  -  D),  dq = dS k,  dk = dS^T q,  dv = (P o keep)^T d(ctx) / (1-p)
+// on mma.sync.m16n8k8 TF32 with every product as three MMAs (hi/lo split of both operands,
+// ptx::mma_3xtf32: fp32-equivalent, the 5e-5 gradient tolerance holds). head_dim = 8 is exactly one
+// k-step. A warp owns a (head, 16-row tile): pass 1 (rows = queries) walks the key tiles and
+// accumulates dq; pass 2 (rows = keys) walks the query tiles and accumulates dk, dv. The 16 x 8
+// tile of dS / P comes out of the score MMA in the accumulator layout and goes back in as the A
+// operand of the next MMA by renaming the k index (k = t <-> column 2t, k = t+4 <-> column 2t+1;
+// the B fragment reads rows 2t, 2t+1 to match): no shuffle, no shared-memory round trip.
+// Operands sit in shared memory as fp32 rows of kE + 4 floats (every fragment load hits 32
+// distinct banks), staged with cp.async; rows / statistics beyond S are zero, which makes the
+// padding of the last tiles inert (P = 0 there). Nothing is written to shared memory after the
+// staging, so the two passes need no barrier between them.
+constexpr int kAttWarps = 14;
+constexpr int kAttThreads = kAttWarps * 32;
+constexpr int kLdA = kE + 4;
+
+struct AttSmem {
+  int q, k, v, d, stat, abits, rows, total;
+};
+__host__ __device__ inline AttSmem make_att_smem(int L) {
+  AttSmem s{};
+  s.rows = (L + 15) & ~15;
+  int o = 0;
+  s.q = o; o += s.rows * kLdA;
+  s.k = o; o += s.rows * kLdA;
+  s.v = o; o += s.rows * kLdA;
+  s.d = o; o += s.rows * kLdA;
+  s.stat = o; o += kHeads * 3 * s.rows;   // [head][m | 1/l | D][row]
+  s.abits = o; o += kHeads * L * 4;
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ void frontend_backward_attn_body(const FrontArgs& a) {
+  extern __shared__ __align__(16) float sm[];
+  const AttSmem o = make_att_smem(a.L);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int S = a.S, RP = o.rows;
+  float* sq = sm + o.q;
+  float* sk = sm + o.k;
+  float* sv = sm + o.v;
+  float* sd = sm + o.d;
+  float* sst = sm + o.stat;
+  uint32_t* sab = reinterpret_cast<uint32_t*>(sm + o.abits);
+  for (int i = tid; i < o.abits; i += kAttThreads) sm[i] = 0.f;   // padding rows / statistics stay zero
+  __syncthreads();
+
+  const int nmt = (S + 15) >> 4, nt8 = (S + 7) >> 3, units = nmt * kHeads;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    float* st = a.state + static_cast<long long>(b) * a.sl.stride;
+    for (int i = tid; i < S * 8; i += kAttThreads) {
+      const int row = i >> 3, c4 = (i & 7) * 4;
+      const int dst = row * kLdA + c4, src = row * kE + c4;
+      ptx::cp_async_16(ptx::smem_u32(sq + dst), st + a.sl.q + src);
+      ptx::cp_async_16(ptx::smem_u32(sk + dst), st + a.sl.k + src);
+      ptx::cp_async_16(ptx::smem_u32(sv + dst), st + a.sl.v + src);
+      ptx::cp_async_16(ptx::smem_u32(sd + dst), st + a.sl.dctx + src);
+    }
+    for (int i = tid; i < kHeads * S; i += kAttThreads)
+      ptx::cp_async_16(ptx::smem_u32(sab + 4 * i), st + a.sl.abits + 4 * i);
+    ptx::cp_async_commit();
+    for (int i = tid; i < S * kHeads; i += kAttThreads) {
+      const float4 x = *reinterpret_cast<const float4*>(st + a.sl.stat + 4 * i);   // (m, 1/l, D, -)
+      const int s = i >> 2, h = i & 3;
+      sst[(h * 3 + 0) * RP + s] = x.x;
+      sst[(h * 3 + 1) * RP + s] = x.y;
+      sst[(h * 3 + 2) * RP + s] = x.z;
+    }
+    ptx::cp_async_wait_all();
+    __syncthreads();
+
+    for (int u = warp; u < 2 * units; u += kAttWarps) {
+      const bool pass1 = u < units;
+      const int uu = pass1 ? u : u - units;
+      const int h = uu & 3, mt = uu >> 2, hc = kDh * h;
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      const float* sth = sst + h * 3 * RP;
+      if (pass1) {
+        // ---- rows = queries r0, r1; stream over key tiles -> dq
+        uint32_t qh[4], ql[4], dh[4], dl[4];
+        {
+          ptx::split_tf32(sq[r0 * kLdA + hc + t], qh[0], ql[0]);
+          ptx::split_tf32(sq[r1 * kLdA + hc + t], qh[1], ql[1]);
+          ptx::split_tf32(sq[r0 * kLdA + hc + t + 4], qh[2], ql[2]);
+          ptx::split_tf32(sq[r1 * kLdA + hc + t + 4], qh[3], ql[3]);
+          ptx::split_tf32(sd[r0 * kLdA + hc + t], dh[0], dl[0]);
+          ptx::split_tf32(sd[r1 * kLdA + hc + t], dh[1], dl[1]);
+          ptx::split_tf32(sd[r0 * kLdA + hc + t + 4], dh[2], dl[2]);
+          ptx::split_tf32(sd[r1 * kLdA + hc + t + 4], dh[3], dl[3]);
+        }
+        const float m0 = sth[r0], m1 = sth[r1], l0 = sth[RP + r0], l1 = sth[RP + r1];
+        const float D0 = sth[2 * RP + r0], D1 = sth[2 * RP + r1];
+        const uint32_t* bp0 = sab + (h * S + min(r0, S - 1)) * 4;
+        const uint32_t* bp1 = sab + (h * S + min(r1, S - 1)) * 4;
+        float dq[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; 32 * w < S; ++w) {
+          const uint32_t w0 = bp0[w] >> (2 * t), w1 = bp1[w] >> (2 * t);   // this lane's key pair, tile 0
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int j = 4 * w + j4;
+            if (8 * j < S) {   // warp-uniform
+              uint32_t bh0, bh1, bl0, bl1;
+              const float* kr = sk + (8 * j + g) * kLdA + hc + t;
+              ptx::split_tf32(kr[0], bh0, bl0);
+              ptx::split_tf32(kr[4], bh1, bl1);
+              float c[4] = {0.f, 0.f, 0.f, 0.f};
+              ptx::mma_3xtf32(c, qh, ql, bh0, bh1, bl0, bl1);        // scores (log2 domain)
+              const float* vr = sv + (8 * j + g) * kLdA + hc + t;
+              ptx::split_tf32(vr[0], bh0, bl0);
+              ptx::split_tf32(vr[4], bh1, bl1);
+              float e[4] = {0.f, 0.f, 0.f, 0.f};
+              ptx::mma_3xtf32(e, dh, dl, bh0, bh1, bl0, bl1);        // dP
+              const uint32_t k0 = w0 >> (8 * j4), k1 = w1 >> (8 * j4);
+              const float p0 = ex2(c[0] - m0) * l0, p1 = ex2(c[1] - m0) * l0;
+              const float p2 = ex2(c[2] - m1) * l1, p3 = ex2(c[3] - m1) * l1;
+              float ds0 = p0 * (((k0 & 1u) ? e[0] : 0.f) - D0);
+              float ds1 = p1 * (((k0 & 2u) ? e[1] : 0.f) - D0);
+              float ds2 = p2 * (((k1 & 1u) ? e[2] : 0.f) - D1);
+              float ds3 = p3 * (((k1 & 2u) ? e[3] : 0.f) - D1);
+              if (8 * j + 8 > S) {   // keys beyond S in the last tile
+                const int key = 8 * j + 2 * t;
+                if (key >= S) { ds0 = 0.f; ds2 = 0.f; }
+                if (key + 1 >= S) { ds1 = 0.f; ds3 = 0.f; }
+              }
+              uint32_t ah[4], al[4];
+              ptx::split_tf32(ds0, ah[0], al[0]);
+              ptx::split_tf32(ds2, ah[1], al[1]);
+              ptx::split_tf32(ds1, ah[2], al[2]);
+              ptx::split_tf32(ds3, ah[3], al[3]);
+              const float* kt = sk + (8 * j + 2 * t) * kLdA + hc + g;
+              ptx::split_tf32(kt[0], bh0, bl0);
+              ptx::split_tf32(kt[kLdA], bh1, bl1);
+              ptx::mma_3xtf32(dq, ah, al, bh0, bh1, bl0, bl1);       // dq += dS k
+            }
+          }
+        }
+        // d(q) of the unscaled projection: d(score) * k / sqrt(head_dim)
+        float* gq = st + a.sl.dq + hc + 2 * t;
+        if (r0 < S) *reinterpret_cast<float2*>(gq + r0 * kE) = make_float2(dq[0] * kInvSqrtDh, dq[1] * kInvSqrtDh);
+        if (r1 < S) *reinterpret_cast<float2*>(gq + r1 * kE) = make_float2(dq[2] * kInvSqrtDh, dq[3] * kInvSqrtDh);
+      } else {
+        // ---- rows = keys r0, r1; stream over query tiles -> dk, dv
+        uint32_t kh[4], kl[4], vh[4], vl[4];
+        ptx::split_tf32(sk[r0 * kLdA + hc + t], kh[0], kl[0]);
+        ptx::split_tf32(sk[r1 * kLdA + hc + t], kh[1], kl[1]);
+        ptx::split_tf32(sk[r0 * kLdA + hc + t + 4], kh[2], kl[2]);
+        ptx::split_tf32(sk[r1 * kLdA + hc + t + 4], kh[3], kl[3]);
+        ptx::split_tf32(sv[r0 * kLdA + hc + t], vh[0], vl[0]);
+        ptx::split_tf32(sv[r1 * kLdA + hc + t], vh[1], vl[1]);
+        ptx::split_tf32(sv[r0 * kLdA + hc + t + 4], vh[2], vl[2]);
+        ptx::split_tf32(sv[r1 * kLdA + hc + t + 4], vh[3], vl[3]);
+        float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+        const int wsel = mt >> 1, sh0 = 16 * (mt & 1) + g;   // key r0 = bit sh0, key r1 = bit sh0 + 8 of word wsel
+#pragma unroll 2
+        for (int j = 0; j < nt8; ++j) {
+          uint32_t bh0, bh1, bl0, bl1;
+          const float* qr = sq + (8 * j + g) * kLdA + hc + t;
+          ptx::split_tf32(qr[0], bh0, bl0);
+          ptx::split_tf32(qr[4], bh1, bl1);
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          ptx::mma_3xtf32(c, kh, kl, bh0, bh1, bl0, bl1);            // scores^T
+          const float* dr = sd + (8 * j + g) * kLdA + hc + t;
+          ptx::split_tf32(dr[0], bh0, bl0);
+          ptx::split_tf32(dr[4], bh1, bl1);
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+          ptx::mma_3xtf32(e, vh, vl, bh0, bh1, bl0, bl1);            // dP^T
+          const int q0 = 8 * j + 2 * t;                              // this lane's query pair
+          const float2 mm = *reinterpret_cast<const float2*>(sth + q0);
+          const float2 ll = *reinterpret_cast<const float2*>(sth + RP + q0);
+          const float2 DD = *reinterpret_cast<const float2*>(sth + 2 * RP + q0);
+          const uint32_t ba = sab[(h * S + min(q0, S - 1)) * 4 + wsel] >> sh0;
+          const uint32_t bb = sab[(h * S + min(q0 + 1, S - 1)) * 4 + wsel] >> sh0;
+          const float p0 = ex2(c[0] - mm.x) * ll.x, p1 = ex2(c[1] - mm.y) * ll.y;
+          const float p2 = ex2(c[2] - mm.x) * ll.x, p3 = ex2(c[3] - mm.y) * ll.y;
+          const bool e0 = ba & 1u, e1 = bb & 1u, e2 = ba & 0x100u, e3 = bb & 0x100u;
+          const float ds0 = p0 * ((e0 ? e[0] : 0.f) - DD.x), ds1 = p1 * ((e1 ? e[1] : 0.f) - DD.y);
+          const float ds2 = p2 * ((e2 ? e[2] : 0.f) - DD.x), ds3 = p3 * ((e3 ? e[3] : 0.f) - DD.y);
+          uint32_t ah[4], al[4];
+          ptx::split_tf32(ds0, ah[0], al[0]);
+          ptx::split_tf32(ds2, ah[1], al[1]);
+          ptx::split_tf32(ds1, ah[2], al[2]);
+          ptx::split_tf32(ds3, ah[3], al[3]);
+          const float* qt = sq + (8 * j + 2 * t) * kLdA + hc + g;
+          ptx::split_tf32(qt[0], bh0, bl0);
+          ptx::split_tf32(qt[kLdA], bh1, bl1);
+          ptx::mma_3xtf32(dk, ah, al, bh0, bh1, bl0, bl1);           // dk += dS^T q
+          ptx::split_tf32(e0 ? p0 : 0.f, ah[0], al[0]);
+          ptx::split_tf32(e2 ? p2 : 0.f, ah[1], al[1]);
+          ptx::split_tf32(e1 ? p1 : 0.f, ah[2], al[2]);
+          ptx::split_tf32(e3 ? p3 : 0.f, ah[3], al[3]);
+          const float* dt = sd + (8 * j + 2 * t) * kLdA + hc + g;
+          ptx::split_tf32(dt[0], bh0, bl0);
+          ptx::split_tf32(dt[kLdA], bh1, bl1);
+          ptx::mma_3xtf32(dv, ah, al, bh0, bh1, bl0, bl1);           // dv += (P o keep)^T d(ctx)/(1-p)
+        }
+        // the stored q carries log2(e)/sqrt(head_dim): d(k) = sum ds * q / sqrt(head_dim)
+        float* gk = st + a.sl.dk + hc + 2 * t;
+        float* gv = st + a.sl.dv + hc + 2 * t;
+        if (r0 < S) {
+          *reinterpret_cast<float2*>(gk + r0 * kE) = make_float2(dk[0] * kLn2, dk[1] * kLn2);
+          *reinterpret_cast<float2*>(gv + r0 * kE) = make_float2(dv[0], dv[1]);
+        }
+        if (r1 < S) {
+          *reinterpret_cast<float2*>(gk + r1 * kE) = make_float2(dk[2] * kLn2, dk[3] * kLn2);
+          *reinterpret_cast<float2*>(gv + r1 * kE) = make_float2(dv[2], dv[3]);
         }
       }
-      // d(q) of the unscaled projection: d(score) * k / sqrt(head_dim)
-      *reinterpret_cast<float4*>(s_dq + s * kE + h * kDh) = make_float4(
-          acc[0].x * kInvSqrtDh, acc[0].y * kInvSqrtDh, acc[1].x * kInvSqrtDh, acc[1].y * kInvSqrtDh);
-      *reinterpret_cast<float4*>(s_dq + s * kE + h * kDh + 4) = make_float4(
-          acc[2].x * kInvSqrtDh, acc[2].y * kInvSqrtDh, acc[3].x * kInvSqrtDh, acc[3].y * kInvSqrtDh);
     }
-    AFR_TICK(8);
-    // pass B: thread = (key t, head h), stream over queries -> dk, dv
-    for (int i = tid; i < S * kHeads; i += kThreads) {
-      int h, t;
-      slot_to_pair(i, S, h, t);
-      float2 k2[4], v2[4];
-      {
-        const float4 k0 = lds4(s_k + t * kE + h * kDh), k1 = lds4(s_k + t * kE + h * kDh + 4);
-        k2[0] = f2(k0.x, k0.y); k2[1] = f2(k0.z, k0.w); k2[2] = f2(k1.x, k1.y); k2[3] = f2(k1.z, k1.w);
-        const float4 v0 = lds4(s_v + t * kE + h * kDh), v1 = lds4(s_v + t * kE + h * kDh + 4);
-        v2[0] = f2(v0.x * inv_a, v0.y * inv_a); v2[1] = f2(v0.z * inv_a, v0.w * inv_a);
-        v2[2] = f2(v1.x * inv_a, v1.y * inv_a); v2[3] = f2(v1.z * inv_a, v1.w * inv_a);
-      }
-      float2 ak[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
-      float2 av[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
-      const float* qh = s_q + h * kDh;
-      const float* ch = s_dctx + h * kDh;
-      const uint32_t* bh = s_abits + h * S * 4 + (t >> 5);
-      const int sh = t & 31;
-#pragma unroll 4
-      for (int s = 0; s < S; ++s) {
-        const float4 q0 = lds4(qh + s * kE), q1 = lds4(qh + s * kE + 4);
-        const float4 c0 = lds4(ch + s * kE), c1 = lds4(ch + s * kE + 4);
-        const float4 stt = lds4(s_stat + (s * kHeads + h) * 4);
-        const bool keep = (bh[s * 4] >> sh) & 1u;
-        const float p = ex2(dot8(k2, q0, q1) - stt.x) * stt.y;
-        const float dp = dot8(v2, c0, c1);
-        const float pk = keep ? p : 0.f;
-        const float ds = p * ((keep ? dp : 0.f) - stt.z);
-        axpy8(av, pk, c0, c1);
-        axpy8(ak, ds, q0, q1);
-      }
-      // the stored q carries log2(e)/sqrt(head_dim): d(k) = sum ds * q / sqrt(head_dim)
-      *reinterpret_cast<float4*>(s_dk + t * kE + h * kDh) =
-          make_float4(ak[0].x * kLn2, ak[0].y * kLn2, ak[1].x * kLn2, ak[1].y * kLn2);
-      *reinterpret_cast<float4*>(s_dk + t * kE + h * kDh + 4) =
-          make_float4(ak[2].x * kLn2, ak[2].y * kLn2, ak[3].x * kLn2, ak[3].y * kLn2);
-      *reinterpret_cast<float4*>(s_dv + t * kE + h * kDh) =
-          make_float4(av[0].x * inv_a, av[0].y * inv_a, av[1].x * inv_a, av[1].y * inv_a);
-      *reinterpret_cast<float4*>(s_dv + t * kE + h * kDh + 4) =
-          make_float4(av[2].x * inv_a, av[2].y * inv_a, av[3].x * inv_a, av[3].y * inv_a);
-    }
-    AFR_TICK(9);
+    __syncthreads();   // every warp is done with this sample's operands
+  }
+}
+
+__global__ void __launch_bounds__(kAttThreads, 2) frontend_backward_attn_kernel(const FrontArgs a) {
+  frontend_backward_attn_body(a);
+}
+__global__ void __maxnreg__(64) frontend_backward_attn_kernel_shared(const FrontArgs a) {
+  frontend_backward_attn_body(a);
+}
+
+// ---------------------------------------------------------------- K3: tail of the backward
+struct TailSmem {
+  int win, dq, dk, dv, e, dr, ebits, tok, hist, fonth, bars, total;
+};
+__host__ __device__ inline TailSmem make_tail_smem(int L, int vocab) {
+  const int L4 = (L + 3) & ~3;
+  TailSmem s{};
+  int o = 0;
+  s.win = o; o += 3 * kE * kLdW;
+  o = (o + 3) & ~3;
+  s.dq = o;  o += L * kE;
+  s.dk = o;  o += L * kE;
+  s.dv = o;  o += L * kE;
+  s.e = o;   o += L * kE;
+  s.dr = o;  o += L * kE;         // d(residual) -> d(embedding rows) (B4)
+  s.ebits = o; o += L4;
+  s.tok = o;  o += L4;
+  s.hist = o; o += vocab <= kEmbSmemMaxVocab ? vocab * kE : 0;
+  s.fonth = o; o += kMaxFonts * kE;   // d(font_embedding) of this CTA's samples
+  o = (o + 3) & ~3;
+  s.bars = o; o += 4;                // 2 mbarriers
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) {
+  extern __shared__ __align__(16) float sm[];
+  const TailSmem o = make_tail_smem(a.L, a.vocab);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, S4 = (S + 3) & ~3;
+  const bool hist_smem = a.vocab <= kEmbSmemMaxVocab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o.bars);
+  float* part = a.partials + static_cast<long long>(blockIdx.x) * a.lay.total;
+
+  load_matrix(a.w.win, sm + o.win, 3 * kE);
+  if (hist_smem) {
+    for (int i = tid; i < a.vocab * kE; i += kThreads) sm[o.hist + i] = 0.f;
+  } else {
+    for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = 0.f;
+  }
+  for (int i = tid; i < kMaxFonts * kE; i += kThreads) sm[o.fonth + i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  float* s_dq = sm + o.dq;
+  float* s_dk = sm + o.dk;
+  float* s_dv = sm + o.dv;
+  float* s_e = sm + o.e;
+  float* s_dr = sm + o.dr;
+  const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + o.ebits);
+  int* s_tok = reinterpret_cast<int*>(sm + o.tok);
+
+  float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // warps 0-11: dWin[8w+2i, 8w+2i+1][c]
+  float g_bin = 0.f;               // warps 0-11, lanes 0-7: dbin[8w+lane]
+  float g_pos[kRowsPerWarp];       // d(positional_encoding)[warp + 13 i][lane]
+#pragma unroll
+  for (int i = 0; i < kRowsPerWarp; ++i) g_pos[i] = 0.f;
+
+  const float inv_e = a.inv_e;
+  uint32_t phase = 0;
+
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x, phase ^= 1u) {
+    ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
     __syncthreads();
-    AFR_TICK(10);
+    if (tid == 0) {
+      const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
+      const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
+      ptx::mbar_arrive_expect_tx(&bars[0], 4u * row_bytes + S4 * 4u);
+      ptx::bulk_load_1d(s_dq, st + a.sl.dq, row_bytes, &bars[0]);
+      ptx::bulk_load_1d(s_dk, st + a.sl.dk, row_bytes, &bars[0]);
+      ptx::bulk_load_1d(s_dv, st + a.sl.dv, row_bytes, &bars[0]);
+      ptx::bulk_load_1d(s_dr, st + a.sl.dr, row_bytes, &bars[0]);
+      ptx::bulk_load_1d(sm + o.ebits, st + a.sl.ebits, S4 * 4u, &bars[0]);
+      ptx::mbar_arrive_expect_tx(&bars[1], row_bytes);
+      ptx::bulk_load_1d(s_e, st + a.sl.e, row_bytes, &bars[1]);
+    }
+    if (tid < S) {
+      long long t = a.tokens[static_cast<long long>(b) * a.token_stride + tid];
+      if (t < 0 || t >= a.vocab) t = 0;
+      s_tok[tid] = static_cast<int>(t);
+    }
 
     // ---- B4: de = dr + [dq dk dv] Win ; dPos ; d(embedding rows) ------------------------------
-    ptx::mbar_wait(&bars[3], phase);
-    AFR_TICK(11);
+    ptx::mbar_wait(&bars[0], phase);
     {
       float de[kRowsPerWarp];
 #pragma unroll
@@ -875,11 +1091,10 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
         }
       }
     }
-    AFR_TICK(12);
     __syncthreads();
-    AFR_TICK(13);
 
     // ---- B5: dWin (warps 0-11) | dbin, embedding scatter-add (warp 12) ------------------------
+    ptx::mbar_wait(&bars[1], phase);
     if (warp < 12) {
       // lane = input channel c; this warp owns rows [8w, 8w+8) of dWin (q | k | v blocks of 32)
       const float* src = (warp < 4 ? s_dq : (warp < 8 ? s_dk : s_dv)) + 8 * (warp & 3);
@@ -928,37 +1143,10 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
       }
       if (a.font.ids != nullptr) sm[o.fonth + a.font.ids[b] * kE + lane] += fsum;   // one writer per (font, lane)
     }
-    AFR_TICK(14);
   }
   __syncthreads();
-  AFR_TICK(15);
-  AFR_TICK_FLUSH(1);
 
   // ---- flush this CTA's partial sums ------------------------------------------------------
-  sm[o.red + warp * kE + lane] = g_gam;
-  sm[o.red + (kWarps + warp) * kE + lane] = g_bet;
-  __syncthreads();
-  if (tid < 2 * kE) {
-    const int which = tid >> 5, c = tid & 31;
-    float acc = 0.f;
-    for (int w = 0; w < kWarps; ++w) acc += sm[o.red + (which * kWarps + w) * kE + c];
-    part[(which == 0 ? a.lay.off_lnw : a.lay.off_lnb) + c] = acc;
-  }
-  if (warp < 8) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      part[a.lay.off_w1 + (8 * warp + 2 * i) * kE + lane] = g_wa[i].x;
-      part[a.lay.off_w1 + (8 * warp + 2 * i + 1) * kE + lane] = g_wa[i].y;
-    }
-    if (lane < 8) part[a.lay.off_b1 + 8 * warp + lane] = g_vec;
-  } else if (warp < 12) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i) * kE + lane] = g_wa[i].x;
-      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i + 1) * kE + lane] = g_wa[i].y;
-    }
-    if (lane < 8) part[a.lay.off_bo + 8 * (warp - 8) + lane] = g_vec;
-  }
   if (warp < 12) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -977,15 +1165,11 @@ __device__ __forceinline__ void frontend_backward_body(const FrontArgs& a) {
   for (int i = tid; i < kMaxFonts * kE; i += kThreads) part[a.lay.off_font + i] = sm[o.fonth + i];
 }
 
-__global__ void __launch_bounds__(kThreads, 1) frontend_backward_kernel(const FrontArgs a) {
-  frontend_backward_body(a);
+__global__ void __launch_bounds__(kThreads, 1) frontend_backward_tail_kernel(const FrontArgs a) {
+  frontend_backward_tail_body(a);
 }
-// The same kernel capped at 112 registers (a few spills): with 13 warps of 128 registers one
-// scheduler partition of the SM holds 4 x 4096 = all 16 K of its registers and no warp of another
-// kernel fits beside it; at 112 the background AdamW sweep (afr_adamw_rows_bg, 40 registers) can
-// share the SM with the front-end backward.
-__global__ void __maxnreg__(112) frontend_backward_kernel_shared(const FrontArgs a) {
-  frontend_backward_body(a);
+__global__ void __maxnreg__(112) frontend_backward_tail_kernel_shared(const FrontArgs a) {
+  frontend_backward_tail_body(a);
 }
 
 // grads[i] = sum over CTAs of partials[cta][i], fixed order.
@@ -1066,8 +1250,9 @@ cudaError_t read_phase_cycles(unsigned long long* host, int reset) {
 #endif
 }
 
-size_t frontend_backward_smem_bytes(int L, int vocab) {
-  return static_cast<size_t>(make_bwd_smem(L, vocab).total) * 4;
+size_t frontend_backward_smem_bytes(int L, int vocab) {   // the largest of the three kernels
+  const size_t head = make_head_smem(L).total, att = make_att_smem(L).total, tail = make_tail_smem(L, vocab).total;
+  return (head > tail ? (head > att ? head : att) : (tail > att ? tail : att)) * 4;
 }
 
 cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, long long token_stride,
@@ -1119,23 +1304,45 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
   a.state = const_cast<float*>(state); a.sl.init(L);
   a.err_flag = g_err_flag;
   fill_dropout(a);
-  const size_t smem = frontend_backward_smem_bytes(L, vocab);
-  static size_t configured = 0;
-  if (smem > configured) {
-    for (auto kern : {frontend_backward_kernel, frontend_backward_kernel_shared}) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      if (e != cudaSuccess) return e;
+  const size_t smem_head = static_cast<size_t>(make_head_smem(L).total) * 4;
+  const size_t smem_att = static_cast<size_t>(make_att_smem(L).total) * 4;
+  const size_t smem_tail = static_cast<size_t>(make_tail_smem(L, vocab).total) * 4;
+  static size_t configured[3] = {0, 0, 0};
+  auto configure = [&](int which, size_t smem, std::initializer_list<const void*> kernels) -> cudaError_t {
+    if (smem <= configured[which]) return cudaSuccess;
+    for (const void* kern : kernels) {
+      cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (err != cudaSuccess) return err;
+      err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (err != cudaSuccess) return err;
     }
-    configured = smem;
-  }
+    configured[which] = smem;
+    return cudaSuccess;
+  };
+  if ((e = configure(0, smem_head, {reinterpret_cast<const void*>(frontend_backward_head_kernel),
+                                    reinterpret_cast<const void*>(frontend_backward_head_kernel_shared)})) != cudaSuccess) return e;
+  if ((e = configure(1, smem_att, {reinterpret_cast<const void*>(frontend_backward_attn_kernel),
+                                   reinterpret_cast<const void*>(frontend_backward_attn_kernel_shared)})) != cudaSuccess) return e;
+  if ((e = configure(2, smem_tail, {reinterpret_cast<const void*>(frontend_backward_tail_kernel),
+                                    reinterpret_cast<const void*>(frontend_backward_tail_kernel_shared)})) != cudaSuccess) return e;
   int grid = num_sms;
   if (grid > B) grid = B;
   if (grid > max_grid) grid = max_grid;
-  *grid_out = grid;
-  if (shared_sm) frontend_backward_kernel_shared<<<grid, kThreads, smem, stream>>>(a);
-  else frontend_backward_kernel<<<grid, kThreads, smem, stream>>>(a);
+  *grid_out = grid;     // CTAs of the head / tail kernels = rows of `partials`
+  int grid_att = 2 * num_sms;
+  if (grid_att > B) grid_att = B;
+  // AFR_FE_BWD_ONLY = 1 | 2 | 3 (profiling, tools/fe_contention.py): launch only that kernel
+  const char* only_env = std::getenv("AFR_FE_BWD_ONLY");
+  const int only = only_env != nullptr ? std::atoi(only_env) : 0;
+  if (shared_sm) {
+    if (only == 0 || only == 1) frontend_backward_head_kernel_shared<<<grid, kThreads, smem_head, stream>>>(a);
+    if (only == 0 || only == 2) frontend_backward_attn_kernel_shared<<<grid_att, kAttThreads, smem_att, stream>>>(a);
+    if (only == 0 || only == 3) frontend_backward_tail_kernel_shared<<<grid, kThreads, smem_tail, stream>>>(a);
+  } else {
+    if (only == 0 || only == 1) frontend_backward_head_kernel<<<grid, kThreads, smem_head, stream>>>(a);
+    if (only == 0 || only == 2) frontend_backward_attn_kernel<<<grid_att, kAttThreads, smem_att, stream>>>(a);
+    if (only == 0 || only == 3) frontend_backward_tail_kernel<<<grid, kThreads, smem_tail, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 

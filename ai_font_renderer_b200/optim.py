@@ -18,7 +18,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model: AttentionFontRenderer, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, fuse_wgrad: bool = True,
                  overlap_dgrad: bool = False, background: bool = False, bg_chunks: int = 1,
-                 bg_ctas: int = 0, bg_stages: int = 0, bg_after_dgrad: bool = False):
+                 bg_ctas: int = 0, bg_stages: int = 0, bg_after_dgrad: bool = True):
         if not isinstance(model, AttentionFontRenderer):
             raise TypeError("FusedAdamW is bound to an ai_font_renderer_b200.AttentionFontRenderer")
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):

@@ -121,9 +121,11 @@ import ctypes as _C
 
 _SMALL_GROUP = None
 # ring depth of the background AdamW sweep: stages x 8 KB (+ the 1 KB the hardware reserves per CTA)
-# of every SM's shared memory are left to it by the dgrad GEMM (ring of 5 instead of 6 stages) and
-# fit beside the front-end kernels' 184 / 2 x 78 KB
-BG_DEFAULT_STAGES = 4
+# of every SM's shared memory are left to it; 8 stages fit beside the front-end kernels' 2 x 78 KB
+# (forward), 82 / 2 x 76 / 96 KB (backward). With the sweep starting before the dgrad GEMM
+# (bg_after_dgrad = False) 4 stages are the better trade: the GEMM's operand ring pays for them.
+BG_DEFAULT_STAGES = 8
+BG_DEFAULT_STAGES_BESIDE_DGRAD = 4
 
 
 class PeerLink:
@@ -280,15 +282,16 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
 
     if world == 1 and getattr(optimizer, "background", False):
         # compute stream : wgrad | dgrad GEMM | front-end backward | small AdamW | next front-end fwd
-        # side stream    :         AdamW sweep over fc_output.weight (background kernel: one
-        #                          128-thread CTA per SM beside whatever the compute stream runs)
+        # side stream    :                      AdamW sweep over fc_output.weight (background kernel:
+        #                          one 128-thread CTA per SM beside whatever the compute stream runs)
         # The join is deferred to the next fc_output GEMM, so the next front-end forward runs under
         # the tail of the sweep too. The sweep writes the inactive bf16 copy: dgrad reads the old
         # one. bg_chunks > 1 splits wgrad / sweep into row chunks (the sweep of chunk k starts
         # under wgrad chunk k + 1); measured slower: the wgrad GEMM and the sweep are both
         # HBM-heavy and gain nothing from sharing the GPU (tools/overlap_probe2.py).
         model.join_pending()
-        stages = optimizer.bg_stages or BG_DEFAULT_STAGES
+        after_dgrad = getattr(optimizer, "bg_after_dgrad", True) and max(1, optimizer.bg_chunks) == 1
+        stages = optimizer.bg_stages or (BG_DEFAULT_STAGES if after_dgrad else BG_DEFAULT_STAGES_BESIDE_DGRAD)
         model.set_smem_reserve(stages * 8192 + 1024)
         side = model.side_stream()
         chunks = row_buckets(P, max(1, optimizer.bg_chunks))
@@ -301,10 +304,10 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
                 model.dgrad_gemm()
                 mark("dgrad_gemm_end")
 
-        # bg_after_dgrad: the sweep starts only after the dgrad GEMM (which then keeps its full
-        # operand ring and HBM to itself: 0.17 instead of 0.30 ms) and runs beside the front-end
-        # backward and the NEXT step's front-end forward instead
-        after_dgrad = getattr(optimizer, "bg_after_dgrad", False) and len(chunks) == 1
+        # bg_after_dgrad (default): the sweep starts only after the dgrad GEMM (which then keeps
+        # its full operand ring and HBM to itself: 0.17 instead of 0.30 ms) and runs beside the
+        # front-end backward and the NEXT step's front-end forward. Off: it starts right after
+        # wgrad, beside dgrad (1.42 instead of 1.385 ms per step at B = 1024).
         if after_dgrad:
             model.set_smem_reserve(0)
         for i, (r0, r1) in enumerate(chunks):

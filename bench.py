@@ -369,8 +369,8 @@ def workload_config(n_gpus, step_mode="two-kernel", dp_mode=None):
                         "1024 glyphs per GPU per step (model.py:409)",
             "optimizer": {"fused": "AdamW of fc_output.weight inside the wgrad GEMM epilogue (gradient not materialised)",
                           "background": "AdamW of fc_output.weight as a background sweep (128-thread cp.async ring "
-                                        "CTAs on a second stream, co-resident with dgrad / front-end backward / the "
-                                        "next front-end forward)",
+                                        "CTAs on a second stream, co-resident with the front-end backward and the "
+                                        "next front-end forward; --bg-after-dgrad 0: also with the dgrad GEMM)",
                           "two-kernel": "AdamW sweep kernel over fc_output.weight"}[step_mode],
             "step_mode": step_mode,
             "batch_per_gpu": BATCH_PER_GPU, "global_batch": BATCH_PER_GPU * n_gpus,
@@ -797,6 +797,9 @@ def main():
     phase_ms["forward_gemm"] = fwd_gemm_ms
     phase_ms["dgrad_gemm"] = dgrad_gemm_ms
 
+    from ai_font_renderer_b200 import training as _tr
+    bg_stages_eff = getattr(opt, "bg_stages", 0) or (
+        _tr.BG_DEFAULT_STAGES if getattr(opt, "bg_after_dgrad", True) else _tr.BG_DEFAULT_STAGES_BESIDE_DGRAD)
     # the same sweep alone on the device (nothing else running), for reference
     iso = []
     if world == 1:
@@ -809,7 +812,7 @@ def main():
             if fused:
                 opt.wgrad_step_rows(t_step, 0, P_PIX)   # dZ / features of the last step are still there
             elif step_mode == "background":
-                opt.step_rows_bg(t_step, 0, P_PIX, opt.bg_ctas, opt.bg_stages)
+                opt.step_rows_bg(t_step, 0, P_PIX, opt.bg_ctas, bg_stages_eff)
             else:
                 opt.step_rows(t_step, 0, P_PIX)
             e1.record()
