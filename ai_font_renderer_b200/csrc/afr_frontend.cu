@@ -23,6 +23,7 @@
 //     position order by one warp.
 #include <cstdlib>
 #include <initializer_list>
+#include <type_traits>
 
 #include "afr_internal.h"
 #include "afr_philox.cuh"
@@ -302,7 +303,9 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
       const float* kh = sk + h * kDh;
       const float* vh = sv + h * kDh;
       const int nblk = (S + 7) >> 3;
-      for (int blk = 0; blk < nblk; ++blk) {
+      // full blocks of 8 keys run without the `t < S` selects; only the last block may be partial
+      auto key_block = [&](const int blk, auto tail_tag) {
+        constexpr bool kTail = decltype(tail_tag)::value;
         const int t0 = blk * 8;
         float sc[8];
         float bm = m;
@@ -310,7 +313,7 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
         for (int u = 0; u < 8; ++u) {
           const float4 k0 = lds4(kh + (t0 + u) * kE), k1 = lds4(kh + (t0 + u) * kE + 4);
           const float d = dot8(q2, k0, k1);
-          sc[u] = (t0 + u < S) ? d : -INFINITY;
+          sc[u] = (!kTail || t0 + u < S) ? d : -INFINITY;
           bm = fmaxf(bm, sc[u]);
         }
         const float corr = ex2(m - bm);      // first block: ex2(-inf) = 0 (l and acc are 0 anyway)
@@ -333,11 +336,11 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
           keep8 = 0;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (t0 + u < S && mrow[t0 + u] != 0) keep8 |= 1u << u;
+            if ((!kTail || t0 + u < S) && mrow[t0 + u] != 0) keep8 |= 1u << u;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          if (t0 + u < S) {     // warp-uniform
+          if (!kTail || t0 + u < S) {     // warp-uniform
             const float p = ex2(sc[u] - m);
             l += p;             // the soft-max denominator counts dropped keys too
             const float pk = ((keep8 >> u) & 1u) ? p : 0.f;
@@ -350,7 +353,10 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
           if (gbits != nullptr) gbits[blk >> 2] = bits;
           bits = 0;
         }
-      }
+      };
+      const int nfull = S >> 3;
+      for (int blk = 0; blk < nfull; ++blk) key_block(blk, std::false_type{});
+      if (nfull < nblk) key_block(nfull, std::true_type{});
       const float linv = 1.f / l;
       const float scale = a.inv_a * linv;
       // q of this (s, h) is dead: the context vector takes its place
@@ -428,32 +434,48 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
         }
       }
       __nv_bfloat16* out = a.feats + static_cast<long long>(b) * KF;
+      // Rows in groups of four: a row's 64 keep decisions are 8 Philox blocks (block j = features
+      // 8j .. 8j+7, lane l needs 16-bit words 2(l & 3), 2(l & 3) + 1 of block l >> 2). Lane l draws
+      // block (l & 7) of the group's row (l >> 3) -- 32 distinct blocks per group instead of every
+      // lane drawing its own copy per row -- and the words travel by shuffle.
 #pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) {
-        const int s = warp + kWarps * i;
-        if (s < S) {
-          float fa = fmaxf(acc[i].x, 0.f), fb = fmaxf(acc[i].y, 0.f);   // ReLU
-          bool ka = true, kb = true;
-          if (mode == 1) {
-            const uint4 r = rng.block(2u, static_cast<uint32_t>(s * (kF / 8) + (lane >> 2)));
-            const uint32_t word = word_of(r, lane & 3);
-            ka = (word & 0xFFFFu) >= a.thr_f;
-            kb = (word >> 16) >= a.thr_f;
-          } else if (mode == 2) {
-            const uint8_t* mk = a.drop.mask_fc1 + (static_cast<long long>(b) * S + s) * kF;
-            ka = mk[2 * lane] != 0;
-            kb = mk[2 * lane + 1] != 0;
+      for (int grp = 0; grp < (kRowsPerWarp + 3) / 4; ++grp) {
+        uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+        if (mode == 1) {
+          const int s_mine = warp + kWarps * (4 * grp + (lane >> 3));   // rows >= S: drawn, never used
+          r4 = rng.block(2u, static_cast<uint32_t>(s_mine * (kF / 8) + (lane & 7)));
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int i = 4 * grp + rr;
+          if (i >= kRowsPerWarp) continue;
+          const int s = warp + kWarps * i;
+          if (s < S) {   // warp-uniform
+            float fa = fmaxf(acc[i].x, 0.f), fb = fmaxf(acc[i].y, 0.f);   // ReLU
+            bool ka = true, kb = true;
+            if (mode == 1) {
+              const int src = 8 * rr + (lane >> 2);
+              const uint32_t w0 = __shfl_sync(0xffffffffu, r4.x, src), w1 = __shfl_sync(0xffffffffu, r4.y, src);
+              const uint32_t w2 = __shfl_sync(0xffffffffu, r4.z, src), w3 = __shfl_sync(0xffffffffu, r4.w, src);
+              const uint32_t word = (lane & 2) ? ((lane & 1) ? w3 : w2) : ((lane & 1) ? w1 : w0);
+              ka = (word & 0xFFFFu) >= a.thr_f;
+              kb = (word >> 16) >= a.thr_f;
+            } else if (mode == 2) {
+              const uint8_t* mk = a.drop.mask_fc1 + (static_cast<long long>(b) * S + s) * kF;
+              ka = mk[2 * lane] != 0;
+              kb = mk[2 * lane + 1] != 0;
+            }
+            const bool pa = ka && fa > 0.f, pb = kb && fb > 0.f;
+            fa = ka ? fa * a.inv_f : 0.f;
+            fb = kb ? fb * a.inv_f : 0.f;
+            *reinterpret_cast<__nv_bfloat162*>(out + s * kF + 2 * lane) = __floats2bfloat162_rn(fa, fb);
+            if (a.feats_f32 != nullptr)
+              *reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF + s * kF + 2 * lane) =
+                  make_float2(fa, fb);
+            const uint32_t w0b = __ballot_sync(0xffffffffu, pa), w1b = __ballot_sync(0xffffffffu, pb);
+            if (st != nullptr && lane == 0)
+              *reinterpret_cast<uint2*>(st + a.sl.fbits + 2 * s) = make_uint2(w0b, w1b);
           }
-          const bool pa = ka && fa > 0.f, pb = kb && fb > 0.f;
-          fa = ka ? fa * a.inv_f : 0.f;
-          fb = kb ? fb * a.inv_f : 0.f;
-          *reinterpret_cast<__nv_bfloat162*>(out + s * kF + 2 * lane) = __floats2bfloat162_rn(fa, fb);
-          if (a.feats_f32 != nullptr)
-            *reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF + s * kF + 2 * lane) =
-                make_float2(fa, fb);
-          const uint32_t w0 = __ballot_sync(0xffffffffu, pa), w1 = __ballot_sync(0xffffffffu, pb);
-          if (st != nullptr && lane == 0)
-            *reinterpret_cast<uint2*>(st + a.sl.fbits + 2 * s) = make_uint2(w0, w1);
         }
       }
       // zero features for positions >= S (model.py:190-193)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of the two front-end kernels (profiling build).
+"""Per-phase cycle breakdown of the front-end forward kernel (profiling build; the backward was
+instrumented the same way while it was one kernel: profiles/r02/frontend_phase_cycles_before_split.log).
 
     AFR_EXTRA_NVCC_FLAGS=-DAFR_PHASE_TIMING python tools/phase_timing.py [B]
 
@@ -22,10 +23,6 @@ from ai_font_renderer_b200.renderer import AttentionFontRenderer  # noqa: E402
 
 FWD = ["(loop top)", "1 embed", "  sync", "2 in-proj", "  sync", "3 attention", "  sync", "4a out-proj+LN",
        "4b fc1", "  sync"]
-BWD = ["top sync + issue copies", "wait xhat/dfeat", "B1 df,dh,LN", "  sync", "wait ctx", "B2 dW1,dWo | dctx",
-       "  sync", "wait q,k,v", "B3 pass A (dq)", "B3 pass B (dk,dv)", "  sync", "wait e", "B4 de rows", "  sync",
-       "B5 dWin | dbin,dEmb", "final sync"]
-
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
@@ -44,9 +41,8 @@ def main():
     _lib.check(lib.afr_debug_phase_cycles(buf, 0))
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     mhz = 1965.0
-    for name, labels, ctas in (("frontend_forward_kernel", FWD, min(B, 2 * sms)),
-                               ("frontend_backward_kernel", BWD, min(B, sms))):
-        base = 0 if labels is FWD else 16
+    for name, labels, ctas in (("frontend_forward_kernel", FWD, min(B, 2 * sms)),):
+        base = 0
         vals = [buf[base + k] / (steps * ctas) for k in range(16)]
         tot = sum(vals)
         print(f"{name}: {tot:.0f} cycles per CTA per launch = {tot / mhz:.1f} us at {mhz:.0f} MHz")
