@@ -606,7 +606,10 @@ wide_attention_bwd_mma_kernel(WideDims d, WideDrop dr, const float* __restrict__
   // ---- stage the sample: bf16 (split for q, k), row-major + transposed; zero padding.
   // Four channels per thread and iteration (128-bit global loads, 64-bit row-major stores).
   for (int i = threadIdx.x; i < SP * (E / 4); i += blockDim.x) {
-    const int s = i / (E / 4), c = (i % (E / 4)) * 4;
+    // a warp covers 8 rows x 16 channels: 64 contiguous bytes per row from global, and the
+    // transposed 2-byte stores of 8 consecutive rows share words (2-way conflicts instead of 16-way)
+    const int wi = i >> 5, li = i & 31;
+    const int s = 8 * (wi / (E / 16)) + (li & 7), c = 16 * (wi % (E / 16)) + 4 * (li >> 3);
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv, vv = qv, dv = qv;
     if (s < S) {
       qv = *reinterpret_cast<const float4*>(base + s * 3 * E + c);
@@ -650,8 +653,28 @@ wide_attention_bwd_mma_kernel(WideDims d, WideDrop dr, const float* __restrict__
       stv = stat[(static_cast<long long>(b) * H + h) * S + s];
       const float* cg = dctx + (static_cast<long long>(b) * S + s) * E + h * DH;
       const __nv_bfloat16* cx = ctx16 + (static_cast<long long>(b) * S + s) * 3 * E + h * DH;   // [hi | lo | hi]
+      float4 gv[DH / 4];
+      uint4 hv[DH / 8], lv[DH / 8];     // all loads first: the chain below then waits once, not DH times
 #pragma unroll
-      for (int j = 0; j < DH; ++j) Dv = fmaf(cg[j], __bfloat162float(cx[j]) + __bfloat162float(cx[E + j]), Dv);
+      for (int j = 0; j < DH / 4; ++j) gv[j] = *reinterpret_cast<const float4*>(cg + 4 * j);
+#pragma unroll
+      for (int j = 0; j < DH / 8; ++j) {
+        hv[j] = *reinterpret_cast<const uint4*>(cx + 8 * j);
+        lv[j] = *reinterpret_cast<const uint4*>(cx + E + 8 * j);
+      }
+#pragma unroll
+      for (int j = 0; j < DH / 8; ++j) {
+        const uint32_t hw[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w}, lw[4] = {lv[j].x, lv[j].y, lv[j].z, lv[j].w};
+        const float ga[8] = {gv[2 * j].x, gv[2 * j].y, gv[2 * j].z, gv[2 * j].w,
+                             gv[2 * j + 1].x, gv[2 * j + 1].y, gv[2 * j + 1].z, gv[2 * j + 1].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {     // a bf16 is the upper half of its fp32
+          const float c0 = __uint_as_float(hw[u] << 16) + __uint_as_float(lw[u] << 16);
+          const float c1 = __uint_as_float(hw[u] & 0xffff0000u) + __uint_as_float(lw[u] & 0xffff0000u);
+          Dv = fmaf(ga[2 * u], c0, Dv);
+          Dv = fmaf(ga[2 * u + 1], c1, Dv);
+        }
+      }
     }
     st_s[i] = stv;
     D_s[i] = Dv;
@@ -809,6 +832,234 @@ wide_attention_bwd_mma_kernel(WideDims d, WideDrop dr, const float* __restrict__
         *reinterpret_cast<uint32_t*>(o) = pack2(dk[nt][2] * kLn2, dk[nt][3] * kLn2);
         *reinterpret_cast<uint32_t*>(o + E) = pack2(dvv[nt][2], dvv[nt][3]);
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- attention forward, tensor cores
+// The forward on the same warp-level bf16 MMAs, every product with split operands so that the
+// context keeps the fp32 accuracy the ReLU downstream needs (see wide_ln_fwd_kernel):
+//   scores = q_hi k_hi + q_lo k_hi + q_hi k_lo,   ctx = p_hi v_hi + p_lo v_hi + p_hi v_lo.
+// A warp owns a (head, 16-query tile) and walks the keys 16 at a time: two 16 x 8 score tiles,
+// online soft-max on the accumulator fragments (row max / sum reduced over the four lanes that
+// share a row), P_kept re-packed in registers as the A fragment of the context product (two
+// adjacent 8-column score tiles = one 16-wide k-step), V read from a transposed bf16 copy.
+// The dropout decisions are the SIMT kernel's (one Philox block per row and 8 keys): lane t of a
+// quad draws the block of (row g or g + 8, first or second tile) and its 8 keep bits reach the
+// other three lanes by shuffle. One CTA per sample, q / k (row-major) and v^T as hi / lo bf16 in
+// shared memory: 106 KB at config 4, two CTAs per SM.
+struct AttnFwdSmem {
+  int ldr, ldt, sp;
+  size_t q_hi, q_lo, k_hi, k_lo, vT_hi, vT_lo, total;   // byte offsets
+};
+__host__ __device__ inline AttnFwdSmem attn_fwd_smem(int S, int E) {
+  AttnFwdSmem m{};
+  m.sp = (S + 15) & ~15;
+  m.ldr = E + 8;
+  m.ldt = m.sp + 8;
+  size_t o = 0;
+  const size_t row = static_cast<size_t>(m.sp) * m.ldr * 2, tr = static_cast<size_t>(E) * m.ldt * 2;
+  m.q_hi = o; o += row; m.q_lo = o; o += row; m.k_hi = o; o += row; m.k_lo = o; o += row;
+  m.vT_hi = o; o += tr; m.vT_lo = o; o += tr;
+  m.total = o;
+  return m;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(512, 2)
+wide_attention_fwd_mma_kernel(WideDims d, WideDrop dr, const float* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx16,
+                              float2* __restrict__ stat, uint32_t* __restrict__ abits) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int KK = DH / 16, NT = DH / 8;
+  const int S = d.S, E = d.E, H = d.H, b = blockIdx.x;
+  const AttnFwdSmem L = attn_fwd_smem(S, E);
+  const int SP = L.sp, LDR = L.ldr, LDT = L.ldt;
+  __nv_bfloat16* q_hi = reinterpret_cast<__nv_bfloat16*>(smraw + L.q_hi);
+  __nv_bfloat16* q_lo = reinterpret_cast<__nv_bfloat16*>(smraw + L.q_lo);
+  __nv_bfloat16* k_hi = reinterpret_cast<__nv_bfloat16*>(smraw + L.k_hi);
+  __nv_bfloat16* k_lo = reinterpret_cast<__nv_bfloat16*>(smraw + L.k_lo);
+  __nv_bfloat16* vT_hi = reinterpret_cast<__nv_bfloat16*>(smraw + L.vT_hi);
+  __nv_bfloat16* vT_lo = reinterpret_cast<__nv_bfloat16*>(smraw + L.vT_lo);
+  const float* base = qkv + static_cast<long long>(b) * S * 3 * E;
+  const float qscale = rsqrtf(static_cast<float>(DH)) * kLog2e;
+
+  // ---- stage the sample as split bf16 (rows >= S: zero)
+  for (int i = threadIdx.x; i < SP * (E / 4); i += blockDim.x) {
+    const int wi = i >> 5, li = i & 31;     // a warp covers 8 rows x 16 channels (see the backward kernel)
+    const int s = 8 * (wi / (E / 16)) + (li & 7), c = 16 * (wi % (E / 16)) + 4 * (li >> 3);
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), kv = qv, vv = qv;
+    if (s < S) {
+      qv = *reinterpret_cast<const float4*>(base + s * 3 * E + c);
+      kv = *reinterpret_cast<const float4*>(base + s * 3 * E + E + c);
+      vv = *reinterpret_cast<const float4*>(base + s * 3 * E + 2 * E + c);
+    }
+    const float q4[4] = {qv.x * qscale, qv.y * qscale, qv.z * qscale, qv.w * qscale};
+    const float k4[4] = {kv.x, kv.y, kv.z, kv.w};
+    const float v4[4] = {vv.x, vv.y, vv.z, vv.w};
+    float ql[4], kl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ql[u] = q4[u] - __bfloat162float(__float2bfloat16_rn(q4[u]));
+      kl[u] = k4[u] - __bfloat162float(__float2bfloat16_rn(k4[u]));
+      const __nv_bfloat16 vh = __float2bfloat16_rn(v4[u]);
+      vT_hi[(c + u) * LDT + s] = vh;
+      vT_lo[(c + u) * LDT + s] = __float2bfloat16_rn(v4[u] - __bfloat162float(vh));
+    }
+    auto st4 = [&](__nv_bfloat16* dst, float a0, float a1, float a2, float a3) {
+      *reinterpret_cast<uint2*>(dst + s * LDR + c) = make_uint2(pack2(a0, a1), pack2(a2, a3));
+    };
+    st4(q_hi, q4[0], q4[1], q4[2], q4[3]);
+    st4(q_lo, ql[0], ql[1], ql[2], ql[3]);
+    st4(k_hi, k4[0], k4[1], k4[2], k4[3]);
+    st4(k_lo, kl[0], kl[1], kl[2], kl[3]);
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int tiles = SP >> 4, tasks = H * tiles;
+  const Rng rng = make_rng(dr, b);
+
+  for (int task = warp; task < tasks; task += nwarps) {
+    const int h = task / tiles, i0 = (task % tiles) << 4;
+    const int rA = i0 + g, rB = rA + 8;
+    uint32_t aqh[KK][4], aql[KK][4];
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) {
+      const int c0 = h * DH + kk * 16 + 2 * t;
+      aqh[kk][0] = lds_u32(q_hi + rA * LDR + c0); aqh[kk][1] = lds_u32(q_hi + rB * LDR + c0);
+      aqh[kk][2] = lds_u32(q_hi + rA * LDR + c0 + 8); aqh[kk][3] = lds_u32(q_hi + rB * LDR + c0 + 8);
+      aql[kk][0] = lds_u32(q_lo + rA * LDR + c0); aql[kk][1] = lds_u32(q_lo + rB * LDR + c0);
+      aql[kk][2] = lds_u32(q_lo + rA * LDR + c0 + 8); aql[kk][3] = lds_u32(q_lo + rB * LDR + c0 + 8);
+    }
+    float o[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+    float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;   // l: this lane's share of the row sum
+    uint32_t bitsA = 0, bitsB = 0;
+    // the Philox block this lane draws per 16 keys: row (t odd ? rB : rA), tile (t >> 1)
+    const uint32_t my_row = static_cast<uint32_t>(h * S + min((t & 1) ? rB : rA, S - 1));
+    for (int jj = 0; jj < tiles; ++jj) {
+      float c[2][4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j0 = jj * 16 + half * 8;
+        c[half][0] = c[half][1] = c[half][2] = c[half][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          const int c0 = h * DH + kk * 16 + 2 * t;
+          const uint32_t bh0 = lds_u32(k_hi + (j0 + g) * LDR + c0), bh1 = lds_u32(k_hi + (j0 + g) * LDR + c0 + 8);
+          const uint32_t bl0 = lds_u32(k_lo + (j0 + g) * LDR + c0), bl1 = lds_u32(k_lo + (j0 + g) * LDR + c0 + 8);
+          mma_bf16_16816(c[half], aql[kk], bh0, bh1);
+          mma_bf16_16816(c[half], aqh[kk], bl0, bl1);
+          mma_bf16_16816(c[half], aqh[kk], bh0, bh1);
+        }
+      }
+      if (jj * 16 + 16 > S) {   // keys beyond S in the last block (warp-uniform)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int key = jj * 16 + half * 8 + 2 * t;
+          if (key >= S) { c[half][0] = -INFINITY; c[half][2] = -INFINITY; }
+          if (key + 1 >= S) { c[half][1] = -INFINITY; c[half][3] = -INFINITY; }
+        }
+      }
+      // online soft-max: rows rA (elements 0, 1) and rB (elements 2, 3) of both tiles
+      float bmA = fmaxf(fmaxf(c[0][0], c[0][1]), fmaxf(c[1][0], c[1][1]));
+      float bmB = fmaxf(fmaxf(c[0][2], c[0][3]), fmaxf(c[1][2], c[1][3]));
+      bmA = fmaxf(bmA, __shfl_xor_sync(0xffffffffu, bmA, 1));
+      bmB = fmaxf(bmB, __shfl_xor_sync(0xffffffffu, bmB, 1));
+      bmA = fmaxf(bmA, __shfl_xor_sync(0xffffffffu, bmA, 2));
+      bmB = fmaxf(bmB, __shfl_xor_sync(0xffffffffu, bmB, 2));
+      bmA = fmaxf(bmA, mA);
+      bmB = fmaxf(bmB, mB);
+      const float corrA = ex2(mA - bmA), corrB = ex2(mB - bmB);   // first block: ex2(-inf) = 0
+      mA = bmA; mB = bmB;
+      lA *= corrA; lB *= corrB;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { o[nt][0] *= corrA; o[nt][1] *= corrA; o[nt][2] *= corrB; o[nt][3] *= corrB; }
+      float p[2][4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        p[half][0] = ex2(c[half][0] - mA); p[half][1] = ex2(c[half][1] - mA);
+        p[half][2] = ex2(c[half][2] - mB); p[half][3] = ex2(c[half][3] - mB);
+        lA += p[half][0] + p[half][1];     // the denominator counts dropped keys too
+        lB += p[half][2] + p[half][3];
+      }
+      if (dr.mode == 1) {
+        const uint32_t mine = keep_bits8(rng.block(1u | (my_row << 2), static_cast<uint32_t>(2 * jj + (t >> 1))), dr.thr_a);
+        const int quad = lane & ~3;
+        const uint32_t kA0 = __shfl_sync(0xffffffffu, mine, quad) >> (2 * t);       // row A, first tile
+        const uint32_t kB0 = __shfl_sync(0xffffffffu, mine, quad + 1) >> (2 * t);   // row B, first tile
+        const uint32_t kA1 = __shfl_sync(0xffffffffu, mine, quad + 2) >> (2 * t);   // row A, second tile
+        const uint32_t kB1 = __shfl_sync(0xffffffffu, mine, quad + 3) >> (2 * t);
+        if (!(kA0 & 1u)) p[0][0] = 0.f;
+        if (!(kA0 & 2u)) p[0][1] = 0.f;
+        if (!(kB0 & 1u)) p[0][2] = 0.f;
+        if (!(kB0 & 2u)) p[0][3] = 0.f;
+        if (!(kA1 & 1u)) p[1][0] = 0.f;
+        if (!(kA1 & 2u)) p[1][1] = 0.f;
+        if (!(kB1 & 1u)) p[1][2] = 0.f;
+        if (!(kB1 & 2u)) p[1][3] = 0.f;
+        const int sh = (jj & 1) * 16 + 2 * t;
+        bitsA |= ((kA0 & 3u) << sh) | ((kA1 & 3u) << (sh + 8));
+        bitsB |= ((kB0 & 3u) << sh) | ((kB1 & 3u) << (sh + 8));
+      } else {
+        const int sh = (jj & 1) * 16 + 2 * t;
+        bitsA |= (3u << sh) | (3u << (sh + 8));
+        bitsB |= (3u << sh) | (3u << (sh + 8));
+      }
+      if ((jj & 1) == 1 || jj == tiles - 1) {   // a 32-key word of keep bits is complete
+        bitsA |= __shfl_xor_sync(0xffffffffu, bitsA, 1); bitsB |= __shfl_xor_sync(0xffffffffu, bitsB, 1);
+        bitsA |= __shfl_xor_sync(0xffffffffu, bitsA, 2); bitsB |= __shfl_xor_sync(0xffffffffu, bitsB, 2);
+        if (abits != nullptr && t == 0) {
+          if (rA < S) abits[((static_cast<long long>(b) * H + h) * S + rA) * 4 + (jj >> 1)] = bitsA;
+          if (rB < S) abits[((static_cast<long long>(b) * H + h) * S + rB) * 4 + (jj >> 1)] = bitsB;
+        }
+        bitsA = 0; bitsB = 0;
+      }
+      // context: the two score tiles are one k-step of 16 keys; P_kept as split bf16
+      uint32_t ah[4], al[4];
+      {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(p[0][0], p[0][1]), h1 = __floats2bfloat162_rn(p[0][2], p[0][3]);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(p[1][0], p[1][1]), h3 = __floats2bfloat162_rn(p[1][2], p[1][3]);
+        ah[0] = *reinterpret_cast<const uint32_t*>(&h0); ah[1] = *reinterpret_cast<const uint32_t*>(&h1);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&h2); ah[3] = *reinterpret_cast<const uint32_t*>(&h3);
+        al[0] = pack2(p[0][0] - __low2float(h0), p[0][1] - __high2float(h0));
+        al[1] = pack2(p[0][2] - __low2float(h1), p[0][3] - __high2float(h1));
+        al[2] = pack2(p[1][0] - __low2float(h2), p[1][1] - __high2float(h2));
+        al[3] = pack2(p[1][2] - __low2float(h3), p[1][3] - __high2float(h3));
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int n0 = h * DH + nt * 8 + g, k0 = jj * 16 + 2 * t;
+        const uint32_t bh0 = lds_u32(vT_hi + n0 * LDT + k0), bh1 = lds_u32(vT_hi + n0 * LDT + k0 + 8);
+        const uint32_t bl0 = lds_u32(vT_lo + n0 * LDT + k0), bl1 = lds_u32(vT_lo + n0 * LDT + k0 + 8);
+        mma_bf16_16816(o[nt], al, bh0, bh1);
+        mma_bf16_16816(o[nt], ah, bl0, bl1);
+        mma_bf16_16816(o[nt], ah, bh0, bh1);
+      }
+    }
+    lA += __shfl_xor_sync(0xffffffffu, lA, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+    lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+    const float linvA = 1.f / lA, linvB = 1.f / lB;
+    const float scA = dr.inv_a * linvA, scB = dr.inv_a * linvB;
+    auto put = [&](int r, int col, float x0, float x1) {   // split bf16 row [hi | lo | hi]
+      __nv_bfloat16* out = ctx16 + (static_cast<long long>(b) * S + r) * 3 * E + col;
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(x0, x1);
+      const uint32_t hiw = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint32_t*>(out) = hiw;
+      *reinterpret_cast<uint32_t*>(out + E) = pack2(x0 - __low2float(hi), x1 - __high2float(hi));
+      *reinterpret_cast<uint32_t*>(out + 2 * E) = hiw;
+    };
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = h * DH + nt * 8 + 2 * t;
+      if (rA < S) put(rA, col, o[nt][0] * scA, o[nt][1] * scA);
+      if (rB < S) put(rB, col, o[nt][2] * scB, o[nt][3] * scB);
+    }
+    if (stat != nullptr && t == 0) {
+      if (rA < S) stat[(static_cast<long long>(b) * H + h) * S + rA] = make_float2(mA, linvA);
+      if (rB < S) stat[(static_cast<long long>(b) * H + h) * S + rB] = make_float2(mB, linvB);
     }
   }
 }
@@ -1011,6 +1262,18 @@ cudaError_t launch_wide_attention_fwd(const WideDims& d, const WideDrop& dr, con
   int threads = d.H * ((d.S + 31) & ~31);
   if (threads > 512) threads = 512;      // 128 registers per thread: q / acc rows stay in registers
   cudaError_t e;
+  static const bool no_mma = std::getenv("AFR_WIDE_ATTN_SIMT") != nullptr;      // diagnostic: force the SIMT kernel
+  const AttnFwdSmem ml = attn_fwd_smem(d.S, d.E);
+  if (!no_mma && (d.dh == 16 || d.dh == 32) && ml.total <= 220 * 1024) {
+    if (d.dh == 16) {
+      if ((e = set_smem(wide_attention_fwd_mma_kernel<16>, ml.total)) != cudaSuccess) return e;
+      wide_attention_fwd_mma_kernel<16><<<d.B, 512, ml.total, st>>>(d, dr, qkv, ctx16, stat, abits);
+    } else {
+      if ((e = set_smem(wide_attention_fwd_mma_kernel<32>, ml.total)) != cudaSuccess) return e;
+      wide_attention_fwd_mma_kernel<32><<<d.B, 512, ml.total, st>>>(d, dr, qkv, ctx16, stat, abits);
+    }
+    return cudaGetLastError();
+  }
   switch (d.dh) {
     case 8:
       if ((e = set_smem(wide_attention_fwd_kernel<8>, smem)) != cudaSuccess) return e;
