@@ -45,9 +45,9 @@ typedef struct afr_config {
   int device;      /* CUDA ordinal */
   int vocab;       /* nn.Embedding rows: 128 */
   int max_length;  /* MAX_CHARS_PER_SHEET: 100 (<= 128) */
-  int embed_dim;   /* EMBEDDING_DIM: 32 (only 32 is built) */
-  int num_heads;   /* NUM_ATTENTION_HEADS: 4 (only 4 is built) */
-  int hidden;      /* fc1 width: 64 (only 64 is built) */
+  int embed_dim;   /* EMBEDDING_DIM: 32; other multiples of 32 up to 256 take the GEMM-based front-end */
+  int num_heads;   /* NUM_ATTENTION_HEADS: 4; embed_dim / num_heads must be 8, 16 or 32 */
+  int hidden;      /* fc1 width: 64; other multiples of 32 with the GEMM-based front-end */
   int sheet_h;     /* SHEET_HEIGHT: 80 */
   int sheet_w;     /* SHEET_WIDTH: 240; sheet_h*sheet_w must be a multiple of 32 */
   int max_batch;   /* largest B any call will pass; sizes the private workspaces */
