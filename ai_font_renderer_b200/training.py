@@ -310,8 +310,22 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
         # wgrad, beside dgrad (1.42 instead of 1.385 ms per step at B = 1024).
         if after_dgrad:
             model.set_smem_reserve(0)
+        # one chunk: fc_output.bias.grad (two small kernels, 16 us) leaves the compute stream too; it
+        # only needs d(logits), and only the small-tensor AdamW at the end of the step needs it
+        ev_bias = None
+        if last == 0 and after_dgrad:       # (afr_train_wgrad_to honours the shared-memory reserve, which is 0 here)
+            ev_fwd = torch.cuda.Event()
+            ev_fwd.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_fwd)
+                optimizer.bias_grad_rows(0, P)
+                ev_bias = torch.cuda.Event()
+                ev_bias.record(side)
         for i, (r0, r1) in enumerate(chunks):
-            model.wgrad_rows(r0, r1)
+            if ev_bias is not None:
+                model.wgrad_rows_to(r0, r1, wgrad, with_bias=False)
+            else:
+                model.wgrad_rows(r0, r1)
             if i == last:
                 mark("wgrad")
             if after_dgrad:
@@ -330,6 +344,8 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
             dgrad()
         model.frontend_backward()
         mark("dgrad")
+        if ev_bias is not None:
+            main.wait_event(ev_bias)
         optimizer.step_small(t_step)
         model.defer_join(side, commit=False)   # afr_adamw_rows_bg activates the copy it completed
         optimizer.end_step()
