@@ -515,7 +515,7 @@ __global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a
 
 // ---------------------------------------------------------------- K1: head of the backward
 struct HeadSmem {
-  int w1, wo, lnw, xhat, df, dr, ctx, fbits, rstd, red, bars, total;
+  int w1, wo, lnw, stage[2], stage_words, xhat, df, ctx, fbits, rstd, dr, red, bars, total;   // xhat .. rstd: offsets inside a stage
 };
 __host__ __device__ inline HeadSmem make_head_smem(int L) {
   const int L4 = (L + 3) & ~3;
@@ -525,15 +525,20 @@ __host__ __device__ inline HeadSmem make_head_smem(int L) {
   s.wo = o;  o += kE * kLdW;
   s.lnw = o; o += kE;
   o = (o + 3) & ~3;
-  s.xhat = o; o += L * kE;        // xhat -> h (B1)
-  s.df = o;   o += L * kF;        // dfeat -> df (B1)
+  // the staged operands of a sample, twice: sample i + 1 loads while sample i computes
+  int q = 0;
+  s.xhat = q; q += L * kE;        // xhat -> h (B1)
+  s.df = q;   q += L * kF;        // dfeat -> df (B1)
+  s.ctx = q;  q += L * kE;
+  s.fbits = q; q += L4 * 2;
+  s.rstd = q; q += L4;
+  s.stage_words = (q + 3) & ~3;
+  s.stage[0] = o; o += s.stage_words;
+  s.stage[1] = o; o += s.stage_words;
   s.dr = o;   o += L * kE;        // d(residual)
-  s.ctx = o;  o += L * kE;
-  s.fbits = o; o += L4 * 2;
-  s.rstd = o; o += L4;
   s.red = o;  o += kWarps * kE * 2;
   o = (o + 3) & ~3;
-  s.bars = o; o += 4;             // 2 mbarriers
+  s.bars = o; o += 8;             // 2 x 2 mbarriers
   s.total = o;
   return s;
 }
@@ -550,16 +555,12 @@ __device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) 
   load_matrix(a.w.wo, sm + o.wo, kE);
   if (tid < kE) sm[o.lnw + tid] = a.w.lnw[tid];
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
 
-  float* s_xhat = sm + o.xhat;
-  float* s_df = sm + o.df;
   float* s_dr = sm + o.dr;
-  float* s_ctx = sm + o.ctx;
-  const uint32_t* s_fbits = reinterpret_cast<const uint32_t*>(sm + o.fbits);
 
   // gradient accumulators that live in registers for the whole kernel
   // (lane = input channel c; a warp owns a band of output rows)
@@ -569,26 +570,42 @@ __device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) 
   float g_gam = 0.f, g_bet = 0.f;  // (warp, lane = channel) partial of d(LayerNorm weight / bias)
 
   const float inv_a = a.inv_a, inv_f = a.inv_f;
-  uint32_t phase = 0;
 
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x, phase ^= 1u) {
+  // stage sample b's operands into buffer `buf`: two groups, each waited for right before its first use
+  auto issue = [&](int b, int buf) {
     float* st = a.state + static_cast<long long>(b) * a.sl.stride;
-    // ---- stage this sample's operands: two groups, each waited for right before its first use
+    float* base = sm + o.stage[0] + buf * o.stage_words;
+    uint64_t* bar = bars + 2 * buf;
+    const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
+    ptx::mbar_arrive_expect_tx(&bar[0], row_bytes + 2u * row_bytes + S4 * 8u + S4 * 4u);
+    ptx::bulk_load_1d(base + o.xhat, st + a.sl.xhat, row_bytes, &bar[0]);
+    ptx::bulk_load_1d(base + o.df, a.dfeat + static_cast<long long>(b) * KF, 2u * row_bytes, &bar[0]);
+    ptx::bulk_load_1d(base + o.fbits, st + a.sl.fbits, S4 * 8u, &bar[0]);
+    ptx::bulk_load_1d(base + o.rstd, st + a.sl.rstd, S4 * 4u, &bar[0]);
+    ptx::mbar_arrive_expect_tx(&bar[1], row_bytes);
+    ptx::bulk_load_1d(base + o.ctx, st + a.sl.ctx, row_bytes, &bar[1]);
+  };
+  if (tid == 0 && static_cast<int>(blockIdx.x) < a.B) issue(blockIdx.x, 0);
+
+  int it = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
+    float* st = a.state + static_cast<long long>(b) * a.sl.stride;
+    const int cur = it & 1;
+    const uint32_t phase = static_cast<uint32_t>(it >> 1) & 1u;
+    uint64_t* bar = bars + 2 * cur;
+    float* s_xhat = sm + (o.stage[0] + cur * o.stage_words) + o.xhat;
+    float* s_df = sm + (o.stage[0] + cur * o.stage_words) + o.df;
+    float* s_ctx = sm + (o.stage[0] + cur * o.stage_words) + o.ctx;
+    const uint32_t* s_fbits = reinterpret_cast<const uint32_t*>(sm + (o.stage[0] + cur * o.stage_words) + o.fbits);
+    const float* s_rstd = sm + (o.stage[0] + cur * o.stage_words) + o.rstd;
+    // the next sample's operands load into the other buffer while this one computes (cp.async.bulk
+    // moves ~8 B/clk per CTA: 64 KB exposed per sample was a third of this kernel's time)
     ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
     __syncthreads();
-    if (tid == 0) {
-      const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
-      ptx::mbar_arrive_expect_tx(&bars[0], row_bytes + 2u * row_bytes + S4 * 8u + S4 * 4u);
-      ptx::bulk_load_1d(s_xhat, st + a.sl.xhat, row_bytes, &bars[0]);
-      ptx::bulk_load_1d(s_df, a.dfeat + static_cast<long long>(b) * KF, 2u * row_bytes, &bars[0]);
-      ptx::bulk_load_1d(sm + o.fbits, st + a.sl.fbits, S4 * 8u, &bars[0]);
-      ptx::bulk_load_1d(sm + o.rstd, st + a.sl.rstd, S4 * 4u, &bars[0]);
-      ptx::mbar_arrive_expect_tx(&bars[1], row_bytes);
-      ptx::bulk_load_1d(s_ctx, st + a.sl.ctx, row_bytes, &bars[1]);
-    }
+    if (tid == 0 && b + static_cast<int>(gridDim.x) < a.B) issue(b + gridDim.x, cur ^ 1);
 
     // ---- B1: df = dfeat * ReLU' * dropout ; dh = df W1 ; LayerNorm backward -> dr ; h --------
-    ptx::mbar_wait(&bars[0], phase);
+    ptx::mbar_wait(&bar[0], phase);
     {
       float2 w1c[kF / 2];   // column `lane` of W1, packed along the feature index
 #pragma unroll
@@ -602,7 +619,7 @@ __device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) 
         const bool two = s1 < S;                  // warp-uniform
         const int sb = two ? s1 : s0;             // row b aliases row a when there is no second row
         const float xh_a = s_xhat[s0 * kE + lane], xh_b = s_xhat[sb * kE + lane];
-        const float rs_a = sm[o.rstd + s0], rs_b = sm[o.rstd + sb];
+        const float rs_a = s_rstd[s0], rs_b = s_rstd[sb];
         {
           float2 da = *reinterpret_cast<const float2*>(s_df + s0 * kF + 2 * lane);
           const uint32_t a0 = s_fbits[2 * s0], a1 = s_fbits[2 * s0 + 1];
@@ -653,7 +670,7 @@ __device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) 
       }
     }
     // ---- B1b: dctx = dr Wo and D = dctx . ctx for the rows this warp just produced (for K2) -----
-    ptx::mbar_wait(&bars[1], phase);   // ctx
+    ptx::mbar_wait(&bar[1], phase);   // ctx
     __syncwarp();
     {
       float2 woc[kE / 2];   // column `lane` of Wo, packed along the output channel
@@ -991,7 +1008,7 @@ __global__ void __maxnreg__(64) frontend_backward_attn_kernel_shared(const Front
 
 // ---------------------------------------------------------------- K3: tail of the backward
 struct TailSmem {
-  int win, dq, dk, dv, e, dr, ebits, tok, hist, fonth, bars, total;
+  int win, stage[2], stage_words, dq, dk, dv, dr, ebits, e, tok, hist, fonth, bars, total;   // dq .. ebits: offsets inside a stage
 };
 __host__ __device__ inline TailSmem make_tail_smem(int L, int vocab) {
   const int L4 = (L + 3) & ~3;
@@ -999,17 +1016,23 @@ __host__ __device__ inline TailSmem make_tail_smem(int L, int vocab) {
   int o = 0;
   s.win = o; o += 3 * kE * kLdW;
   o = (o + 3) & ~3;
-  s.dq = o;  o += L * kE;
-  s.dk = o;  o += L * kE;
-  s.dv = o;  o += L * kE;
+  // dq, dk, dv, d(residual), embedding keep bits of a sample, twice (the next sample loads while
+  // this one computes); e is needed last (B5) and loads into its single buffer during B4
+  int q = 0;
+  s.dq = q;  q += L * kE;
+  s.dk = q;  q += L * kE;
+  s.dv = q;  q += L * kE;
+  s.dr = q;  q += L * kE;         // d(residual) -> d(embedding rows) (B4)
+  s.ebits = q; q += L4;
+  s.stage_words = (q + 3) & ~3;
+  s.stage[0] = o; o += s.stage_words;
+  s.stage[1] = o; o += s.stage_words;
   s.e = o;   o += L * kE;
-  s.dr = o;  o += L * kE;         // d(residual) -> d(embedding rows) (B4)
-  s.ebits = o; o += L4;
   s.tok = o;  o += L4;
   s.hist = o; o += vocab <= kEmbSmemMaxVocab ? vocab * kE : 0;
   s.fonth = o; o += kMaxFonts * kE;   // d(font_embedding) of this CTA's samples
   o = (o + 3) & ~3;
-  s.bars = o; o += 4;                // 2 mbarriers
+  s.bars = o; o += 8;                // 3 mbarriers: stage 0, stage 1, e
   s.total = o;
   return s;
 }
@@ -1031,17 +1054,12 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
   }
   for (int i = tid; i < kMaxFonts * kE; i += kThreads) sm[o.fonth + i] = 0.f;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3; ++i) ptx::mbar_init(&bars[i], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
 
-  float* s_dq = sm + o.dq;
-  float* s_dk = sm + o.dk;
-  float* s_dv = sm + o.dv;
   float* s_e = sm + o.e;
-  float* s_dr = sm + o.dr;
-  const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + o.ebits);
   int* s_tok = reinterpret_cast<int*>(sm + o.tok);
 
   float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // warps 0-11: dWin[8w+2i, 8w+2i+1][c]
@@ -1051,22 +1069,37 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
   for (int i = 0; i < kRowsPerWarp; ++i) g_pos[i] = 0.f;
 
   const float inv_e = a.inv_e;
-  uint32_t phase = 0;
 
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x, phase ^= 1u) {
+  auto issue = [&](int b, int buf) {
+    const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
+    float* base = sm + o.stage[0] + buf * o.stage_words;
+    const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
+    ptx::mbar_arrive_expect_tx(&bars[buf], 4u * row_bytes + S4 * 4u);
+    ptx::bulk_load_1d(base + o.dq, st + a.sl.dq, row_bytes, &bars[buf]);
+    ptx::bulk_load_1d(base + o.dk, st + a.sl.dk, row_bytes, &bars[buf]);
+    ptx::bulk_load_1d(base + o.dv, st + a.sl.dv, row_bytes, &bars[buf]);
+    ptx::bulk_load_1d(base + o.dr, st + a.sl.dr, row_bytes, &bars[buf]);
+    ptx::bulk_load_1d(base + o.ebits, st + a.sl.ebits, S4 * 4u, &bars[buf]);
+  };
+  if (tid == 0 && static_cast<int>(blockIdx.x) < a.B) issue(blockIdx.x, 0);
+
+  int it = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
+    const int cur = it & 1;
+    const uint32_t phase = static_cast<uint32_t>(it >> 1) & 1u, phase_e = static_cast<uint32_t>(it) & 1u;
+    float* s_dq = sm + (o.stage[0] + cur * o.stage_words) + o.dq;
+    float* s_dk = sm + (o.stage[0] + cur * o.stage_words) + o.dk;
+    float* s_dv = sm + (o.stage[0] + cur * o.stage_words) + o.dv;
+    float* s_dr = sm + (o.stage[0] + cur * o.stage_words) + o.dr;
+    const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + (o.stage[0] + cur * o.stage_words) + o.ebits);
     ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
     __syncthreads();
     if (tid == 0) {
+      if (b + static_cast<int>(gridDim.x) < a.B) issue(b + gridDim.x, cur ^ 1);   // next sample, other buffer
       const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
       const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
-      ptx::mbar_arrive_expect_tx(&bars[0], 4u * row_bytes + S4 * 4u);
-      ptx::bulk_load_1d(s_dq, st + a.sl.dq, row_bytes, &bars[0]);
-      ptx::bulk_load_1d(s_dk, st + a.sl.dk, row_bytes, &bars[0]);
-      ptx::bulk_load_1d(s_dv, st + a.sl.dv, row_bytes, &bars[0]);
-      ptx::bulk_load_1d(s_dr, st + a.sl.dr, row_bytes, &bars[0]);
-      ptx::bulk_load_1d(sm + o.ebits, st + a.sl.ebits, S4 * 4u, &bars[0]);
-      ptx::mbar_arrive_expect_tx(&bars[1], row_bytes);
-      ptx::bulk_load_1d(s_e, st + a.sl.e, row_bytes, &bars[1]);
+      ptx::mbar_arrive_expect_tx(&bars[2], row_bytes);
+      ptx::bulk_load_1d(s_e, st + a.sl.e, row_bytes, &bars[2]);
     }
     if (tid < S) {
       long long t = a.tokens[static_cast<long long>(b) * a.token_stride + tid];
@@ -1075,7 +1108,7 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
     }
 
     // ---- B4: de = dr + [dq dk dv] Win ; dPos ; d(embedding rows) ------------------------------
-    ptx::mbar_wait(&bars[0], phase);
+    ptx::mbar_wait(&bars[cur], phase);
     {
       float de[kRowsPerWarp];
 #pragma unroll
@@ -1116,7 +1149,7 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
     __syncthreads();
 
     // ---- B5: dWin (warps 0-11) | dbin, embedding scatter-add (warp 12) ------------------------
-    ptx::mbar_wait(&bars[1], phase);
+    ptx::mbar_wait(&bars[2], phase_e);
     if (warp < 12) {
       // lane = input channel c; this warp owns rows [8w, 8w+8) of dWin (q | k | v blocks of 32)
       const float* src = (warp < 4 ? s_dq : (warp < 8 ? s_dk : s_dv)) + 8 * (warp & 3);
