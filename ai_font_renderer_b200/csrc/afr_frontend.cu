@@ -394,7 +394,7 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
         const float rstd = 1.f / sqrtf(var + 1e-5f);
         const float xhat = d * rstd;
         if (st != nullptr) {
-          st[a.sl.e + s * kE + lane] = ev;
+          st[a.sl.e + s * kLdT + lane] = ev;
           st[a.sl.ctx + s * kE + lane] = sq[s * kE + lane];
           st[a.sl.xhat + s * kE + lane] = xhat;
           if (lane == 0) st[a.sl.rstd + s] = rstd;
@@ -659,12 +659,12 @@ __device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) 
         warp_sum2(m1b, m2b);
         const float dr_a = rs_a * (dhg_a - m1a * (1.f / kE) - xh_a * (m2a * (1.f / kE)));
         s_dr[s0 * kE + lane] = dr_a;
-        g_dr[s0 * kE + lane] = dr_a;                     // for K3
+        g_dr[s0 * kLdT + lane] = dr_a;                   // for K3
         s_xhat[s0 * kE + lane] = fmaf(xh_a, gam, bet);   // h, for dW1
         if (two) {
           const float dr_b = rs_b * (dhg_b - m1b * (1.f / kE) - xh_b * (m2b * (1.f / kE)));
           s_dr[s1 * kE + lane] = dr_b;
-          g_dr[s1 * kE + lane] = dr_b;
+          g_dr[s1 * kLdT + lane] = dr_b;
           s_xhat[s1 * kE + lane] = fmaf(xh_b, gam, bet);
         }
       }
@@ -925,8 +925,8 @@ __device__ __forceinline__ void frontend_backward_attn_body(const FrontArgs& a) 
         }
         // d(q) of the unscaled projection: d(score) * k / sqrt(head_dim)
         float* gq = st + a.sl.dq + hc + 2 * t;
-        if (r0 < S) *reinterpret_cast<float2*>(gq + r0 * kE) = make_float2(dq[0] * kInvSqrtDh, dq[1] * kInvSqrtDh);
-        if (r1 < S) *reinterpret_cast<float2*>(gq + r1 * kE) = make_float2(dq[2] * kInvSqrtDh, dq[3] * kInvSqrtDh);
+        if (r0 < S) *reinterpret_cast<float2*>(gq + r0 * kLdT) = make_float2(dq[0] * kInvSqrtDh, dq[1] * kInvSqrtDh);
+        if (r1 < S) *reinterpret_cast<float2*>(gq + r1 * kLdT) = make_float2(dq[2] * kInvSqrtDh, dq[3] * kInvSqrtDh);
       } else {
         // ---- rows = keys r0, r1; stream over query tiles -> dk, dv
         uint32_t kh[4], kl[4], vh[4], vl[4];
@@ -986,12 +986,12 @@ __device__ __forceinline__ void frontend_backward_attn_body(const FrontArgs& a) 
         float* gk = st + a.sl.dk + hc + 2 * t;
         float* gv = st + a.sl.dv + hc + 2 * t;
         if (r0 < S) {
-          *reinterpret_cast<float2*>(gk + r0 * kE) = make_float2(dk[0] * kLn2, dk[1] * kLn2);
-          *reinterpret_cast<float2*>(gv + r0 * kE) = make_float2(dv[0], dv[1]);
+          *reinterpret_cast<float2*>(gk + r0 * kLdT) = make_float2(dk[0] * kLn2, dk[1] * kLn2);
+          *reinterpret_cast<float2*>(gv + r0 * kLdT) = make_float2(dv[0], dv[1]);
         }
         if (r1 < S) {
-          *reinterpret_cast<float2*>(gk + r1 * kE) = make_float2(dk[2] * kLn2, dk[3] * kLn2);
-          *reinterpret_cast<float2*>(gv + r1 * kE) = make_float2(dv[2], dv[3]);
+          *reinterpret_cast<float2*>(gk + r1 * kLdT) = make_float2(dk[2] * kLn2, dk[3] * kLn2);
+          *reinterpret_cast<float2*>(gv + r1 * kLdT) = make_float2(dv[2], dv[3]);
         }
       }
     }
@@ -1007,165 +1007,184 @@ __global__ void __maxnreg__(64) frontend_backward_attn_kernel_shared(const Front
 }
 
 // ---------------------------------------------------------------- K3: tail of the backward
+// de = dr + [dq dk dv] Win (B4) and dWin += [dq dk dv]^T e, dbin += column sums (B5) as 3xTF32 warp
+// MMAs (the FFMA2 forms were one LDS per 1-2 FMAs: 31 k warp instructions per sample); the
+// embedding scatter-add stays a position-ordered walk by one warp. All operands are rows of kLdT =
+// 40 floats (the producers write them that way into the record): 8t + g is a distinct bank for
+// every lane of a B / A^T fragment load. 14 warps: B4 = 7 row tiles x 2 column halves, B5 = 6
+// channel tiles x 2 column halves (+ a ones-tile for dbin) beside the scatter warp.
+constexpr int kTailWarps = 14;
+constexpr int kTailThreads = kTailWarps * 32;
+
 struct TailSmem {
-  int win, stage[2], stage_words, dq, dk, dv, dr, ebits, e, tok, hist, fonth, bars, total;   // dq .. ebits: offsets inside a stage
+  int win_hi, win_lo, dq, dk, dv, dr, e, de, ebits, tok, hist, fonth, rows, total;
 };
 __host__ __device__ inline TailSmem make_tail_smem(int L, int vocab) {
   const int L4 = (L + 3) & ~3;
   TailSmem s{};
+  s.rows = (L + 15) & ~15;
   int o = 0;
-  s.win = o; o += 3 * kE * kLdW;
-  o = (o + 3) & ~3;
-  // dq, dk, dv, d(residual), embedding keep bits of a sample, twice (the next sample loads while
-  // this one computes); e is needed last (B5) and loads into its single buffer during B4
-  int q = 0;
-  s.dq = q;  q += L * kE;
-  s.dk = q;  q += L * kE;
-  s.dv = q;  q += L * kE;
-  s.dr = q;  q += L * kE;         // d(residual) -> d(embedding rows) (B4)
-  s.ebits = q; q += L4;
-  s.stage_words = (q + 3) & ~3;
-  s.stage[0] = o; o += s.stage_words;
-  s.stage[1] = o; o += s.stage_words;
-  s.e = o;   o += L * kE;
+  s.win_hi = o; o += 3 * kE * kLdT;     // Win split once per CTA: TF32 hi / lo words
+  s.win_lo = o; o += 3 * kE * kLdT;
+  s.dq = o;  o += s.rows * kLdT;
+  s.dk = o;  o += s.rows * kLdT;
+  s.dv = o;  o += s.rows * kLdT;
+  s.e = o;   o += s.rows * kLdT;
+  s.dr = o;  o += L * kLdT;
+  s.de = o;  o += L * kE;               // d(embedding rows) after the dropout mask, for the scatter walk
+  s.ebits = o; o += L4;
   s.tok = o;  o += L4;
   s.hist = o; o += vocab <= kEmbSmemMaxVocab ? vocab * kE : 0;
   s.fonth = o; o += kMaxFonts * kE;   // d(font_embedding) of this CTA's samples
-  o = (o + 3) & ~3;
-  s.bars = o; o += 8;                // 3 mbarriers: stage 0, stage 1, e
-  s.total = o;
+  s.total = (o + 3) & ~3;
   return s;
 }
 
 __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) {
   extern __shared__ __align__(16) float sm[];
   const TailSmem o = make_tail_smem(a.L, a.vocab);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int S = a.S, S4 = (S + 3) & ~3;
   const bool hist_smem = a.vocab <= kEmbSmemMaxVocab;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o.bars);
   float* part = a.partials + static_cast<long long>(blockIdx.x) * a.lay.total;
 
-  load_matrix(a.w.win, sm + o.win, 3 * kE);
+  uint32_t* win_hi = reinterpret_cast<uint32_t*>(sm + o.win_hi);
+  uint32_t* win_lo = reinterpret_cast<uint32_t*>(sm + o.win_lo);
+  for (int i = tid; i < 3 * kE * kE; i += kTailThreads) {
+    uint32_t hi, lo;
+    ptx::split_tf32(a.w.win[i], hi, lo);
+    win_hi[(i / kE) * kLdT + (i % kE)] = hi;
+    win_lo[(i / kE) * kLdT + (i % kE)] = lo;
+  }
+  // rows >= S of dq, dk, dv, e stay zero: they pad the reduction over positions of B5
+  for (int i = tid; i < 4 * o.rows * kLdT; i += kTailThreads) sm[o.dq + i] = 0.f;
   if (hist_smem) {
-    for (int i = tid; i < a.vocab * kE; i += kThreads) sm[o.hist + i] = 0.f;
+    for (int i = tid; i < a.vocab * kE; i += kTailThreads) sm[o.hist + i] = 0.f;
   } else {
-    for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = 0.f;
+    for (int i = tid; i < a.vocab * kE; i += kTailThreads) part[a.lay.off_emb + i] = 0.f;
   }
-  for (int i = tid; i < kMaxFonts * kE; i += kThreads) sm[o.fonth + i] = 0.f;
-  if (tid == 0) {
-    for (int i = 0; i < 3; ++i) ptx::mbar_init(&bars[i], 1);
-    ptx::fence_mbar_init();
-  }
+  for (int i = tid; i < kMaxFonts * kE; i += kTailThreads) sm[o.fonth + i] = 0.f;
   __syncthreads();
 
+  float* s_dq = sm + o.dq;
   float* s_e = sm + o.e;
+  float* s_dr = sm + o.dr;
+  float* s_de = sm + o.de;
+  const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + o.ebits);
   int* s_tok = reinterpret_cast<int*>(sm + o.tok);
 
-  float2 g_win[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};   // warps 0-11: dWin[8w+2i, 8w+2i+1][c]
-  float g_bin = 0.f;               // warps 0-11, lanes 0-7: dbin[8w+lane]
-  float g_pos[kRowsPerWarp];       // d(positional_encoding)[warp + 13 i][lane]
+  // accumulators that live in registers for the whole kernel (MMA accumulator layout)
+  float g_pos[2][4];   // B4 unit (mt = warp >> 1, nh = warp & 1): d(pos) rows 16 mt + {g, g+8}, cols 16 nh + 8 nt + {2t, 2t+1}
+  float g_win[2][4];   // B5 unit (warps 0-11): dWin rows 16 mt + {g, g+8}, same columns
+  float g_bin[4];      // B5, nh == 0: dbin rows 16 mt + {g, g+8} (every column of the ones-tile holds the sum)
 #pragma unroll
-  for (int i = 0; i < kRowsPerWarp; ++i) g_pos[i] = 0.f;
+  for (int i = 0; i < 4; ++i) { g_pos[0][i] = g_pos[1][i] = g_win[0][i] = g_win[1][i] = g_bin[i] = 0.f; }
 
   const float inv_e = a.inv_e;
+  const int mt = warp >> 1, nh = warp & 1;
+  const uint32_t one = __float_as_uint(1.f);
 
-  auto issue = [&](int b, int buf) {
-    const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
-    float* base = sm + o.stage[0] + buf * o.stage_words;
-    const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
-    ptx::mbar_arrive_expect_tx(&bars[buf], 4u * row_bytes + S4 * 4u);
-    ptx::bulk_load_1d(base + o.dq, st + a.sl.dq, row_bytes, &bars[buf]);
-    ptx::bulk_load_1d(base + o.dk, st + a.sl.dk, row_bytes, &bars[buf]);
-    ptx::bulk_load_1d(base + o.dv, st + a.sl.dv, row_bytes, &bars[buf]);
-    ptx::bulk_load_1d(base + o.dr, st + a.sl.dr, row_bytes, &bars[buf]);
-    ptx::bulk_load_1d(base + o.ebits, st + a.sl.ebits, S4 * 4u, &bars[buf]);
-  };
-  if (tid == 0 && static_cast<int>(blockIdx.x) < a.B) issue(blockIdx.x, 0);
-
-  int it = 0;
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
-    const int cur = it & 1;
-    const uint32_t phase = static_cast<uint32_t>(it >> 1) & 1u, phase_e = static_cast<uint32_t>(it) & 1u;
-    float* s_dq = sm + (o.stage[0] + cur * o.stage_words) + o.dq;
-    float* s_dk = sm + (o.stage[0] + cur * o.stage_words) + o.dk;
-    float* s_dv = sm + (o.stage[0] + cur * o.stage_words) + o.dv;
-    float* s_dr = sm + (o.stage[0] + cur * o.stage_words) + o.dr;
-    const uint32_t* s_ebits = reinterpret_cast<const uint32_t*>(sm + (o.stage[0] + cur * o.stage_words) + o.ebits);
-    ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
-    __syncthreads();
-    if (tid == 0) {
-      if (b + static_cast<int>(gridDim.x) < a.B) issue(b + gridDim.x, cur ^ 1);   // next sample, other buffer
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    __syncthreads();     // every warp is done with the previous sample's operands
+    {
+      // cp.async by all threads: group 0 = dq, dk, dv, dr, keep bits; group 1 = e (needed by B5 only).
+      // (cp.async.bulk + mbarrier, a double-buffered variant and an L2 prefetch of the next sample
+      // all measure the same 0.071-0.073 ms: the wait at the top is not what bounds this kernel.)
       const float* st = a.state + static_cast<long long>(b) * a.sl.stride;
-      const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
-      ptx::mbar_arrive_expect_tx(&bars[2], row_bytes);
-      ptx::bulk_load_1d(s_e, st + a.sl.e, row_bytes, &bars[2]);
+      const int chunks = S * kLdT / 4;
+      for (int i = tid; i < chunks; i += kTailThreads) {
+        ptx::cp_async_16(ptx::smem_u32(s_dq + 4 * i), st + a.sl.dq + 4 * i);
+        ptx::cp_async_16(ptx::smem_u32(sm + o.dk + 4 * i), st + a.sl.dk + 4 * i);
+        ptx::cp_async_16(ptx::smem_u32(sm + o.dv + 4 * i), st + a.sl.dv + 4 * i);
+        ptx::cp_async_16(ptx::smem_u32(s_dr + 4 * i), st + a.sl.dr + 4 * i);
+      }
+      if (tid < S4 / 4) ptx::cp_async_16(ptx::smem_u32(sm + o.ebits + 4 * tid), st + a.sl.ebits + 4 * tid);
+      ptx::cp_async_commit();
+      for (int i = tid; i < chunks; i += kTailThreads)
+        ptx::cp_async_16(ptx::smem_u32(s_e + 4 * i), st + a.sl.e + 4 * i);
+      ptx::cp_async_commit();
     }
     if (tid < S) {
-      long long t = a.tokens[static_cast<long long>(b) * a.token_stride + tid];
-      if (t < 0 || t >= a.vocab) t = 0;
-      s_tok[tid] = static_cast<int>(t);
+      long long tk = a.tokens[static_cast<long long>(b) * a.token_stride + tid];
+      if (tk < 0 || tk >= a.vocab) tk = 0;
+      s_tok[tid] = static_cast<int>(tk);
     }
-
-    // ---- B4: de = dr + [dq dk dv] Win ; dPos ; d(embedding rows) ------------------------------
-    ptx::mbar_wait(&bars[cur], phase);
-    {
-      float de[kRowsPerWarp];
-#pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) de[i] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        const float* src = j == 0 ? s_dq : (j == 1 ? s_dk : s_dv);
-        float2 wc[kE / 2];   // column `lane` of the j-th block of Win, packed along its rows
-#pragma unroll
-        for (int r = 0; r < kE / 2; ++r)
-          wc[r] = f2(sm[o.win + (32 * j + 2 * r) * kLdW + lane], sm[o.win + (32 * j + 2 * r + 1) * kLdW + lane]);
-#pragma unroll
-        for (int i = 0; i < kRowsPerWarp; ++i) {
-          const int s = warp + kWarps * i;
-          if (s < S) {
-            float2 acc0 = f2(0.f, 0.f), acc1 = f2(0.f, 0.f);
-#pragma unroll
-            for (int r4 = 0; r4 < kE / 4; ++r4) {
-              const float4 x = lds4(src + s * kE + 4 * r4);
-              acc0 = fma2(f2(x.x, x.y), wc[2 * r4], acc0);
-              acc1 = fma2(f2(x.z, x.w), wc[2 * r4 + 1], acc1);
-            }
-            de[i] += (acc0.x + acc0.y) + (acc1.x + acc1.y);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) {
-        const int s = warp + kWarps * i;
-        if (s < S) {
-          const float d = de[i] + s_dr[s * kE + lane];
-          g_pos[i] += d;
-          // through the embedding dropout: scale or zero
-          s_dr[s * kE + lane] = ((s_ebits[s] >> lane) & 1u) ? d * inv_e : 0.f;
-        }
-      }
-    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
 
-    // ---- B5: dWin (warps 0-11) | dbin, embedding scatter-add (warp 12) ------------------------
-    ptx::mbar_wait(&bars[2], phase_e);
-    if (warp < 12) {
-      // lane = input channel c; this warp owns rows [8w, 8w+8) of dWin (q | k | v blocks of 32)
-      const float* src = (warp < 4 ? s_dq : (warp < 8 ? s_dk : s_dv)) + 8 * (warp & 3);
-      float sum_b = 0.f;   // lanes 0-7: dbin[8w + lane]
+    // ---- B4: de = dr + [dq dk dv] Win ; dPos ; d(embedding rows) ------------------------------
+    if (16 * mt < S) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      float acc[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = 0.f;
 #pragma unroll 4
-      for (int s = 0; s < S; ++s) {
-        const float ev = s_e[s * kE + lane];
-        const float4 d0 = lds4(src + s * kE), d1 = lds4(src + s * kE + 4);
-        g_win[0] = fma2(f2(d0.x, d0.y), f2(ev, ev), g_win[0]);
-        g_win[1] = fma2(f2(d0.z, d0.w), f2(ev, ev), g_win[1]);
-        g_win[2] = fma2(f2(d1.x, d1.y), f2(ev, ev), g_win[2]);
-        g_win[3] = fma2(f2(d1.z, d1.w), f2(ev, ev), g_win[3]);
-        sum_b += src[s * kE + (lane & 7)];
+      for (int ks = 0; ks < 12; ++ks) {       // reduction index 32 j + kk: channel kk of dq (j = 0), dk, dv
+        const float* src = s_dq + (ks >> 2) * (o.rows * kLdT) + 8 * (ks & 3) + t;
+        uint32_t ah[4], al[4];
+        ptx::split_tf32(src[r0 * kLdT], ah[0], al[0]);
+        ptx::split_tf32(src[r1 * kLdT], ah[1], al[1]);
+        ptx::split_tf32(src[r0 * kLdT + 4], ah[2], al[2]);
+        ptx::split_tf32(src[r1 * kLdT + 4], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int wi = (8 * ks + t) * kLdT + 16 * nh + 8 * nt + g;     // Win[32 j + kk + t][column]
+          ptx::mma_3xtf32(acc[nt], ah, al, win_hi[wi], win_hi[wi + 4 * kLdT], win_lo[wi], win_lo[wi + 4 * kLdT]);
+        }
       }
-      g_bin += sum_b;
-    } else {
+      const uint32_t eb0 = r0 < S ? s_ebits[r0] : 0u, eb1 = r1 < S ? s_ebits[r1] : 0u;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int col = 16 * nh + 8 * nt + 2 * t;
+        if (r0 < S) {
+          const float2 dr = *reinterpret_cast<const float2*>(s_dr + r0 * kLdT + col);
+          const float d0 = acc[nt][0] + dr.x, d1 = acc[nt][1] + dr.y;
+          g_pos[nt][0] += d0;
+          g_pos[nt][1] += d1;
+          // through the embedding dropout: scale or zero
+          *reinterpret_cast<float2*>(s_de + r0 * kE + col) =
+              make_float2(((eb0 >> col) & 1u) ? d0 * inv_e : 0.f, ((eb0 >> (col + 1)) & 1u) ? d1 * inv_e : 0.f);
+        }
+        if (r1 < S) {
+          const float2 dr = *reinterpret_cast<const float2*>(s_dr + r1 * kLdT + col);
+          const float d2 = acc[nt][2] + dr.x, d3 = acc[nt][3] + dr.y;
+          g_pos[nt][2] += d2;
+          g_pos[nt][3] += d3;
+          *reinterpret_cast<float2*>(s_de + r1 * kE + col) =
+              make_float2(((eb1 >> col) & 1u) ? d2 * inv_e : 0.f, ((eb1 >> (col + 1)) & 1u) ? d3 * inv_e : 0.f);
+        }
+      }
+    }
+    ptx::cp_async_wait_all();     // e
+    __syncthreads();
+
+    // ---- B5: dWin, dbin (warps 0-11) | embedding scatter-add (warp 12) ------------------------
+    if (warp < 12) {
+      // rows of the tile = channels 16 (mt & 1) + {g, g+8} of dq (mt = 0, 1), dk (2, 3), dv (4, 5)
+      const float* src = s_dq + (mt >> 1) * (o.rows * kLdT) + 16 * (mt & 1) + g;
+      const int nk = (S + 7) >> 3;
+#pragma unroll 2
+      for (int ks = 0; ks < nk; ++ks) {
+        const int k0 = 8 * ks + t;
+        uint32_t ah[4], al[4];
+        ptx::split_tf32(src[k0 * kLdT], ah[0], al[0]);
+        ptx::split_tf32(src[k0 * kLdT + 8], ah[1], al[1]);
+        ptx::split_tf32(src[(k0 + 4) * kLdT], ah[2], al[2]);
+        ptx::split_tf32(src[(k0 + 4) * kLdT + 8], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const float* er = s_e + k0 * kLdT + 16 * nh + 8 * nt + g;
+          uint32_t bh0, bl0, bh1, bl1;
+          ptx::split_tf32(er[0], bh0, bl0);
+          ptx::split_tf32(er[4 * kLdT], bh1, bl1);
+          ptx::mma_3xtf32(g_win[nt], ah, al, bh0, bh1, bl0, bl1);
+        }
+        if (nh == 0) {   // warp-uniform: column sums through a tile of ones
+          ptx::mma_tf32(g_bin, al, one, one);
+          ptx::mma_tf32(g_bin, ah, one, one);
+        }
+      }
+    } else if (warp == 12) {
       // embedding scatter-add. Rows hit by several positions are summed in position order:
       // deterministic, no atomics. Operands are fetched four positions ahead of the dependent
       // read-modify-write chain on the table.
@@ -1175,8 +1194,8 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
         int s = 0;
         for (; s + 4 <= S; s += 4) {
           const int t0 = s_tok[s], t1 = s_tok[s + 1], t2 = s_tok[s + 2], t3 = s_tok[s + 3];
-          const float v0 = s_dr[s * kE + lane], v1 = s_dr[(s + 1) * kE + lane];
-          const float v2 = s_dr[(s + 2) * kE + lane], v3 = s_dr[(s + 3) * kE + lane];
+          const float v0 = s_de[s * kE + lane], v1 = s_de[(s + 1) * kE + lane];
+          const float v2 = s_de[(s + 2) * kE + lane], v3 = s_de[(s + 3) * kE + lane];
           hist[t0 * kE] += v0;
           hist[t1 * kE] += v1;
           hist[t2 * kE] += v2;
@@ -1184,14 +1203,14 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
           fsum += (v0 + v1) + (v2 + v3);
         }
         for (; s < S; ++s) {
-          const float v0 = s_dr[s * kE + lane];
+          const float v0 = s_de[s * kE + lane];
           hist[s_tok[s] * kE] += v0;
           fsum += v0;
         }
       } else {
         for (int s = 0; s < S; ++s) {
           float* pe = part + a.lay.off_emb + static_cast<long long>(s_tok[s]) * kE + lane;
-          const float v0 = s_dr[s * kE + lane];
+          const float v0 = s_de[s * kE + lane];
           __stcg(pe, __ldcg(pe) + v0);
           fsum += v0;
         }
@@ -1204,23 +1223,30 @@ __device__ __forceinline__ void frontend_backward_tail_body(const FrontArgs& a) 
   // ---- flush this CTA's partial sums ------------------------------------------------------
   if (warp < 12) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      part[a.lay.off_win + (8 * warp + 2 * i) * kE + lane] = g_win[i].x;
-      part[a.lay.off_win + (8 * warp + 2 * i + 1) * kE + lane] = g_win[i].y;
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = 16 * nh + 8 * nt + 2 * t;
+      float* w0 = part + a.lay.off_win + (16 * mt + g) * kE + col;
+      w0[0] = g_win[nt][0]; w0[1] = g_win[nt][1];
+      w0[8 * kE] = g_win[nt][2]; w0[8 * kE + 1] = g_win[nt][3];
     }
-    if (lane < 8) part[a.lay.off_bin + 8 * warp + lane] = g_bin;
+    if (nh == 0 && t == 0) {
+      part[a.lay.off_bin + 16 * mt + g] = g_bin[0];
+      part[a.lay.off_bin + 16 * mt + g + 8] = g_bin[2];
+    }
   }
+  // d(pos): rows of the tiles beyond L were never touched (stay zero) and are not part of the layout
 #pragma unroll
-  for (int i = 0; i < kRowsPerWarp; ++i) {
-    const int s = warp + kWarps * i;
-    if (s < a.L) part[a.lay.off_pos + s * kE + lane] = g_pos[i];
+  for (int nt = 0; nt < 2; ++nt) {
+    const int col = 16 * nh + 8 * nt + 2 * t, r0 = 16 * mt + g, r1 = r0 + 8;
+    if (r0 < a.L) { part[a.lay.off_pos + r0 * kE + col] = g_pos[nt][0]; part[a.lay.off_pos + r0 * kE + col + 1] = g_pos[nt][1]; }
+    if (r1 < a.L) { part[a.lay.off_pos + r1 * kE + col] = g_pos[nt][2]; part[a.lay.off_pos + r1 * kE + col + 1] = g_pos[nt][3]; }
   }
   if (hist_smem)
-    for (int i = tid; i < a.vocab * kE; i += kThreads) part[a.lay.off_emb + i] = sm[o.hist + i];
-  for (int i = tid; i < kMaxFonts * kE; i += kThreads) part[a.lay.off_font + i] = sm[o.fonth + i];
+    for (int i = tid; i < a.vocab * kE; i += kTailThreads) part[a.lay.off_emb + i] = sm[o.hist + i];
+  for (int i = tid; i < kMaxFonts * kE; i += kTailThreads) part[a.lay.off_font + i] = sm[o.fonth + i];
 }
 
-__global__ void __launch_bounds__(kThreads, 1) frontend_backward_tail_kernel(const FrontArgs a) {
+__global__ void __launch_bounds__(kTailThreads, 1) frontend_backward_tail_kernel(const FrontArgs a) {
   frontend_backward_tail_body(a);
 }
 __global__ void __maxnreg__(112) frontend_backward_tail_kernel_shared(const FrontArgs a) {
@@ -1392,11 +1418,11 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
   if (shared_sm) {
     if (only == 0 || only == 1) frontend_backward_head_kernel_shared<<<grid, kThreads, smem_head, stream>>>(a);
     if (only == 0 || only == 2) frontend_backward_attn_kernel_shared<<<grid_att, kAttThreads, smem_att, stream>>>(a);
-    if (only == 0 || only == 3) frontend_backward_tail_kernel_shared<<<grid, kThreads, smem_tail, stream>>>(a);
+    if (only == 0 || only == 3) frontend_backward_tail_kernel_shared<<<grid, kTailThreads, smem_tail, stream>>>(a);
   } else {
     if (only == 0 || only == 1) frontend_backward_head_kernel<<<grid, kThreads, smem_head, stream>>>(a);
     if (only == 0 || only == 2) frontend_backward_attn_kernel<<<grid_att, kAttThreads, smem_att, stream>>>(a);
-    if (only == 0 || only == 3) frontend_backward_tail_kernel<<<grid, kThreads, smem_tail, stream>>>(a);
+    if (only == 0 || only == 3) frontend_backward_tail_kernel<<<grid, kTailThreads, smem_tail, stream>>>(a);
   }
   return cudaGetLastError();
 }

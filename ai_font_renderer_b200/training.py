@@ -292,7 +292,10 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
         model.join_pending()
         after_dgrad = getattr(optimizer, "bg_after_dgrad", True) and max(1, optimizer.bg_chunks) == 1
         stages = optimizer.bg_stages or (BG_DEFAULT_STAGES if after_dgrad else BG_DEFAULT_STAGES_BESIDE_DGRAD)
-        model.set_smem_reserve(stages * 8192 + 1024)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        ring_ctas_per_sm = max(1, -(-int(optimizer.bg_ctas or 0) // sms))
+        reserve = ring_ctas_per_sm * (stages * 8192 + 1024)
+        model.set_smem_reserve(reserve)
         side = model.side_stream()
         chunks = row_buckets(P, max(1, optimizer.bg_chunks))
         last = len(chunks) - 1
@@ -330,7 +333,7 @@ def backward_and_step(model, optimizer, buckets, world: int, has_samples: bool =
                 mark("wgrad")
             if after_dgrad:
                 dgrad()
-                model.set_smem_reserve(stages * 8192 + 1024)
+                model.set_smem_reserve(reserve)
             ev = torch.cuda.Event()
             ev.record(main)
             with torch.cuda.stream(side):
