@@ -1,5 +1,5 @@
 F="--steps 30 --warmup 5 --no-cpu-baseline --no-gpu-eager --no-render"
-for args in "" "--bg-ctas 296 --bg-stages 4" "--bg-ctas 296 --bg-stages 3" "--bg-ctas 444 --bg-stages 2" "--bg-stages 6"; do
+for args in "--bg-chunks 2" "--bg-chunks 2 --bg-stages 6" "--bg-chunks 3" "--bg-chunks 2 --bg-stages 8"; do
   echo "== $args"
   python bench.py $F $args 2>&1 | tail -1 | python -c "
 import json,sys
