@@ -144,15 +144,49 @@ __device__ __forceinline__ void load_matrix(const float* __restrict__ g, float* 
 }
 
 // ============================================================================ forward kernel
+// 14 warps. The linear layers (in-projection, out-projection, fc1) run on warp-level TF32 MMAs
+// with 3-way split products (ptx::mma_3xtf32, fp32-equivalent: the 1e-5 tolerance holds): a warp
+// owns a 16-row tile and half (or all) of the output columns, the row tile's A fragment of one
+// k-step is split once and reused for all its column tiles. The FFMA2 forms (a lane per output
+// channel, the row broadcast by LDS.128) cost 43 k warp instructions per sample, these 11 k.
+// Activations and weights sit in shared memory as rows of 32 floats with their 4-float groups
+// XOR-swizzled by the row (group ^ (row & 7)): every fragment load hits 32 distinct banks with no
+// padding, and the attention phase's LDS.128 rows stay 16-byte aligned.
+constexpr int kFwdWarps = 14;
+constexpr int kFwdThreads = kFwdWarps * 32;
+
+__device__ __forceinline__ int swz(int row, int col) {   // word offset of (row, col) in a swizzled [rows][32] array
+  return row * kE + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
+}
+__device__ __forceinline__ void load_matrix_swz(const float* __restrict__ g, float* sm, int rows) {
+  for (int i = threadIdx.x; i < rows * kE; i += kFwdThreads) sm[swz(i / kE, i % kE)] = g[i];
+}
+// A fragment (rows r0, r1; columns 8 ks + {t, t + 4}) of a swizzled activation array, split
+__device__ __forceinline__ void load_a_frag(const float* x, int r0, int r1, int ks, int t, uint32_t (&ah)[4],
+                                            uint32_t (&al)[4]) {
+  ptx::split_tf32(x[swz(r0, 8 * ks + t)], ah[0], al[0]);
+  ptx::split_tf32(x[swz(r1, 8 * ks + t)], ah[1], al[1]);
+  ptx::split_tf32(x[swz(r0, 8 * ks + t + 4)], ah[2], al[2]);
+  ptx::split_tf32(x[swz(r1, 8 * ks + t + 4)], ah[3], al[3]);
+}
+// acc += A . W^T for output channels n0 .. n0 + 7 (W row-major [out][in], swizzled), one k-step
+__device__ __forceinline__ void mma_w(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                      const float* w, int n0, int ks, int g, int t) {
+  uint32_t bh0, bl0, bh1, bl1;
+  ptx::split_tf32(w[swz(n0 + g, 8 * ks + t)], bh0, bl0);
+  ptx::split_tf32(w[swz(n0 + g, 8 * ks + t + 4)], bh1, bl1);
+  ptx::mma_3xtf32(acc, ah, al, bh0, bh1, bl0, bl1);
+}
+
 struct FwdSmem {
   int win, wo, w1, bin, bo, lnw, lnb, b1, e, q, k, v, total;
 };
 __host__ __device__ inline FwdSmem make_fwd_smem(int L) {
   FwdSmem s{};
   int o = 0;
-  s.win = o; o += 3 * kE * kLdW;
-  s.wo = o;  o += kE * kLdW;
-  s.w1 = o;  o += kF * kLdW;
+  s.win = o; o += 3 * kE * kE;
+  s.wo = o;  o += kE * kE;
+  s.w1 = o;  o += kF * kE;
   s.bin = o; o += 3 * kE;
   s.bo = o;  o += kE;
   s.lnw = o; o += kE;
@@ -170,15 +204,15 @@ __host__ __device__ inline FwdSmem make_fwd_smem(int L) {
 __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
   extern __shared__ __align__(16) float sm[];
   const FwdSmem o = make_fwd_smem(a.L);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int S = a.S, KF = a.L * kF;
   const int mode = a.drop.mode;
 
-  load_matrix(a.w.win, sm + o.win, 3 * kE);
-  load_matrix(a.w.wo, sm + o.wo, kE);
-  load_matrix(a.w.w1, sm + o.w1, kF);
-  for (int i = tid; i < 3 * kE; i += kThreads) sm[o.bin + i] = a.w.bin[i];
-  for (int i = tid; i < kF; i += kThreads) sm[o.b1 + i] = a.w.b1[i];
+  load_matrix_swz(a.w.win, sm + o.win, 3 * kE);
+  load_matrix_swz(a.w.wo, sm + o.wo, kE);
+  load_matrix_swz(a.w.w1, sm + o.w1, kF);
+  for (int i = tid; i < 3 * kE; i += kFwdThreads) sm[o.bin + i] = a.w.bin[i];
+  for (int i = tid; i < kF; i += kFwdThreads) sm[o.b1 + i] = a.w.b1[i];
   if (tid < kE) {
     sm[o.bo + tid] = a.w.bo[tid];
     sm[o.lnw + tid] = a.w.lnw[tid];
@@ -190,6 +224,7 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
   float* sq = sm + o.q;
   float* sk = sm + o.k;
   float* sv = sm + o.v;
+  const int ntile_rows = (S + 15) >> 4;     // 16-row tiles of this batch
 
   AFR_TICK_DECL
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -201,16 +236,16 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
 
     // ---- (1) e = dropout(Emb[tok]) + Pos        model.py:167-172 (dropout BEFORE positions)
     // one thread per 8 channels = one Philox block
-    for (int base = 0; base < S * 4; base += kThreads) {
+    for (int base = 0; base < S * 4; base += kFwdThreads) {
       const int i8 = base + tid;
       const bool valid = i8 < S * 4;
       uint32_t keep8 = 0xFFu;
       if (valid) {
         const int s = i8 >> 2, c0 = (i8 & 3) * 8;
-        long long t = tok[s];
-        if (t < 0 || t >= a.vocab) { atomicOr(a.err_flag, 1); t = 0; }
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.w.emb + t * kE + c0));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.w.emb + t * kE + c0 + 4));
+        long long tk = tok[s];
+        if (tk < 0 || tk >= a.vocab) { atomicOr(a.err_flag, 1); tk = 0; }
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(a.w.emb + tk * kE + c0));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(a.w.emb + tk * kE + c0 + 4));
         const float4 p0 = __ldg(reinterpret_cast<const float4*>(a.w.pos + s * kE + c0));
         const float4 p1 = __ldg(reinterpret_cast<const float4*>(a.w.pos + s * kE + c0 + 4));
         if (mode == 1) {
@@ -241,8 +276,12 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           ov[u] = ((keep8 >> u) & 1u) ? fmaf(ev[u], a.inv_e, pv[u]) : pv[u];
-        *reinterpret_cast<float4*>(se + s * kE + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        *reinterpret_cast<float4*>(se + s * kE + c0 + 4) = make_float4(ov[4], ov[5], ov[6], ov[7]);
+        *reinterpret_cast<float4*>(se + swz(s, c0)) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<float4*>(se + swz(s, c0 + 4)) = make_float4(ov[4], ov[5], ov[6], ov[7]);
+        if (st != nullptr) {     // the record's copy (backward: dWin), rows of kLdT floats
+          *reinterpret_cast<float4*>(st + a.sl.e + s * kLdT + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+          *reinterpret_cast<float4*>(st + a.sl.e + s * kLdT + c0 + 4) = make_float4(ov[4], ov[5], ov[6], ov[7]);
+        }
       }
       if (st != nullptr) {   // 32 keep bits per position, assembled from the 4 threads of the row
         uint32_t wbits = keep8 << (8 * (tid & 3));
@@ -256,28 +295,39 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
     AFR_TICK(2);
 
     // ---- (2) packed in-projection q|k|v = e Win^T + bin  (torch functional.py:5836) -----------
-    // lane = output channel; its weight row lives in registers, the e row is broadcast.
-#pragma unroll 1
-    for (int j = 0; j < 3; ++j) {
-      float2 w2[kE / 2];
+    // warp = (row tile, half of the 96 output channels)
+    if ((warp >> 1) < ntile_rows) {
+      const int mt = warp >> 1, nb = 48 * (warp & 1);
+      const int r0 = 16 * mt + g, r1 = r0 + 8, q0 = min(r0, S - 1), q1 = min(r1, S - 1);
+      float acc[6][4];
 #pragma unroll
-      for (int c = 0; c < kE / 2; ++c)
-        w2[c] = f2(sm[o.win + (32 * j + lane) * kLdW + 2 * c], sm[o.win + (32 * j + lane) * kLdW + 2 * c + 1]);
-      const float bias = sm[o.bin + 32 * j + lane];
-      const float scale = j == 0 ? kInvSqrtDh * kLog2e : 1.f;   // q also carries log2(e): ex2 soft-max
-      float* dst = j == 0 ? sq : (j == 1 ? sk : sv);
-      float* gdst = st != nullptr ? st + (j == 0 ? a.sl.q : (j == 1 ? a.sl.k : a.sl.v)) : nullptr;
-      for (int s = warp; s < S; s += kWarps) {
-        float2 acc = f2(bias, 0.f);
+      for (int nt = 0; nt < 6; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-        for (int c4 = 0; c4 < kE / 4; ++c4) {
-          const float4 x = lds4(se + s * kE + 4 * c4);
-          acc = fma2(f2(x.x, x.y), w2[2 * c4], acc);
-          acc = fma2(f2(x.z, x.w), w2[2 * c4 + 1], acc);
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[4], al[4];
+        load_a_frag(se, q0, q1, ks, t, ah, al);
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) mma_w(acc[nt], ah, al, sm + o.win, nb + 8 * nt, ks, g, t);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        const int n = nb + 8 * nt + 2 * t, j = n >> 5, ch = n & 31;     // j: 0 = q, 1 = k, 2 = v
+        const float scale = j == 0 ? kInvSqrtDh * kLog2e : 1.f;          // q also carries log2(e): ex2 soft-max
+        const float b0 = sm[o.bin + n], b1 = sm[o.bin + n + 1];
+        float* dst = j == 0 ? sq : (j == 1 ? sk : sv);
+        float* gdst = st != nullptr ? st + (j == 0 ? a.sl.q : (j == 1 ? a.sl.k : a.sl.v)) : nullptr;
+        // q (later: the context, A operand of the out-projection) is swizzled; k and v are only read
+        // row by row by the attention phase and stay plain
+        if (r0 < S) {
+          const float2 v = make_float2((acc[nt][0] + b0) * scale, (acc[nt][1] + b1) * scale);
+          *reinterpret_cast<float2*>(dst + (j == 0 ? swz(r0, ch) : r0 * kE + ch)) = v;
+          if (gdst != nullptr) *reinterpret_cast<float2*>(gdst + r0 * kE + ch) = v;
         }
-        const float r = (acc.x + acc.y) * scale;
-        dst[s * kE + lane] = r;
-        if (gdst != nullptr) gdst[s * kE + lane] = r;
+        if (r1 < S) {
+          const float2 v = make_float2((acc[nt][2] + b0) * scale, (acc[nt][3] + b1) * scale);
+          *reinterpret_cast<float2*>(dst + (j == 0 ? swz(r1, ch) : r1 * kE + ch)) = v;
+          if (gdst != nullptr) *reinterpret_cast<float2*>(gdst + r1 * kE + ch) = v;
+        }
       }
     }
     AFR_TICK(3);
@@ -285,12 +335,12 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
     AFR_TICK(4);
 
     // ---- (3) per (query s, head h): ctx = dropout(softmax(q k^T)) v   (functional.py:6642-6647)
-    for (int i = tid; i < S * kHeads; i += kThreads) {
+    for (int i = tid; i < S * kHeads; i += kFwdThreads) {
       int h, s;
       slot_to_pair(i, S, h, s);
       float2 q2[4];
       {
-        const float4 q0 = lds4(sq + s * kE + h * kDh), q1 = lds4(sq + s * kE + h * kDh + 4);
+        const float4 q0 = lds4(sq + swz(s, h * kDh)), q1 = lds4(sq + swz(s, h * kDh + 4));
         q2[0] = f2(q0.x, q0.y); q2[1] = f2(q0.z, q0.w); q2[2] = f2(q1.x, q1.y); q2[3] = f2(q1.z, q1.w);
       }
       float m = -INFINITY, l = 0.f;
@@ -360,9 +410,9 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
       const float linv = 1.f / l;
       const float scale = a.inv_a * linv;
       // q of this (s, h) is dead: the context vector takes its place
-      *reinterpret_cast<float4*>(sq + s * kE + h * kDh) =
+      *reinterpret_cast<float4*>(sq + swz(s, h * kDh)) =
           make_float4(acc[0].x * scale, acc[0].y * scale, acc[1].x * scale, acc[1].y * scale);
-      *reinterpret_cast<float4*>(sq + s * kE + h * kDh + 4) =
+      *reinterpret_cast<float4*>(sq + swz(s, h * kDh + 4)) =
           make_float4(acc[2].x * scale, acc[2].y * scale, acc[3].x * scale, acc[3].y * scale);
       if (st != nullptr)
         *reinterpret_cast<float4*>(st + a.sl.stat + (s * kHeads + h) * 4) = make_float4(m, linv, 0.f, 0.f);
@@ -372,114 +422,162 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
     AFR_TICK(6);
 
     // ---- (4a) out-projection + residual + LayerNorm (model.py:180); h overwrites e ----------
-    {
-      float2 wo2[kE / 2];
+    // warp = row tile with all 32 output channels: the row statistics stay inside a quad
+    if (warp < ntile_rows) {
+      const int r0 = 16 * warp + g, r1 = r0 + 8, q0 = min(r0, S - 1), q1 = min(r1, S - 1);
+      float acc[4][4];
 #pragma unroll
-      for (int c = 0; c < kE / 2; ++c)
-        wo2[c] = f2(sm[o.wo + lane * kLdW + 2 * c], sm[o.wo + lane * kLdW + 2 * c + 1]);
-      const float bo = sm[o.bo + lane], gam = sm[o.lnw + lane], bet = sm[o.lnb + lane];
-      for (int s = warp; s < S; s += kWarps) {
-        float2 acc = f2(bo, 0.f);
+      for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-        for (int j4 = 0; j4 < kE / 4; ++j4) {
-          const float4 x = lds4(sq + s * kE + 4 * j4);
-          acc = fma2(f2(x.x, x.y), wo2[2 * j4], acc);
-          acc = fma2(f2(x.z, x.w), wo2[2 * j4 + 1], acc);
-        }
-        const float ev = se[s * kE + lane];
-        const float r = ev + (acc.x + acc.y);              // residual uses the dropped+positioned e
-        const float mean = warp_sum(r) * (1.f / kE);
-        const float d = r - mean;
-        const float var = warp_sum(d * d) * (1.f / kE);    // biased variance, eps = 1e-5
-        const float rstd = 1.f / sqrtf(var + 1e-5f);
-        const float xhat = d * rstd;
-        if (st != nullptr) {
-          st[a.sl.e + s * kLdT + lane] = ev;
-          st[a.sl.ctx + s * kE + lane] = sq[s * kE + lane];
-          st[a.sl.xhat + s * kE + lane] = xhat;
-          if (lane == 0) st[a.sl.rstd + s] = rstd;
-        }
-        se[s * kE + lane] = fmaf(xhat, gam, bet);
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[4], al[4];
+        load_a_frag(sq, q0, q1, ks, t, ah, al);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_w(acc[nt], ah, al, sm + o.wo, 8 * nt, ks, g, t);
       }
+      // residual uses the dropped + positioned e; rows r0 (elements 0, 1) and r1 (2, 3)
+      float ev[4][4];
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        const float2 ea = *reinterpret_cast<const float2*>(se + swz(q0, c));
+        const float2 eb = *reinterpret_cast<const float2*>(se + swz(q1, c));
+        const float bo0 = sm[o.bo + c], bo1 = sm[o.bo + c + 1];
+        ev[nt][0] = ea.x; ev[nt][1] = ea.y; ev[nt][2] = eb.x; ev[nt][3] = eb.y;
+        acc[nt][0] += ea.x + bo0; acc[nt][1] += ea.y + bo1;
+        acc[nt][2] += eb.x + bo0; acc[nt][3] += eb.y + bo1;
+        sa += acc[nt][0] + acc[nt][1];
+        sb += acc[nt][2] + acc[nt][3];
+      }
+      sa += __shfl_xor_sync(0xffffffffu, sa, 1); sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+      sa += __shfl_xor_sync(0xffffffffu, sa, 2); sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      const float mean_a = sa * (1.f / kE), mean_b = sb * (1.f / kE);
+      float va = 0.f, vb = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] -= mean_a; acc[nt][1] -= mean_a; acc[nt][2] -= mean_b; acc[nt][3] -= mean_b;
+        va = fmaf(acc[nt][0], acc[nt][0], va); va = fmaf(acc[nt][1], acc[nt][1], va);
+        vb = fmaf(acc[nt][2], acc[nt][2], vb); vb = fmaf(acc[nt][3], acc[nt][3], vb);
+      }
+      va += __shfl_xor_sync(0xffffffffu, va, 1); vb += __shfl_xor_sync(0xffffffffu, vb, 1);
+      va += __shfl_xor_sync(0xffffffffu, va, 2); vb += __shfl_xor_sync(0xffffffffu, vb, 2);
+      const float rstd_a = 1.f / sqrtf(va * (1.f / kE) + 1e-5f);    // biased variance, eps = 1e-5
+      const float rstd_b = 1.f / sqrtf(vb * (1.f / kE) + 1e-5f);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        const float g0 = sm[o.lnw + c], g1 = sm[o.lnw + c + 1], be0 = sm[o.lnb + c], be1 = sm[o.lnb + c + 1];
+        const float xa0 = acc[nt][0] * rstd_a, xa1 = acc[nt][1] * rstd_a;
+        const float xb0 = acc[nt][2] * rstd_b, xb1 = acc[nt][3] * rstd_b;
+        if (r0 < S) {
+          if (st != nullptr) {
+            *reinterpret_cast<float2*>(st + a.sl.ctx + r0 * kE + c) = *reinterpret_cast<const float2*>(sq + swz(r0, c));
+            *reinterpret_cast<float2*>(st + a.sl.xhat + r0 * kE + c) = make_float2(xa0, xa1);
+          }
+          *reinterpret_cast<float2*>(se + swz(r0, c)) = make_float2(fmaf(xa0, g0, be0), fmaf(xa1, g1, be1));
+        }
+        if (r1 < S) {
+          if (st != nullptr) {
+            *reinterpret_cast<float2*>(st + a.sl.ctx + r1 * kE + c) = *reinterpret_cast<const float2*>(sq + swz(r1, c));
+            *reinterpret_cast<float2*>(st + a.sl.xhat + r1 * kE + c) = make_float2(xb0, xb1);
+          }
+          *reinterpret_cast<float2*>(se + swz(r1, c)) = make_float2(fmaf(xb0, g0, be0), fmaf(xb1, g1, be1));
+        }
+      }
+      if (st != nullptr && t == 0) {
+        if (r0 < S) st[a.sl.rstd + r0] = rstd_a;
+        if (r1 < S) st[a.sl.rstd + r1] = rstd_b;
+      }
+      (void)ev;
     }
-    __syncwarp();   // (4b) reads only the rows this warp wrote in (4a)
+    __syncthreads();   // (4b) reads rows other warps normalised
     AFR_TICK(7);
 
-    // ---- (4b) f = dropout(relu(fc1(h)))  (model.py:183-184). lane owns features 2*lane, 2*lane+1
-    {
-      float2 acc[kRowsPerWarp];
-      const float2 bias = f2(sm[o.b1 + 2 * lane], sm[o.b1 + 2 * lane + 1]);
+    // ---- (4b) f = dropout(relu(fc1(h)))  (model.py:183-184). warp = (row tile, half of the 64 features)
+    if ((warp >> 1) < ntile_rows) {
+      const int mt = warp >> 1, nh = warp & 1;
+      const int r0 = 16 * mt + g, r1 = r0 + 8, q0 = min(r0, S - 1), q1 = min(r1, S - 1);
+      float acc[4][4];
 #pragma unroll
-      for (int i = 0; i < kRowsPerWarp; ++i) acc[i] = bias;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float2 w2[kE / 2];
+      for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-        for (int c = 0; c < kE / 2; ++c)
-          w2[c] = f2(sm[o.w1 + (2 * lane) * kLdW + 16 * half + c],
-                     sm[o.w1 + (2 * lane + 1) * kLdW + 16 * half + c]);
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ah[4], al[4];
+        load_a_frag(se, q0, q1, ks, t, ah, al);
 #pragma unroll
-        for (int i = 0; i < kRowsPerWarp; ++i) {
-          const int s = warp + kWarps * i;
-          if (s < S) {
+        for (int nt = 0; nt < 4; ++nt) mma_w(acc[nt], ah, al, sm + o.w1, 32 * nh + 8 * nt, ks, g, t);
+      }
+      // keep decisions: Philox block (row, 8-feature group) = one column tile of one row. Lane t of a
+      // quad draws the blocks of row (t & 1 ? r1 : r0) for column tiles (t >> 1) and (t >> 1) + 2; the
+      // 8 keep bits of a block reach the other lanes by shuffle.
+      uint32_t keepm[2] = {0xFFu, 0xFFu};
+      if (mode == 1) {
+        const int my_row = (t & 1) ? q1 : q0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float4 x = lds4(se + s * kE + 16 * half + 4 * u);
-              acc[i] = fma2(f2(x.x, x.x), w2[4 * u], acc[i]);
-              acc[i] = fma2(f2(x.y, x.y), w2[4 * u + 1], acc[i]);
-              acc[i] = fma2(f2(x.z, x.z), w2[4 * u + 2], acc[i]);
-              acc[i] = fma2(f2(x.w, x.w), w2[4 * u + 3], acc[i]);
-            }
-          }
+        for (int w = 0; w < 2; ++w) {
+          const int jt = 4 * nh + (t >> 1) + 2 * w;     // 8-feature group of the row
+          const uint4 r = rng.block(2u, static_cast<uint32_t>(my_row * (kF / 8) + jt));
+          keepm[w] = (u16_of<0>(r) >= a.thr_f ? 1u : 0u) | (u16_of<1>(r) >= a.thr_f ? 2u : 0u) |
+                     (u16_of<2>(r) >= a.thr_f ? 4u : 0u) | (u16_of<3>(r) >= a.thr_f ? 8u : 0u) |
+                     (u16_of<4>(r) >= a.thr_f ? 16u : 0u) | (u16_of<5>(r) >= a.thr_f ? 32u : 0u) |
+                     (u16_of<6>(r) >= a.thr_f ? 64u : 0u) | (u16_of<7>(r) >= a.thr_f ? 128u : 0u);
         }
       }
       __nv_bfloat16* out = a.feats + static_cast<long long>(b) * KF;
-      // Rows in groups of four: a row's 64 keep decisions are 8 Philox blocks (block j = features
-      // 8j .. 8j+7, lane l needs 16-bit words 2(l & 3), 2(l & 3) + 1 of block l >> 2). Lane l draws
-      // block (l & 7) of the group's row (l >> 3) -- 32 distinct blocks per group instead of every
-      // lane drawing its own copy per row -- and the words travel by shuffle.
+      const int quad = lane & ~3;
+      uint32_t fb0a = 0, fb1a = 0, fb0b = 0, fb1b = 0;   // (ReLU' & keep) bits of rows r0 / r1: even / odd features
 #pragma unroll
-      for (int grp = 0; grp < (kRowsPerWarp + 3) / 4; ++grp) {
-        uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = 32 * nh + 8 * nt + 2 * t;
+        const float b0 = sm[o.b1 + n], b1 = sm[o.b1 + n + 1];
+        float fa0 = fmaxf(acc[nt][0] + b0, 0.f), fa1 = fmaxf(acc[nt][1] + b1, 0.f);   // ReLU
+        float fc0 = fmaxf(acc[nt][2] + b0, 0.f), fc1 = fmaxf(acc[nt][3] + b1, 0.f);
+        bool ka0 = true, ka1 = true, kc0 = true, kc1 = true;
         if (mode == 1) {
-          const int s_mine = warp + kWarps * (4 * grp + (lane >> 3));   // rows >= S: drawn, never used
-          r4 = rng.block(2u, static_cast<uint32_t>(s_mine * (kF / 8) + (lane & 7)));
+          // column tile nt of row r0 was drawn by quad lane 2 (nt & 1), of row r1 by lane 2 (nt & 1) + 1, as block nt >> 1
+          const uint32_t ma = __shfl_sync(0xffffffffu, keepm[nt >> 1], quad + 2 * (nt & 1)) >> (2 * t);
+          const uint32_t mc = __shfl_sync(0xffffffffu, keepm[nt >> 1], quad + 2 * (nt & 1) + 1) >> (2 * t);
+          ka0 = ma & 1u; ka1 = ma & 2u; kc0 = mc & 1u; kc1 = mc & 2u;
+        } else if (mode == 2) {
+          const uint8_t* mka = a.drop.mask_fc1 + (static_cast<long long>(b) * S + q0) * kF + n;
+          const uint8_t* mkc = a.drop.mask_fc1 + (static_cast<long long>(b) * S + q1) * kF + n;
+          ka0 = mka[0] != 0; ka1 = mka[1] != 0; kc0 = mkc[0] != 0; kc1 = mkc[1] != 0;
         }
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int i = 4 * grp + rr;
-          if (i >= kRowsPerWarp) continue;
-          const int s = warp + kWarps * i;
-          if (s < S) {   // warp-uniform
-            float fa = fmaxf(acc[i].x, 0.f), fb = fmaxf(acc[i].y, 0.f);   // ReLU
-            bool ka = true, kb = true;
-            if (mode == 1) {
-              const int src = 8 * rr + (lane >> 2);
-              const uint32_t w0 = __shfl_sync(0xffffffffu, r4.x, src), w1 = __shfl_sync(0xffffffffu, r4.y, src);
-              const uint32_t w2 = __shfl_sync(0xffffffffu, r4.z, src), w3 = __shfl_sync(0xffffffffu, r4.w, src);
-              const uint32_t word = (lane & 2) ? ((lane & 1) ? w3 : w2) : ((lane & 1) ? w1 : w0);
-              ka = (word & 0xFFFFu) >= a.thr_f;
-              kb = (word >> 16) >= a.thr_f;
-            } else if (mode == 2) {
-              const uint8_t* mk = a.drop.mask_fc1 + (static_cast<long long>(b) * S + s) * kF;
-              ka = mk[2 * lane] != 0;
-              kb = mk[2 * lane + 1] != 0;
-            }
-            const bool pa = ka && fa > 0.f, pb = kb && fb > 0.f;
-            fa = ka ? fa * a.inv_f : 0.f;
-            fb = kb ? fb * a.inv_f : 0.f;
-            *reinterpret_cast<__nv_bfloat162*>(out + s * kF + 2 * lane) = __floats2bfloat162_rn(fa, fb);
-            if (a.feats_f32 != nullptr)
-              *reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF + s * kF + 2 * lane) =
-                  make_float2(fa, fb);
-            const uint32_t w0b = __ballot_sync(0xffffffffu, pa), w1b = __ballot_sync(0xffffffffu, pb);
-            if (st != nullptr && lane == 0)
-              *reinterpret_cast<uint2*>(st + a.sl.fbits + 2 * s) = make_uint2(w0b, w1b);
-          }
+        const int bit = 4 * nt + t;      // feature 2 (16 nh + bit) (+ 1): bit `bit` of this warp's 16-bit half
+        fb0a |= (ka0 && fa0 > 0.f ? 1u : 0u) << bit; fb1a |= (ka1 && fa1 > 0.f ? 1u : 0u) << bit;
+        fb0b |= (kc0 && fc0 > 0.f ? 1u : 0u) << bit; fb1b |= (kc1 && fc1 > 0.f ? 1u : 0u) << bit;
+        fa0 = ka0 ? fa0 * a.inv_f : 0.f; fa1 = ka1 ? fa1 * a.inv_f : 0.f;
+        fc0 = kc0 ? fc0 * a.inv_f : 0.f; fc1 = kc1 ? fc1 * a.inv_f : 0.f;
+        if (r0 < S) {
+          *reinterpret_cast<__nv_bfloat162*>(out + r0 * kF + n) = __floats2bfloat162_rn(fa0, fa1);
+          if (a.feats_f32 != nullptr)
+            *reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF + r0 * kF + n) = make_float2(fa0, fa1);
+        }
+        if (r1 < S) {
+          *reinterpret_cast<__nv_bfloat162*>(out + r1 * kF + n) = __floats2bfloat162_rn(fc0, fc1);
+          if (a.feats_f32 != nullptr)
+            *reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF + r1 * kF + n) = make_float2(fc0, fc1);
         }
       }
+      if (st != nullptr) {
+        // fbits[s] = (word of the even features, word of the odd features), bit j = feature 2j / 2j + 1:
+        // this warp owns bits 16 nh .. 16 nh + 15 of both words
+        fb0a |= __shfl_xor_sync(0xffffffffu, fb0a, 1); fb1a |= __shfl_xor_sync(0xffffffffu, fb1a, 1);
+        fb0b |= __shfl_xor_sync(0xffffffffu, fb0b, 1); fb1b |= __shfl_xor_sync(0xffffffffu, fb1b, 1);
+        fb0a |= __shfl_xor_sync(0xffffffffu, fb0a, 2); fb1a |= __shfl_xor_sync(0xffffffffu, fb1a, 2);
+        fb0b |= __shfl_xor_sync(0xffffffffu, fb0b, 2); fb1b |= __shfl_xor_sync(0xffffffffu, fb1b, 2);
+        if (t == 0) {
+          uint16_t* fw = reinterpret_cast<uint16_t*>(st + a.sl.fbits);
+          if (r0 < S) { fw[4 * r0 + nh] = static_cast<uint16_t>(fb0a); fw[4 * r0 + 2 + nh] = static_cast<uint16_t>(fb1a); }
+          if (r1 < S) { fw[4 * r1 + nh] = static_cast<uint16_t>(fb0b); fw[4 * r1 + 2 + nh] = static_cast<uint16_t>(fb1b); }
+        }
+      }
+    }
+    {
+      __nv_bfloat16* out = a.feats + static_cast<long long>(b) * KF;
       // zero features for positions >= S (model.py:190-193)
-      for (int i = S * kF / 2 + tid; i < KF / 2; i += kThreads) {
+      for (int i = S * kF / 2 + tid; i < KF / 2; i += kFwdThreads) {
         reinterpret_cast<__nv_bfloat162*>(out)[i] = __floats2bfloat162_rn(0.f, 0.f);
         if (a.feats_f32 != nullptr)
           reinterpret_cast<float2*>(a.feats_f32 + static_cast<long long>(b) * KF)[i] = make_float2(0.f, 0.f);
@@ -492,12 +590,12 @@ __device__ __forceinline__ void frontend_forward_body(const FrontArgs& a) {
   AFR_TICK_FLUSH(0);
 }
 
-__global__ void __launch_bounds__(kThreads, 2) frontend_forward_kernel(const FrontArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 2) frontend_forward_kernel(const FrontArgs a) {
   frontend_forward_body(a);
 }
-// Capped at 64 registers (72 otherwise; a few spills): two CTAs of 13 warps put 7 warps on two
-// of the SM's four scheduler partitions, 7 x 72 x 32 registers leave no room there for a warp of
-// another kernel; at 64 the background AdamW sweep's CTA (4 warps x 40 registers) fits beside both.
+// Capped at 64 registers: two CTAs of 14 warps put 7 warps on each of the SM's four scheduler
+// partitions, 7 x 72 x 32 registers leave no room there for a warp of another kernel; at 64 the
+// background AdamW sweep's CTA (4 warps x 40 registers) fits beside both.
 __global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a) {
   frontend_forward_body(a);
 }
@@ -1364,8 +1462,8 @@ cudaError_t launch_frontend_forward(const Tensors& w, const long long* tokens, l
   }
   int grid = num_sms * 2;
   if (grid > B) grid = B;
-  if (shared_sm) frontend_forward_kernel_shared<<<grid, kThreads, smem, stream>>>(a);
-  else frontend_forward_kernel<<<grid, kThreads, smem, stream>>>(a);
+  if (shared_sm) frontend_forward_kernel_shared<<<grid, kFwdThreads, smem, stream>>>(a);
+  else frontend_forward_kernel<<<grid, kFwdThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
