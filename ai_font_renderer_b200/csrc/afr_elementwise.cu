@@ -339,7 +339,8 @@ __device__ __forceinline__ uint4 ld_reduce_mc_bf16(const __nv_bfloat16* g_mc, lo
                : "memory");
   return s;
 }
-__global__ void __launch_bounds__(1024, 1)
+constexpr int kGatherNvlsThreads = 512;   // 128 registers per thread: 16 reductions of 16 B in flight each
+__global__ void __launch_bounds__(kGatherNvlsThreads, 1)
 adamw_gather_nvls_bf16_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long long n8,
                               AdamHyper h, const __nv_bfloat16* g_mc, __nv_bfloat16* sh_mc) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -354,12 +355,16 @@ adamw_gather_nvls_bf16_kernel(float* __restrict__ p, float* __restrict__ m, floa
                  "r"(packed.x), "r"(packed.y), "r"(packed.z), "r"(packed.w)
                  : "memory");
   };
-  for (; i + 3 * stride < n8; i += 4 * stride) {
-    uint4 s[4];
+  // 16 in-switch reductions (16 B each) in flight per thread: the round trip through the NVSwitch is
+  // ~2.5 us, so a CTA's link throughput is its bytes in flight over that (12 CTAs x 1024 threads x
+  // 64 B = 0.79 MB gave 336 GB/s at 8 GPUs: 0.64 ms for the exchange, the longest chain of the step)
+  constexpr int kDepth = 16;
+  for (; i + (kDepth - 1) * stride < n8; i += kDepth * stride) {
+    uint4 s[kDepth];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] = ld_reduce_mc_bf16(g_mc, i + u * stride);
+    for (int u = 0; u < kDepth; ++u) s[u] = ld_reduce_mc_bf16(g_mc, i + u * stride);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) one(i + u * stride, s[u]);
+    for (int u = 0; u < kDepth; ++u) one(i + u * stride, s[u]);
   }
   for (; i < n8; i += stride) one(i, ld_reduce_mc_bf16(g_mc, i));
 }
@@ -575,7 +580,7 @@ cudaError_t launch_adamw_gather_nvls_bf16(float* p, float* m, float* v, long lon
                                           const __nv_bfloat16* g_mc, __nv_bfloat16* sh_mc, int ctas,
                                           cudaStream_t s) {
   if ((n % 8) != 0 || ctas < 1 || g_mc == nullptr || sh_mc == nullptr) return cudaErrorInvalidValue;
-  adamw_gather_nvls_bf16_kernel<<<ctas, 1024, 0, s>>>(p, m, v, n / 8, h, g_mc, sh_mc);
+  adamw_gather_nvls_bf16_kernel<<<ctas, kGatherNvlsThreads, 0, s>>>(p, m, v, n / 8, h, g_mc, sh_mc);
   return cudaGetLastError();
 }
 
