@@ -143,7 +143,8 @@ class PeerLink:
         --comm-ctas sweeps): the owned shard -- and with it the kernel's local HBM work -- shrinks
         with the number of ranks while its NVLink volume stays, so fewer SMs saturate it. With bf16
         gradient rows the link volume halves and the kernel hides under the rest of backward on
-        half as many SMs (8 GPUs, profiles/r02: 24 CTAs 1.40 ms/step, 16: 1.29, 12: 1.27)."""
+        half as many SMs (8 GPUs, profiles/r02: 24 CTAs 1.40 ms/step, 16: 1.29, 12: 1.27; with the final
+        kernels 12: 1.204, 16 and 20 no better, 8: 1.28)."""
         if grad_bf16:
             return 32 if world <= 2 else (20 if world <= 4 else 12)
         return 48 if world <= 2 else (32 if world <= 4 else 24)
