@@ -4,21 +4,24 @@
 // MHA follows torch.nn.functional.multi_head_attention_forward (packed in-proj, q scaled by
 // sqrt(1/head_dim), softmax over all S keys with no padding mask, dropout on probabilities).
 //
-// 2.5 MFLOP/sample, S = 100 and head_dim = 8: this does not tile onto tcgen05, and it has to hold
-// the fp32 tolerance (1e-5), so it is fp32 SIMT built around what sm_100a's SIMT side is good at
-// (measured, tools/microbench/fp32_rates.cu): packed FFMA2 (118 FMA/clk/SM in half the issue
-// slots of FFMA) fed by warp-uniform LDS.128 (one clock per warp).
-//   * 13-warp CTAs (416 threads >= 4 heads x 100 queries), a whole sample in shared memory.
-//     Attention runs one thread per (query, head) with head-uniform warps, so every K/V row is a
-//     broadcast load; the soft-max is an online one over blocks of 8 keys in the log2 domain
-//     (MUFU.EX2); the linear layers run one warp per position with the lane's weight row/column
-//     in registers and the activation row broadcast.
-//   * The training forward leaves a 86 KB record per sample (e, q, k, v, context, normalised
-//     residual, soft-max statistics and every dropout decision as bit masks). The backward (three
-//     kernels, see below) stages it into shared memory with cp.async.bulk + mbarriers / cp.async:
-//     no random number is drawn twice; its attention part runs on warp-level TF32 MMAs (3xTF32).
+// 2.5 MFLOP/sample forward, S = 100, E = 32, head_dim = 8: far below a tcgen05 tile, and it has to
+// hold the fp32 tolerance (1e-5 forward / 5e-5 backward against the oracle). Two tools:
+//   * warp-level TF32 MMAs with 3-way split products (ptx::mma_3xtf32: fp32-equivalent; one HMMA
+//     issues per 2.2 clocks per SM, tools/microbench/mma_rates.cu) for every linear layer of the
+//     forward, for the attention backward and for the in-projection part of the backward: a
+//     fragment load replaces eight broadcast LDS and the accumulators of the weight gradients live
+//     in the MMA accumulator layout across all samples of a CTA;
+//   * packed FFMA2 (118 FMA/clk/SM in half the issue slots of FFMA, tools/microbench/
+//     fp32_rates.cu) fed by warp-uniform LDS.128 where the shapes do not pay for fragments: the
+//     forward attention (one thread per (query, head), head-uniform warps, online soft-max over
+//     blocks of 8 keys in the log2 domain, MUFU.EX2) and the head of the backward.
+// A whole sample sits in shared memory per CTA.
+//   * The training forward leaves a record per sample (e, q, k, v, context, normalised residual,
+//     soft-max statistics and every dropout decision as bit masks; FrontStateLayout). The backward
+//     (three kernels, see below) stages it back in and hands its intermediates from kernel to
+//     kernel through the same record: no random number is drawn twice.
 //   * The ten small weight gradients accumulate in registers across all samples of a CTA and
-//     leave as per-CTA partials that a second kernel sums in a fixed order: deterministic, no
+//     leave as per-CTA partials that a last kernel sums in a fixed order: deterministic, no
 //     float atomics. The embedding scatter-add is a per-CTA shared-memory table walked in
 //     position order by one warp.
 #include <cstdlib>
@@ -36,7 +39,7 @@ using ptx::ex2;
 using ptx::fma2;
 using ptx::mul2;
 
-constexpr int kThreads = 416;
+constexpr int kThreads = 416;                                   // head kernel of the backward: 13 warps
 constexpr int kWarps = kThreads / 32;                           // 13
 constexpr int kRowsPerWarp = (kMaxL + kWarps - 1) / kWarps;     // 10
 constexpr int kLdW = kE + 1;                                    // padded weight rows in smem

@@ -121,8 +121,8 @@ import ctypes as _C
 
 _SMALL_GROUP = None
 # ring depth of the background AdamW sweep: stages x 8 KB (+ the 1 KB the hardware reserves per CTA)
-# of every SM's shared memory are left to it; 8 stages fit beside the front-end kernels' 2 x 78 KB
-# (forward), 82 / 2 x 76 / 96 KB (backward). With the sweep starting before the dgrad GEMM
+# of every SM's shared memory are left to it; 8 stages fit beside the front-end kernels' 2 x 76 KB
+# (forward), 131 / 2 x 76 / 151 KB (backward head / attention / tail). With the sweep starting before the dgrad GEMM
 # (bg_after_dgrad = False) 4 stages are the better trade: the GEMM's operand ring pays for them.
 BG_DEFAULT_STAGES = 8
 BG_DEFAULT_STAGES_BESIDE_DGRAD = 4
