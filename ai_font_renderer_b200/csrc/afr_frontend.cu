@@ -615,272 +615,313 @@ __global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a
 // of its time in the attention phase. Split, the attention part takes two CTAs of 14 warps per SM.
 
 // ---------------------------------------------------------------- K1: head of the backward
+// dh = df W1 with the LayerNorm backward on the accumulator fragments (B1), d(ctx) = dr Wo with
+// D = d(ctx) . ctx per head (B1b), dW1 += df^T h, dWo += dr^T ctx, db1, dbo (B2): all as 3xTF32
+// warp MMAs like the tail kernel. W1 and Wo are split into TF32 hi / lo words once per CTA. Rows
+// of 40 floats (xhat / h, dr, ctx) and 72 floats (df): 8t + g is a distinct bank for every lane of
+// the B / A^T fragment loads, row-major A loads are 2-way. Rows beyond S are zero and pad the
+// reductions over positions. 14 warps: 7 row tiles for B1 / B1b (the row statistics of the
+// LayerNorm stay inside a quad), 8 + 4 tiles of the weight gradients for B2.
+constexpr int kHeadWarps = 14;
+constexpr int kHeadThreads = kHeadWarps * 32;
+constexpr int kLdF = kF + 8;      // row stride of df
+
 struct HeadSmem {
-  int w1, wo, lnw, stage[2], stage_words, xhat, df, ctx, fbits, rstd, dr, red, bars, total;   // xhat .. rstd: offsets inside a stage
+  int w1_hi, w1_lo, wo_hi, wo_lo, lnw, lnb, xh, df, dr, ctx, fbits, rstd, red, rows, total;
 };
 __host__ __device__ inline HeadSmem make_head_smem(int L) {
   const int L4 = (L + 3) & ~3;
   HeadSmem s{};
+  s.rows = (L + 15) & ~15;
   int o = 0;
-  s.w1 = o;  o += kF * kLdW;
-  s.wo = o;  o += kE * kLdW;
+  s.w1_hi = o; o += kF * kLdT;
+  s.w1_lo = o; o += kF * kLdT;
+  s.wo_hi = o; o += kE * kLdT;
+  s.wo_lo = o; o += kE * kLdT;
   s.lnw = o; o += kE;
-  o = (o + 3) & ~3;
-  // the staged operands of a sample, twice: sample i + 1 loads while sample i computes
-  int q = 0;
-  s.xhat = q; q += L * kE;        // xhat -> h (B1)
-  s.df = q;   q += L * kF;        // dfeat -> df (B1)
-  s.ctx = q;  q += L * kE;
-  s.fbits = q; q += L4 * 2;
-  s.rstd = q; q += L4;
-  s.stage_words = (q + 3) & ~3;
-  s.stage[0] = o; o += s.stage_words;
-  s.stage[1] = o; o += s.stage_words;
-  s.dr = o;   o += L * kE;        // d(residual)
-  s.red = o;  o += kWarps * kE * 2;
-  o = (o + 3) & ~3;
-  s.bars = o; o += 8;             // 2 x 2 mbarriers
-  s.total = o;
+  s.lnb = o; o += kE;
+  s.xh = o;  o += s.rows * kLdT;     // xhat -> h (B1)
+  s.dr = o;  o += s.rows * kLdT;     // d(residual)
+  s.ctx = o; o += s.rows * kLdT;
+  s.df = o;  o += s.rows * kLdF;     // dfeat -> df
+  s.fbits = o; o += L4 * 2;
+  s.rstd = o; o += L4;
+  s.red = o;  o += 2 * 7 * kE;       // d(LayerNorm weight / bias) partials of the 7 row-tile warps
+  s.total = (o + 3) & ~3;
   return s;
 }
 
 __device__ __forceinline__ void frontend_backward_head_body(const FrontArgs& a) {
   extern __shared__ __align__(16) float sm[];
   const HeadSmem o = make_head_smem(a.L);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int S = a.S, S4 = (S + 3) & ~3, KF = a.L * kF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + o.bars);
   float* part = a.partials + static_cast<long long>(blockIdx.x) * a.lay.total;
 
-  load_matrix(a.w.w1, sm + o.w1, kF);
-  load_matrix(a.w.wo, sm + o.wo, kE);
-  if (tid < kE) sm[o.lnw + tid] = a.w.lnw[tid];
-  if (tid == 0) {
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bars[i], 1);
-    ptx::fence_mbar_init();
+  uint32_t* w1_hi = reinterpret_cast<uint32_t*>(sm + o.w1_hi);
+  uint32_t* w1_lo = reinterpret_cast<uint32_t*>(sm + o.w1_lo);
+  uint32_t* wo_hi = reinterpret_cast<uint32_t*>(sm + o.wo_hi);
+  uint32_t* wo_lo = reinterpret_cast<uint32_t*>(sm + o.wo_lo);
+  for (int i = tid; i < kF * kE; i += kHeadThreads) {
+    uint32_t hi, lo;
+    ptx::split_tf32(a.w.w1[i], hi, lo);
+    w1_hi[(i / kE) * kLdT + (i % kE)] = hi;
+    w1_lo[(i / kE) * kLdT + (i % kE)] = lo;
   }
+  for (int i = tid; i < kE * kE; i += kHeadThreads) {
+    uint32_t hi, lo;
+    ptx::split_tf32(a.w.wo[i], hi, lo);
+    wo_hi[(i / kE) * kLdT + (i % kE)] = hi;
+    wo_lo[(i / kE) * kLdT + (i % kE)] = lo;
+  }
+  if (tid < kE) {
+    sm[o.lnw + tid] = a.w.lnw[tid];
+    sm[o.lnb + tid] = a.w.lnb[tid];
+  }
+  // rows >= S of xhat / h, dr, ctx, df stay zero (xh, dr, ctx, df are contiguous)
+  for (int i = tid; i < 3 * o.rows * kLdT + o.rows * kLdF; i += kHeadThreads) sm[o.xh + i] = 0.f;
   __syncthreads();
 
+  float* s_xh = sm + o.xh;
+  float* s_df = sm + o.df;
   float* s_dr = sm + o.dr;
+  float* s_ctx = sm + o.ctx;
+  const uint32_t* s_fbits = reinterpret_cast<const uint32_t*>(sm + o.fbits);
+  const float* s_rstd = sm + o.rstd;
 
-  // gradient accumulators that live in registers for the whole kernel
-  // (lane = input channel c; a warp owns a band of output rows)
-  float2 g_wa[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};    // warps 0-7: dW1[8w+2i, 8w+2i+1][c];
-                                                                // warps 8-11: dWo[8(w-8)+2i, +1][c]
-  float g_vec = 0.f;               // lanes 0-7 of warps 0-7: db1[8w+lane]; of warps 8-11: dbo[8(w-8)+lane]
-  float g_gam = 0.f, g_bet = 0.f;  // (warp, lane = channel) partial of d(LayerNorm weight / bias)
+  // accumulators that live in registers for the whole kernel (MMA accumulator layout)
+  float g_w[2][4];     // B2 unit: dW1 (warps 0-7) / dWo (warps 8-11) rows 16 mt + {g, g+8}, cols 16 nh + 8 nt + {2t, 2t+1}
+  float g_b[4];        // B2, nh == 0: db1 / dbo of those rows (every column of the ones-tile holds the sum)
+  float g_gam[4][2], g_bet[4][2];   // warps 0-6: d(LayerNorm weight / bias) of columns 8 nt + {2t, 2t+1}, this lane's rows
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    g_w[0][i] = g_w[1][i] = g_b[i] = 0.f;
+    g_gam[i][0] = g_gam[i][1] = g_bet[i][0] = g_bet[i][1] = 0.f;
+  }
 
   const float inv_a = a.inv_a, inv_f = a.inv_f;
+  const uint32_t one = __float_as_uint(1.f);
+  const int n_row_tiles = (S + 15) >> 4;
 
-  // stage sample b's operands into buffer `buf`: two groups, each waited for right before its first use
-  auto issue = [&](int b, int buf) {
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     float* st = a.state + static_cast<long long>(b) * a.sl.stride;
-    float* base = sm + o.stage[0] + buf * o.stage_words;
-    uint64_t* bar = bars + 2 * buf;
-    const uint32_t row_bytes = static_cast<uint32_t>(S) * kE * 4u;
-    ptx::mbar_arrive_expect_tx(&bar[0], row_bytes + 2u * row_bytes + S4 * 8u + S4 * 4u);
-    ptx::bulk_load_1d(base + o.xhat, st + a.sl.xhat, row_bytes, &bar[0]);
-    ptx::bulk_load_1d(base + o.df, a.dfeat + static_cast<long long>(b) * KF, 2u * row_bytes, &bar[0]);
-    ptx::bulk_load_1d(base + o.fbits, st + a.sl.fbits, S4 * 8u, &bar[0]);
-    ptx::bulk_load_1d(base + o.rstd, st + a.sl.rstd, S4 * 4u, &bar[0]);
-    ptx::mbar_arrive_expect_tx(&bar[1], row_bytes);
-    ptx::bulk_load_1d(base + o.ctx, st + a.sl.ctx, row_bytes, &bar[1]);
-  };
-  if (tid == 0 && static_cast<int>(blockIdx.x) < a.B) issue(blockIdx.x, 0);
-
-  int it = 0;
-  for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
-    float* st = a.state + static_cast<long long>(b) * a.sl.stride;
-    const int cur = it & 1;
-    const uint32_t phase = static_cast<uint32_t>(it >> 1) & 1u;
-    uint64_t* bar = bars + 2 * cur;
-    float* s_xhat = sm + (o.stage[0] + cur * o.stage_words) + o.xhat;
-    float* s_df = sm + (o.stage[0] + cur * o.stage_words) + o.df;
-    float* s_ctx = sm + (o.stage[0] + cur * o.stage_words) + o.ctx;
-    const uint32_t* s_fbits = reinterpret_cast<const uint32_t*>(sm + (o.stage[0] + cur * o.stage_words) + o.fbits);
-    const float* s_rstd = sm + (o.stage[0] + cur * o.stage_words) + o.rstd;
-    // the next sample's operands load into the other buffer while this one computes (cp.async.bulk
-    // moves ~8 B/clk per CTA: 64 KB exposed per sample was a third of this kernel's time)
-    ptx::fence_proxy_async_smem();   // order the previous sample's generic smem traffic first
-    __syncthreads();
-    if (tid == 0 && b + static_cast<int>(gridDim.x) < a.B) issue(b + gridDim.x, cur ^ 1);
-
-    // ---- B1: df = dfeat * ReLU' * dropout ; dh = df W1 ; LayerNorm backward -> dr ; h --------
-    ptx::mbar_wait(&bar[0], phase);
+    __syncthreads();     // every warp is done with the previous sample's operands
     {
-      float2 w1c[kF / 2];   // column `lane` of W1, packed along the feature index
+      const float* gx = st + a.sl.xhat;
+      const float* gc = st + a.sl.ctx;
+      const float* gd = a.dfeat + static_cast<long long>(b) * KF;
+      for (int i = tid; i < S * (kE / 4); i += kHeadThreads) {
+        const int row = i >> 3, c4 = (i & 7) * 4;
+        ptx::cp_async_16(ptx::smem_u32(s_xh + row * kLdT + c4), gx + row * kE + c4);
+        ptx::cp_async_16(ptx::smem_u32(s_ctx + row * kLdT + c4), gc + row * kE + c4);
+      }
+      for (int i = tid; i < S * (kF / 4); i += kHeadThreads) {
+        const int row = i >> 4, c4 = (i & 15) * 4;
+        ptx::cp_async_16(ptx::smem_u32(s_df + row * kLdF + c4), gd + row * kF + c4);
+      }
+      if (tid < S4 / 2) ptx::cp_async_16(ptx::smem_u32(sm + o.fbits + 4 * tid), st + a.sl.fbits + 4 * tid);
+      if (tid < S4 / 4) ptx::cp_async_16(ptx::smem_u32(sm + o.rstd + 4 * tid), st + a.sl.rstd + 4 * tid);
+      ptx::cp_async_commit();
+      ptx::cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---- df = dfeat * ReLU' * dropout: thread = (position, feature pair 2j, 2j + 1) --------------
+    for (int i = tid; i < S * (kF / 2); i += kHeadThreads) {
+      const int s = i >> 5, j = i & 31;
+      float2 d = *reinterpret_cast<const float2*>(s_df + s * kLdF + 2 * j);
+      d.x = ((s_fbits[2 * s] >> j) & 1u) ? d.x * inv_f : 0.f;
+      d.y = ((s_fbits[2 * s + 1] >> j) & 1u) ? d.y * inv_f : 0.f;
+      *reinterpret_cast<float2*>(s_df + s * kLdF + 2 * j) = d;
+    }
+    __syncthreads();
+
+    // ---- B1: dh = df W1 ; LayerNorm backward -> dr ; h.  B1b: dctx = dr Wo, D ------------------
+    if (warp < n_row_tiles) {
+      const int r0 = 16 * warp + g, r1 = r0 + 8;
+      float acc[4][4];
 #pragma unroll
-      for (int j = 0; j < kF / 2; ++j)
-        w1c[j] = f2(sm[o.w1 + (2 * j) * kLdW + lane], sm[o.w1 + (2 * j + 1) * kLdW + lane]);
-      const float gam = sm[o.lnw + lane], bet = a.w.lnb[lane];
-      float* g_dr = st + a.sl.dr;
-      // two rows per iteration: their dependent chains (LDS -> FFMA2 chain -> butterflies) interleave
-      for (int s0 = warp; s0 < S; s0 += 2 * kWarps) {
-        const int s1 = s0 + kWarps;
-        const bool two = s1 < S;                  // warp-uniform
-        const int sb = two ? s1 : s0;             // row b aliases row a when there is no second row
-        const float xh_a = s_xhat[s0 * kE + lane], xh_b = s_xhat[sb * kE + lane];
-        const float rs_a = s_rstd[s0], rs_b = s_rstd[sb];
-        {
-          float2 da = *reinterpret_cast<const float2*>(s_df + s0 * kF + 2 * lane);
-          const uint32_t a0 = s_fbits[2 * s0], a1 = s_fbits[2 * s0 + 1];
-          da.x = ((a0 >> lane) & 1u) ? da.x * inv_f : 0.f;
-          da.y = ((a1 >> lane) & 1u) ? da.y * inv_f : 0.f;
-          *reinterpret_cast<float2*>(s_df + s0 * kF + 2 * lane) = da;
-          if (two) {
-            float2 db = *reinterpret_cast<const float2*>(s_df + s1 * kF + 2 * lane);
-            const uint32_t b0 = s_fbits[2 * s1], b1 = s_fbits[2 * s1 + 1];
-            db.x = ((b0 >> lane) & 1u) ? db.x * inv_f : 0.f;
-            db.y = ((b1 >> lane) & 1u) ? db.y * inv_f : 0.f;
-            *reinterpret_cast<float2*>(s_df + s1 * kF + 2 * lane) = db;
-          }
-        }
-        __syncwarp();
-        float2 acc_a0 = f2(0.f, 0.f), acc_a1 = f2(0.f, 0.f), acc_b0 = f2(0.f, 0.f), acc_b1 = f2(0.f, 0.f);
+      for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll 2
+      for (int ks = 0; ks < kF / 8; ++ks) {
+        uint32_t ah[4], al[4];
+        ptx::split_tf32(s_df[r0 * kLdF + 8 * ks + t], ah[0], al[0]);
+        ptx::split_tf32(s_df[r1 * kLdF + 8 * ks + t], ah[1], al[1]);
+        ptx::split_tf32(s_df[r0 * kLdF + 8 * ks + t + 4], ah[2], al[2]);
+        ptx::split_tf32(s_df[r1 * kLdF + 8 * ks + t + 4], ah[3], al[3]);
 #pragma unroll
-        for (int j4 = 0; j4 < kF / 4; ++j4) {
-          const float4 xa = lds4(s_df + s0 * kF + 4 * j4);
-          const float4 xb = lds4(s_df + sb * kF + 4 * j4);
-          acc_a0 = fma2(f2(xa.x, xa.y), w1c[2 * j4], acc_a0);
-          acc_a1 = fma2(f2(xa.z, xa.w), w1c[2 * j4 + 1], acc_a1);
-          acc_b0 = fma2(f2(xb.x, xb.y), w1c[2 * j4], acc_b0);
-          acc_b1 = fma2(f2(xb.z, xb.w), w1c[2 * j4 + 1], acc_b1);
-        }
-        const float dh_a = (acc_a0.x + acc_a0.y) + (acc_a1.x + acc_a1.y);
-        const float dh_b = (acc_b0.x + acc_b0.y) + (acc_b1.x + acc_b1.y);
-        g_gam = fmaf(dh_a, xh_a, g_gam);
-        g_bet += dh_a;
-        if (two) {
-          g_gam = fmaf(dh_b, xh_b, g_gam);
-          g_bet += dh_b;
-        }
-        const float dhg_a = dh_a * gam, dhg_b = dh_b * gam;
-        float m1a = dhg_a, m2a = dhg_a * xh_a, m1b = dhg_b, m2b = dhg_b * xh_b;
-        warp_sum2(m1a, m2a);
-        warp_sum2(m1b, m2b);
-        const float dr_a = rs_a * (dhg_a - m1a * (1.f / kE) - xh_a * (m2a * (1.f / kE)));
-        s_dr[s0 * kE + lane] = dr_a;
-        g_dr[s0 * kLdT + lane] = dr_a;                   // for K3
-        s_xhat[s0 * kE + lane] = fmaf(xh_a, gam, bet);   // h, for dW1
-        if (two) {
-          const float dr_b = rs_b * (dhg_b - m1b * (1.f / kE) - xh_b * (m2b * (1.f / kE)));
-          s_dr[s1 * kE + lane] = dr_b;
-          g_dr[s1 * kLdT + lane] = dr_b;
-          s_xhat[s1 * kE + lane] = fmaf(xh_b, gam, bet);
+        for (int nt = 0; nt < 4; ++nt) {
+          const int wi = (8 * ks + t) * kLdT + 8 * nt + g;       // W1[feature 8 ks + t (+ 4)][channel]
+          ptx::mma_3xtf32(acc[nt], ah, al, w1_hi[wi], w1_hi[wi + 4 * kLdT], w1_lo[wi], w1_lo[wi + 4 * kLdT]);
         }
       }
-    }
-    // ---- B1b: dctx = dr Wo and D = dctx . ctx for the rows this warp just produced (for K2) -----
-    ptx::mbar_wait(&bar[1], phase);   // ctx
-    __syncwarp();
-    {
-      float2 woc[kE / 2];   // column `lane` of Wo, packed along the output channel
+      // LayerNorm backward on the fragments: rows r0 (elements 0, 1) and r1 (2, 3), 8 columns per lane
+      float xa[4][2], xb[4][2];
+      float m1a = 0.f, m2a = 0.f, m1b = 0.f, m2b = 0.f;
 #pragma unroll
-      for (int c = 0; c < kE / 2; ++c)
-        woc[c] = f2(sm[o.wo + (2 * c) * kLdW + lane], sm[o.wo + (2 * c + 1) * kLdW + lane]);
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        const float2 x0 = *reinterpret_cast<const float2*>(s_xh + r0 * kLdT + c);
+        const float2 x1 = *reinterpret_cast<const float2*>(s_xh + r1 * kLdT + c);
+        const float gm0 = sm[o.lnw + c], gm1 = sm[o.lnw + c + 1];
+        xa[nt][0] = x0.x; xa[nt][1] = x0.y; xb[nt][0] = x1.x; xb[nt][1] = x1.y;
+        // rows beyond S: df = 0 -> dh = 0, xhat = 0: they add nothing
+        g_gam[nt][0] = fmaf(acc[nt][0], x0.x, g_gam[nt][0]); g_gam[nt][1] = fmaf(acc[nt][1], x0.y, g_gam[nt][1]);
+        g_gam[nt][0] = fmaf(acc[nt][2], x1.x, g_gam[nt][0]); g_gam[nt][1] = fmaf(acc[nt][3], x1.y, g_gam[nt][1]);
+        g_bet[nt][0] += acc[nt][0] + acc[nt][2];
+        g_bet[nt][1] += acc[nt][1] + acc[nt][3];
+        acc[nt][0] *= gm0; acc[nt][1] *= gm1; acc[nt][2] *= gm0; acc[nt][3] *= gm1;   // dh * gamma
+        m1a += acc[nt][0] + acc[nt][1];
+        m2a = fmaf(acc[nt][0], x0.x, m2a); m2a = fmaf(acc[nt][1], x0.y, m2a);
+        m1b += acc[nt][2] + acc[nt][3];
+        m2b = fmaf(acc[nt][2], x1.x, m2b); m2b = fmaf(acc[nt][3], x1.y, m2b);
+      }
+#pragma unroll
+      for (int msk = 1; msk <= 2; msk <<= 1) {
+        m1a += __shfl_xor_sync(0xffffffffu, m1a, msk); m2a += __shfl_xor_sync(0xffffffffu, m2a, msk);
+        m1b += __shfl_xor_sync(0xffffffffu, m1b, msk); m2b += __shfl_xor_sync(0xffffffffu, m2b, msk);
+      }
+      m1a *= (1.f / kE); m2a *= (1.f / kE); m1b *= (1.f / kE); m2b *= (1.f / kE);
+      const float rs_a = r0 < S ? s_rstd[r0] : 0.f, rs_b = r1 < S ? s_rstd[r1] : 0.f;
+      float* g_dr = st + a.sl.dr;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c = 8 * nt + 2 * t;
+        const float gm0 = sm[o.lnw + c], gm1 = sm[o.lnw + c + 1], be0 = sm[o.lnb + c], be1 = sm[o.lnb + c + 1];
+        if (r0 < S) {
+          const float2 d = make_float2(rs_a * (acc[nt][0] - m1a - xa[nt][0] * m2a), rs_a * (acc[nt][1] - m1a - xa[nt][1] * m2a));
+          *reinterpret_cast<float2*>(s_dr + r0 * kLdT + c) = d;
+          *reinterpret_cast<float2*>(g_dr + r0 * kLdT + c) = d;                 // for the tail kernel
+          *reinterpret_cast<float2*>(s_xh + r0 * kLdT + c) = make_float2(fmaf(xa[nt][0], gm0, be0), fmaf(xa[nt][1], gm1, be1));   // h, for dW1
+        }
+        if (r1 < S) {
+          const float2 d = make_float2(rs_b * (acc[nt][2] - m1b - xb[nt][0] * m2b), rs_b * (acc[nt][3] - m1b - xb[nt][1] * m2b));
+          *reinterpret_cast<float2*>(s_dr + r1 * kLdT + c) = d;
+          *reinterpret_cast<float2*>(g_dr + r1 * kLdT + c) = d;
+          *reinterpret_cast<float2*>(s_xh + r1 * kLdT + c) = make_float2(fmaf(xb[nt][0], gm0, be0), fmaf(xb[nt][1], gm1, be1));
+        }
+      }
+      __syncwarp();
+      // B1b: d(ctx) = dr Wo for the same rows; D[s][head] = sum over the head's 8 channels of d(ctx) * ctx
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < kE / 8; ++ks) {
+        uint32_t ah[4], al[4];
+        ptx::split_tf32(s_dr[r0 * kLdT + 8 * ks + t], ah[0], al[0]);
+        ptx::split_tf32(s_dr[r1 * kLdT + 8 * ks + t], ah[1], al[1]);
+        ptx::split_tf32(s_dr[r0 * kLdT + 8 * ks + t + 4], ah[2], al[2]);
+        ptx::split_tf32(s_dr[r1 * kLdT + 8 * ks + t + 4], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int wi = (8 * ks + t) * kLdT + 8 * nt + g;       // Wo[out channel 8 ks + t (+ 4)][ctx channel]
+          ptx::mma_3xtf32(acc[nt], ah, al, wo_hi[wi], wo_hi[wi + 4 * kLdT], wo_lo[wi], wo_lo[wi + 4 * kLdT]);
+        }
+      }
       float* g_dc = st + a.sl.dctx;
       float* g_stat = st + a.sl.stat;
-      for (int s0 = warp; s0 < S; s0 += 2 * kWarps) {
-        const int s1 = s0 + kWarps;
-        const bool two = s1 < S;
-        const int sb = two ? s1 : s0;
-        float2 a0 = f2(0.f, 0.f), a1 = f2(0.f, 0.f), b0 = f2(0.f, 0.f), b1 = f2(0.f, 0.f);
 #pragma unroll
-        for (int c4 = 0; c4 < kE / 4; ++c4) {
-          const float4 xa = lds4(s_dr + s0 * kE + 4 * c4);
-          const float4 xb = lds4(s_dr + sb * kE + 4 * c4);
-          a0 = fma2(f2(xa.x, xa.y), woc[2 * c4], a0);
-          a1 = fma2(f2(xa.z, xa.w), woc[2 * c4 + 1], a1);
-          b0 = fma2(f2(xb.x, xb.y), woc[2 * c4], b0);
-          b1 = fma2(f2(xb.z, xb.w), woc[2 * c4 + 1], b1);
+      for (int nt = 0; nt < 4; ++nt) {          // column tile nt = head nt
+        const int c = 8 * nt + 2 * t;
+        const float2 ca = *reinterpret_cast<const float2*>(s_ctx + r0 * kLdT + c);
+        const float2 cb = *reinterpret_cast<const float2*>(s_ctx + r1 * kLdT + c);
+        float pa = acc[nt][0] * ca.x + acc[nt][1] * ca.y, pb = acc[nt][2] * cb.x + acc[nt][3] * cb.y;
+        pa += __shfl_xor_sync(0xffffffffu, pa, 1); pb += __shfl_xor_sync(0xffffffffu, pb, 1);
+        pa += __shfl_xor_sync(0xffffffffu, pa, 2); pb += __shfl_xor_sync(0xffffffffu, pb, 2);
+        if (r0 < S) {
+          *reinterpret_cast<float2*>(g_dc + r0 * kE + c) = make_float2(acc[nt][0] * inv_a, acc[nt][1] * inv_a);   // d(P_dropped) carries 1 / (1 - p)
+          if (t == 0) g_stat[(r0 * kHeads + nt) * 4 + 2] = pa;
         }
-        const float dca = (a0.x + a0.y) + (a1.x + a1.y), dcb = (b0.x + b0.y) + (b1.x + b1.y);
-        // D[s][h] = sum_{j in head h} dctx[s][j] * ctx[s][j]   (= sum_t P_dropped dP)
-        float pa = dca * s_ctx[s0 * kE + lane], pb = dcb * s_ctx[sb * kE + lane];
-#pragma unroll
-        for (int m = 1; m <= 4; m <<= 1) {
-          const float qa = __shfl_xor_sync(0xffffffffu, pa, m), qb = __shfl_xor_sync(0xffffffffu, pb, m);
-          pa += qa;
-          pb += qb;
-        }
-        g_dc[s0 * kE + lane] = dca * inv_a;    // d(P_dropped) = d(ctx) V^T carries 1 / (1 - p)
-        if ((lane & 7) == 0) g_stat[(s0 * kHeads + (lane >> 3)) * 4 + 2] = pa;
-        if (two) {
-          g_dc[s1 * kE + lane] = dcb * inv_a;
-          if ((lane & 7) == 0) g_stat[(s1 * kHeads + (lane >> 3)) * 4 + 2] = pb;
+        if (r1 < S) {
+          *reinterpret_cast<float2*>(g_dc + r1 * kE + c) = make_float2(acc[nt][2] * inv_a, acc[nt][3] * inv_a);
+          if (t == 0) g_stat[(r1 * kHeads + nt) * 4 + 2] = pb;
         }
       }
     }
     __syncthreads();
 
     // ---- B2: dW1, db1 (warps 0-7) | dWo, dbo (warps 8-11) --------------------------------------
-    // lane = input channel c; a warp owns 8 output rows: per position one conflict-free scalar
-    // load of the lane's own operand and warp-uniform LDS.128 of the row operand (1 clock each;
-    // any non-uniform LDS.128 costs 4).
-    if (warp < 8) {
-      const float* dfw = s_df + 8 * warp;
-      float sum_b = 0.f;                  // lanes 0-7: db1[8w + lane]
-#pragma unroll 4
-      for (int s = 0; s < S; ++s) {
-        const float h = s_xhat[s * kE + lane];
-        const float4 d0 = lds4(dfw + s * kF), d1 = lds4(dfw + s * kF + 4);
-        g_wa[0] = fma2(f2(d0.x, d0.y), f2(h, h), g_wa[0]);
-        g_wa[1] = fma2(f2(d0.z, d0.w), f2(h, h), g_wa[1]);
-        g_wa[2] = fma2(f2(d1.x, d1.y), f2(h, h), g_wa[2]);
-        g_wa[3] = fma2(f2(d1.z, d1.w), f2(h, h), g_wa[3]);
-        sum_b += dfw[s * kF + (lane & 7)];
+    if (warp < 12) {
+      const bool w1part = warp < 8;
+      const int mt = w1part ? (warp >> 1) : ((warp - 8) >> 1), nh = warp & 1;
+      // A^T: rows of the tile = features (df) / out-projection outputs (dr) 16 mt + {g, g+8}
+      const float* src = w1part ? s_df + 16 * mt + g : s_dr + 16 * mt + g;
+      const int lds = w1part ? kLdF : kLdT;
+      const float* bsrc = (w1part ? s_xh : s_ctx) + 16 * nh + g;       // h (dW1) / ctx (dWo)
+      const int nk = (S + 7) >> 3;
+#pragma unroll 2
+      for (int ks = 0; ks < nk; ++ks) {
+        const int k0 = 8 * ks + t;
+        uint32_t ah[4], al[4];
+        ptx::split_tf32(src[k0 * lds], ah[0], al[0]);
+        ptx::split_tf32(src[k0 * lds + 8], ah[1], al[1]);
+        ptx::split_tf32(src[(k0 + 4) * lds], ah[2], al[2]);
+        ptx::split_tf32(src[(k0 + 4) * lds + 8], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          uint32_t bh0, bl0, bh1, bl1;
+          ptx::split_tf32(bsrc[k0 * kLdT + 8 * nt], bh0, bl0);
+          ptx::split_tf32(bsrc[(k0 + 4) * kLdT + 8 * nt], bh1, bl1);
+          ptx::mma_3xtf32(g_w[nt], ah, al, bh0, bh1, bl0, bl1);
+        }
+        if (nh == 0) {   // warp-uniform: column sums through a tile of ones
+          ptx::mma_tf32(g_b, al, one, one);
+          ptx::mma_tf32(g_b, ah, one, one);
+        }
       }
-      g_vec += sum_b;
-    } else if (warp < 12) {
-      const float* drw = s_dr + 8 * (warp - 8);
-      float sum_b = 0.f;                  // lanes 0-7: dbo[8(w-8) + lane]
-#pragma unroll 4
-      for (int s = 0; s < S; ++s) {
-        const float x = s_ctx[s * kE + lane];
-        const float4 r0 = lds4(drw + s * kE), r1 = lds4(drw + s * kE + 4);
-        g_wa[0] = fma2(f2(r0.x, r0.y), f2(x, x), g_wa[0]);
-        g_wa[1] = fma2(f2(r0.z, r0.w), f2(x, x), g_wa[1]);
-        g_wa[2] = fma2(f2(r1.x, r1.y), f2(x, x), g_wa[2]);
-        g_wa[3] = fma2(f2(r1.z, r1.w), f2(x, x), g_wa[3]);
-        sum_b += drw[s * kE + (lane & 7)];
-      }
-      g_vec += sum_b;
     }
   }
   __syncthreads();
 
   // ---- flush this CTA's partial sums ------------------------------------------------------
-  sm[o.red + warp * kE + lane] = g_gam;
-  sm[o.red + (kWarps + warp) * kE + lane] = g_bet;
+  if (warp < 7) {
+    // d(LayerNorm weight / bias): sum this lane's columns over the 8 row groups g, then over the warps
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float x = g_gam[nt][e], y = g_bet[nt][e];
+#pragma unroll
+        for (int msk = 4; msk <= 16; msk <<= 1) {
+          x += __shfl_xor_sync(0xffffffffu, x, msk);
+          y += __shfl_xor_sync(0xffffffffu, y, msk);
+        }
+        if (g == 0) {
+          sm[o.red + warp * kE + 8 * nt + 2 * t + e] = x;
+          sm[o.red + (7 + warp) * kE + 8 * nt + 2 * t + e] = y;
+        }
+      }
+  }
   __syncthreads();
   if (tid < 2 * kE) {
     const int which = tid >> 5, c = tid & 31;
     float acc = 0.f;
-    for (int w = 0; w < kWarps; ++w) acc += sm[o.red + (which * kWarps + w) * kE + c];
+    for (int w = 0; w < 7; ++w) acc += sm[o.red + (which * 7 + w) * kE + c];
     part[(which == 0 ? a.lay.off_lnw : a.lay.off_lnb) + c] = acc;
   }
-  if (warp < 8) {
+  if (warp < 12) {
+    const bool w1part = warp < 8;
+    const int mt = w1part ? (warp >> 1) : ((warp - 8) >> 1), nh = warp & 1;
+    float* wbase = part + (w1part ? a.lay.off_w1 : a.lay.off_wo);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      part[a.lay.off_w1 + (8 * warp + 2 * i) * kE + lane] = g_wa[i].x;
-      part[a.lay.off_w1 + (8 * warp + 2 * i + 1) * kE + lane] = g_wa[i].y;
+    for (int nt = 0; nt < 2; ++nt) {
+      float* w0 = wbase + (16 * mt + g) * kE + 16 * nh + 8 * nt + 2 * t;
+      w0[0] = g_w[nt][0]; w0[1] = g_w[nt][1];
+      w0[8 * kE] = g_w[nt][2]; w0[8 * kE + 1] = g_w[nt][3];
     }
-    if (lane < 8) part[a.lay.off_b1 + 8 * warp + lane] = g_vec;
-  } else if (warp < 12) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i) * kE + lane] = g_wa[i].x;
-      part[a.lay.off_wo + (8 * (warp - 8) + 2 * i + 1) * kE + lane] = g_wa[i].y;
+    if (nh == 0 && t == 0) {
+      float* bbase = part + (w1part ? a.lay.off_b1 : a.lay.off_bo);
+      bbase[16 * mt + g] = g_b[0];
+      bbase[16 * mt + g + 8] = g_b[2];
     }
-    if (lane < 8) part[a.lay.off_bo + 8 * (warp - 8) + lane] = g_vec;
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) frontend_backward_head_kernel(const FrontArgs a) {
+__global__ void __launch_bounds__(kHeadThreads, 1) frontend_backward_head_kernel(const FrontArgs a) {
   frontend_backward_head_body(a);
 }
-// Register-capped variants of the backward kernels (a few spills): 13 warps of 128 registers fill
-// one scheduler partition's 16 K registers and no warp of another kernel fits beside them; capped,
+// Register-capped variants of the backward kernels (a few spills): 14 warps of 128 registers fill
+// the scheduler partitions' register files and no warp of another kernel fits beside them; capped,
 // the background AdamW sweep (afr_adamw_rows_bg, 4 warps x 40 registers) shares the SM.
 __global__ void __maxnreg__(112) frontend_backward_head_kernel_shared(const FrontArgs a) {
   frontend_backward_head_body(a);
@@ -1517,11 +1558,11 @@ cudaError_t launch_frontend_backward(const Tensors& w, const long long* tokens, 
   const char* only_env = std::getenv("AFR_FE_BWD_ONLY");
   const int only = only_env != nullptr ? std::atoi(only_env) : 0;
   if (shared_sm) {
-    if (only == 0 || only == 1) frontend_backward_head_kernel_shared<<<grid, kThreads, smem_head, stream>>>(a);
+    if (only == 0 || only == 1) frontend_backward_head_kernel_shared<<<grid, kHeadThreads, smem_head, stream>>>(a);
     if (only == 0 || only == 2) frontend_backward_attn_kernel_shared<<<grid_att, kAttThreads, smem_att, stream>>>(a);
     if (only == 0 || only == 3) frontend_backward_tail_kernel_shared<<<grid, kTailThreads, smem_tail, stream>>>(a);
   } else {
-    if (only == 0 || only == 1) frontend_backward_head_kernel<<<grid, kThreads, smem_head, stream>>>(a);
+    if (only == 0 || only == 1) frontend_backward_head_kernel<<<grid, kHeadThreads, smem_head, stream>>>(a);
     if (only == 0 || only == 2) frontend_backward_attn_kernel<<<grid_att, kAttThreads, smem_att, stream>>>(a);
     if (only == 0 || only == 3) frontend_backward_tail_kernel<<<grid, kTailThreads, smem_tail, stream>>>(a);
   }
