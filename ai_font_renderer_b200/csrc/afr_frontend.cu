@@ -8,13 +8,13 @@
 // hold the fp32 tolerance (1e-5 forward / 5e-5 backward against the oracle). Two tools:
 //   * warp-level TF32 MMAs with 3-way split products (ptx::mma_3xtf32: fp32-equivalent; one HMMA
 //     issues per 2.2 clocks per SM, tools/microbench/mma_rates.cu) for every linear layer of the
-//     forward, for the attention backward and for the in-projection part of the backward: a
-//     fragment load replaces eight broadcast LDS and the accumulators of the weight gradients live
-//     in the MMA accumulator layout across all samples of a CTA;
+//     forward and the backward and for the attention backward: a fragment load replaces eight
+//     broadcast LDS and the accumulators of the weight gradients live in the MMA accumulator
+//     layout across all samples of a CTA;
 //   * packed FFMA2 (118 FMA/clk/SM in half the issue slots of FFMA, tools/microbench/
 //     fp32_rates.cu) fed by warp-uniform LDS.128 where the shapes do not pay for fragments: the
 //     forward attention (one thread per (query, head), head-uniform warps, online soft-max over
-//     blocks of 8 keys in the log2 domain, MUFU.EX2) and the head of the backward.
+//     blocks of 8 keys in the log2 domain, MUFU.EX2).
 // A whole sample sits in shared memory per CTA.
 //   * The training forward leaves a record per sample (e, q, k, v, context, normalised residual,
 //     soft-max statistics and every dropout decision as bit masks; FrontStateLayout). The backward
@@ -39,10 +39,6 @@ using ptx::ex2;
 using ptx::fma2;
 using ptx::mul2;
 
-constexpr int kThreads = 416;                                   // head kernel of the backward: 13 warps
-constexpr int kWarps = kThreads / 32;                           // 13
-constexpr int kRowsPerWarp = (kMaxL + kWarps - 1) / kWarps;     // 10
-constexpr int kLdW = kE + 1;                                    // padded weight rows in smem
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kInvSqrtDh = 0.35355339059327373f;              // math.sqrt(1.0 / 8)
@@ -92,21 +88,6 @@ struct FrontArgs {
   FontCond font;                  // optional font conditioning (ids == nullptr: none)
 };
 
-__device__ __forceinline__ float warp_sum(float x) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  return x;
-}
-// two independent butterfly sums at once (the shuffles of one hide the latency of the other)
-__device__ __forceinline__ void warp_sum2(float& x, float& y) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float xo = __shfl_xor_sync(0xffffffffu, x, o);
-    const float yo = __shfl_xor_sync(0xffffffffu, y, o);
-    x += xo;
-    y += yo;
-  }
-}
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
 
@@ -139,11 +120,6 @@ __device__ __forceinline__ void axpy8(float2 (&acc)[4], float w, const float4& r
   acc[1] = fma2(ww, f2(r0.z, r0.w), acc[1]);
   acc[2] = fma2(ww, f2(r1.x, r1.y), acc[2]);
   acc[3] = fma2(ww, f2(r1.z, r1.w), acc[3]);
-}
-
-// weights -> smem, rows padded to kLdW floats
-__device__ __forceinline__ void load_matrix(const float* __restrict__ g, float* sm, int rows) {
-  for (int i = threadIdx.x; i < rows * kE; i += kThreads) sm[(i / kE) * kLdW + (i % kE)] = g[i];
 }
 
 // ============================================================================ forward kernel
@@ -606,7 +582,8 @@ __global__ void __maxnreg__(64) frontend_forward_kernel_shared(const FrontArgs a
 // =========================================================================== backward kernels
 // Three kernels per batch, each a loop over samples with the sample's operands in shared memory:
 //   K1 frontend_backward_head_kernel : fc1 / ReLU / dropout / LayerNorm backward, out-projection
-//      backward (B1, B1b) and dW1, db1, dWo, dbo (B2); hands d(residual), d(ctx) and D to the record
+//      backward (B1, B1b) and dW1, db1, dWo, dbo (B2) on TF32 MMAs; hands d(residual), d(ctx) and D
+//      to the record
 //   K2 frontend_backward_attn_kernel : soft-max attention backward on warp-level TF32 MMAs
 //   K3 frontend_backward_tail_kernel : in-projection backward, dPos, d(embedding) (B4) and dWin,
 //      dbin (B5)
