@@ -28,7 +28,7 @@ def default_state():
 
 
 # ------------------------------------------------------------------------------------ front-end, fp32
-@pytest.mark.parametrize("S", [100, 37])
+@pytest.mark.parametrize("S", [100, 37, 16, 9, 1])
 @pytest.mark.parametrize("use_masks", [False, True])
 def test_default_shape_frontend_fp32_forward_and_backward(default_state, S, use_masks):
     """embedding / attention / LayerNorm / fc1 (model.py:167-193) alone, at the reference's shape
