@@ -231,10 +231,12 @@ int afr_adamw_rows_gather_nvls(afr_ctx* ctx, double lr, double beta1, double bet
                                const void* grad_multicast, void* shadow_multicast, int ctas,
                                void* stream);
 /* afr_adamw_rows as a BACKGROUND kernel: a persistent launch of `ctas` small CTAs (128 threads,
- * <= 40 registers, `stages` x 8 KB of shared memory; 0 = one CTA per SM / 4 stages) that streams
- * p / g / m / v through a bulk-copy ring, so that -- enqueued on its own stream -- it shares every
- * SM with the compute kernels of the step (GEMMs, front-end kernels: registers and shared memory
- * are theirs, the HBM bandwidth is idle) instead of taking the GPU for itself. Bit-identical to
+ * <= 40 registers, `stages` x 8 KB of shared memory; 0 = one CTA per SM / 4 stages; built depths
+ * 2, 3, 4, 6, 8, 12) in which every thread streams its own 16-byte groups of p / g / m / v through
+ * a private slot of a cp.async ring, so that -- enqueued on its own stream -- it shares every SM
+ * with the compute kernels of the step (front-end kernels: registers and shared memory are theirs,
+ * the HBM bandwidth is idle; see afr_set_smem_reserve) instead of taking the GPU for itself.
+ * training.py runs it with 8 stages after the dgrad GEMM. Bit-identical to
  * afr_adamw_rows. grad_rows: the gradient of rows [row_begin,row_end) ([rows, 64*max_length] fp32,
  * e.g. the L2-resident chunk afr_train_wgrad_to has just written), or NULL for the bound
  * fc_output.weight.grad. Replaces optimizer.step() (model.py:310) for those rows. */
